@@ -1,0 +1,395 @@
+"""ctypes binding of libcosnarks_gpu.so (the C ABI declared in include/cosnarks_gpu.h).
+
+This is the Python stand-in for the Rust `extern "C"` shim a co-snarks maintainer would write
+(INTEGRATION.md); tests and bench.py drive the library through it.  There is no CPU fallback: if
+the shared library is missing, `load()` raises, and without a CUDA device `Context()` raises with
+the library's error message.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(_HERE, "libcosnarks_gpu.so")
+
+CS_BN254, CS_BLS12_381 = 0, 1
+CS_G1, CS_G2 = 0, 1
+CS_PLAIN, CS_REP3 = 0, 1
+
+u64p = C.POINTER(C.c_uint64)
+u32p = C.POINTER(C.c_uint32)
+
+
+class CsError(RuntimeError):
+    pass
+
+
+class KeyDesc(C.Structure):
+    _fields_ = [
+        ("curve", C.c_int),
+        ("num_constraints", C.c_size_t), ("num_instance_variables", C.c_size_t), ("num_witness_variables", C.c_size_t),
+        ("a_row_ptr", u32p), ("a_col", u32p), ("a_coeff", u64p), ("a_nnz", C.c_size_t),
+        ("b_row_ptr", u32p), ("b_col", u32p), ("b_coeff", u64p), ("b_nnz", C.c_size_t),
+        ("alpha_g1", u64p), ("beta_g1", u64p), ("beta_g2", u64p), ("delta_g1", u64p), ("delta_g2", u64p),
+        ("a_query", u64p), ("a_query_len", C.c_size_t),
+        ("b_g1_query", u64p), ("b_g1_query_len", C.c_size_t),
+        ("b_g2_query", u64p), ("b_g2_query_len", C.c_size_t),
+        ("l_query", u64p), ("l_query_len", C.c_size_t),
+        ("h_query", u64p), ("h_query_len", C.c_size_t),
+        ("window_bits", C.c_int),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/cosnarks_gpu.h declares
+SIGNATURES = {
+    "cs_last_error": (C.c_char_p, []),
+    "cs_version": (C.c_char_p, []),
+    "cs_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cs_ctx_destroy": (None, [C.c_void_p]),
+    "cs_ctx_synchronize": (C.c_int, [C.c_void_p]),
+    "cs_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
+    "cs_dev_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cs_dev_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cs_host_free_pinned": (C.c_int, [C.c_void_p]),
+    "cs_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_bases_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
+    "cs_bases_free": (None, [C.c_void_p]),
+    "cs_bases_len": (C.c_size_t, [C.c_void_p]),
+    "cs_msm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "cs_msm_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "cs_domain_create": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cs_domain_free": (None, [C.c_void_p]),
+    "cs_domain_size": (C.c_size_t, [C.c_void_p]),
+    "cs_ifft_in_to_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_fft_out_to_in": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_bit_reverse": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_uint]),
+    "cs_ifft_in_to_out_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_fft_out_to_in_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_vec_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_vec_add": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_vec_sub": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_vec_scale_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint]),
+    "cs_rep3_local_mul_vec": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
+    "cs_groth16_pk_free": (None, [C.c_void_p]),
+    "cs_groth16_domain_size": (C.c_size_t, [C.c_void_p]),
+    "cs_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_groth16_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_groth16_rep3_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 11),
+    "cs_point_scalar_mul": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_point_add": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_point_neg": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "cs_fr_to_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_fr_from_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_fq_to_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_fq_from_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_groth16_roots_of_unity": (C.c_int, [C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
+}
+
+_LIBS = {}
+
+
+def load(path=None, strict=True):
+    """Load the shared library and attach signatures.  Raises if it is missing -- build it with
+    `python -c "import __graft_entry__ as g; g.build()"` (nvcc, sm_100a)."""
+    path = os.path.abspath(path or DEFAULT_LIB)
+    if path in _LIBS:
+        return _LIBS[path]
+    if not os.path.exists(path):
+        raise CsError("%s not found: the CUDA extension is not built (no CPU fallback exists)" % path)
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        if not strict and not hasattr(lib, name):
+            continue
+        fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIBS[path] = lib
+    return lib
+
+
+# ------------------------------------------------------------------------------------------ data helpers
+def limbs_of(curve, field):
+    """64-bit limbs of a field element: field in {'fr', 'fq'}."""
+    if field == "fr":
+        return 4
+    return 4 if curve == CS_BN254 else 6
+
+
+def ints_to_limbs(vals, nlimbs):
+    """list of python ints -> np.uint64 array [len, nlimbs], little-endian limbs."""
+    vals = list(vals)
+    raw = b"".join(int(v).to_bytes(8 * nlimbs, "little") for v in vals)
+    return np.frombuffer(raw, dtype=np.uint64).reshape(len(vals), nlimbs).copy()
+
+
+def limbs_to_ints(arr):
+    arr = np.ascontiguousarray(arr, dtype=np.uint64)
+    nl = arr.shape[-1]
+    flat = arr.reshape(-1, nl)
+    raw = flat.tobytes()
+    return [int.from_bytes(raw[i * 8 * nl:(i + 1) * 8 * nl], "little") for i in range(flat.shape[0])]
+
+
+def to_mont_ints(vals, p, nlimbs):
+    R = 1 << (64 * nlimbs)
+    return [int(v) * R % p for v in vals]
+
+
+def from_mont_ints(vals, p, nlimbs):
+    Rinv = pow(1 << (64 * nlimbs), -1, p)
+    return [int(v) * Rinv % p for v in vals]
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(a)  # raw device / host address
+
+
+class Context:
+    """cs_ctx wrapper.  `stream` may be a raw cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.lib = load(lib_path)
+        h = C.c_void_p()
+        self._check(self.lib.cs_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise CsError("cosnarks_gpu error %d: %s" % (rc, self.lib.cs_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cs_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        self._check(self.lib.cs_ctx_synchronize(self.h))
+
+    def launch_count(self):
+        return int(self.lib.cs_ctx_launch_count(self.h))
+
+    # ---- device memory
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        self._check(self.lib.cs_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        self._check(self.lib.cs_dev_free(self.h, C.c_void_p(dptr)))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._check(self.lib.cs_memcpy_h2d(self.h, C.c_void_p(dptr), _ptr(arr), arr.nbytes))
+
+    def d2h(self, dptr, shape, dtype=np.uint64):
+        out = np.empty(shape, dtype=dtype)
+        self._check(self.lib.cs_memcpy_d2h(self.h, _ptr(out), C.c_void_p(dptr), out.nbytes))
+        return out
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        d = self.alloc(arr.nbytes)
+        self.h2d(d, arr)
+        return d
+
+    # ---- MSM
+    def bases_upload(self, curve, group, points_mont, window_bits=0):
+        points_mont = np.ascontiguousarray(points_mont, dtype=np.uint64)
+        h = C.c_void_p()
+        self._check(self.lib.cs_bases_upload(self.h, curve, group, _ptr(points_mont), points_mont.shape[0],
+                                             window_bits, C.byref(h)))
+        return Bases(self, h, curve, group)
+
+    def msm(self, bases, scalars, offset=0, n=None, montgomery=True, device=False):
+        plimbs = limbs_of(bases.curve, "fq") * (2 if bases.group == CS_G1 else 4)
+        out = np.zeros(plimbs, dtype=np.uint64)
+        inf = C.c_int(0)
+        if device:
+            assert n is not None
+            self._check(self.lib.cs_msm_device(self.h, bases.h, offset, C.c_void_p(scalars), n, int(montgomery),
+                                               _ptr(out), C.byref(inf)))
+        else:
+            scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+            if n is None:
+                n = scalars.shape[0]
+            self._check(self.lib.cs_msm(self.h, bases.h, offset, _ptr(scalars) if n else None, n, int(montgomery),
+                                        _ptr(out), C.byref(inf)))
+        return out, bool(inf.value)
+
+    # ---- NTT
+    def domain(self, curve, log_n, group_gen_mont=None):
+        h = C.c_void_p()
+        g = None if group_gen_mont is None else np.ascontiguousarray(group_gen_mont, dtype=np.uint64)
+        self._check(self.lib.cs_domain_create(self.h, curve, log_n, _ptr(g), C.byref(h)))
+        return Domain(self, h, curve, log_n)
+
+    def roots_of_unity(self, curve, power):
+        gen = np.zeros(4, dtype=np.uint64)
+        shift = np.zeros(4, dtype=np.uint64)
+        self._check(self.lib.cs_groth16_roots_of_unity(curve, power, _ptr(gen), _ptr(shift)))
+        return gen, shift
+
+
+class Bases:
+    def __init__(self, ctx, h, curve, group):
+        self.ctx, self.h, self.curve, self.group = ctx, h, curve, group
+
+    def __len__(self):
+        return int(self.ctx.lib.cs_bases_len(self.h))
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.cs_bases_free(self.h)
+            self.h = None
+
+
+class Domain:
+    def __init__(self, ctx, h, curve, log_n):
+        self.ctx, self.h, self.curve, self.log_n = ctx, h, curve, log_n
+
+    def size(self):
+        return int(self.ctx.lib.cs_domain_size(self.h))
+
+    def ifft_in_to_out(self, data, batch=1):
+        """data: np.uint64 host array (transformed in place via the host wrapper) or a raw device address."""
+        if isinstance(data, np.ndarray):
+            self.ctx._check(self.ctx.lib.cs_ifft_in_to_out_host(self.ctx.h, self.h, _ptr(data), batch))
+        else:
+            self.ctx._check(self.ctx.lib.cs_ifft_in_to_out(self.ctx.h, self.h, C.c_void_p(data), batch))
+        return data
+
+    def fft_out_to_in(self, data, batch=1):
+        if isinstance(data, np.ndarray):
+            self.ctx._check(self.ctx.lib.cs_fft_out_to_in_host(self.ctx.h, self.h, _ptr(data), batch))
+        else:
+            self.ctx._check(self.ctx.lib.cs_fft_out_to_in(self.ctx.h, self.h, C.c_void_p(data), batch))
+        return data
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.cs_domain_free(self.h)
+            self.h = None
+
+
+# ------------------------------------------------------------------------------------------ Groth16
+class Groth16Key:
+    """Device-resident proving key + constraint matrices (cs_groth16_pk).
+
+    `arrays` keeps the numpy buffers the descriptor points at alive until the upload is done."""
+
+    def __init__(self, ctx, curve, matrices_csr, points, window_bits=0):
+        """matrices_csr: dict(num_constraints, num_instance_variables, num_witness_variables,
+        a=(row_ptr u32, col u32, coeff u64[nnz,4] Montgomery), b=(...));
+        points: dict of np.uint64 arrays in Montgomery form: alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2,
+        a_query, b_g1_query, b_g2_query, l_query, h_query."""
+        self.ctx, self.curve = ctx, curve
+        d = KeyDesc()
+        d.curve = curve
+        d.num_constraints = matrices_csr["num_constraints"]
+        d.num_instance_variables = matrices_csr["num_instance_variables"]
+        d.num_witness_variables = matrices_csr["num_witness_variables"]
+        keep = []
+        for name in ("a", "b"):
+            rp, col, coeff = matrices_csr[name]
+            rp = np.ascontiguousarray(rp, dtype=np.uint32)
+            col = np.ascontiguousarray(col, dtype=np.uint32)
+            coeff = np.ascontiguousarray(coeff, dtype=np.uint64)
+            keep += [rp, col, coeff]
+            setattr(d, name + "_row_ptr", rp.ctypes.data_as(u32p))
+            setattr(d, name + "_col", col.ctypes.data_as(u32p))
+            setattr(d, name + "_coeff", coeff.ctypes.data_as(u64p))
+            setattr(d, name + "_nnz", col.shape[0])
+        for name in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2"):
+            arr = np.ascontiguousarray(points[name], dtype=np.uint64)
+            keep.append(arr)
+            setattr(d, name, arr.ctypes.data_as(u64p))
+        for name in ("a_query", "b_g1_query", "b_g2_query", "l_query", "h_query"):
+            arr = np.ascontiguousarray(points[name], dtype=np.uint64)
+            keep.append(arr)
+            setattr(d, name, arr.ctypes.data_as(u64p))
+            setattr(d, name + "_len", arr.shape[0])
+        d.window_bits = window_bits
+        h = C.c_void_p()
+        ctx._check(ctx.lib.cs_groth16_pk_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+        self.ni = d.num_instance_variables
+        self.nw = d.num_witness_variables
+        self.fq = limbs_of(curve, "fq")
+        del keep
+
+    def domain_size(self):
+        return int(self.ctx.lib.cs_groth16_domain_size(self.h))
+
+    def witness_map(self, public_inputs, witness, kind=CS_PLAIN, party=0, mask1=None, mask2=None):
+        n = self.domain_size()
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_groth16_witness_map(
+            self.ctx.h, self.h, kind, party, _ptr(np.ascontiguousarray(public_inputs, dtype=np.uint64)),
+            _ptr(np.ascontiguousarray(witness, dtype=np.uint64)), _ptr(mask1), _ptr(mask2), _ptr(out)))
+        return out
+
+    def prove_plain(self, public_inputs, witness, r_mont, s_mont):
+        """-> (A, B, C) affine Montgomery limb arrays."""
+        a = np.zeros(2 * self.fq, dtype=np.uint64)
+        b = np.zeros(4 * self.fq, dtype=np.uint64)
+        c = np.zeros(2 * self.fq, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_groth16_prove_plain(
+            self.ctx.h, self.h, _ptr(public_inputs), _ptr(witness), _ptr(r_mont), _ptr(s_mont),
+            _ptr(a), _ptr(b), _ptr(c)))
+        return a, b, c
+
+    def rep3_local(self, party, public_inputs, witness_shares, mask1, mask2, r_share, s_share):
+        """-> (g_a, g1_b, g2_b, l_acc, h_acc) affine Montgomery half shares."""
+        g1 = lambda: np.zeros(2 * self.fq, dtype=np.uint64)
+        ga, gb1, gb2, l, h = g1(), g1(), np.zeros(4 * self.fq, dtype=np.uint64), g1(), g1()
+        self.ctx._check(self.ctx.lib.cs_groth16_rep3_local(
+            self.ctx.h, self.h, party, _ptr(public_inputs), _ptr(witness_shares), _ptr(mask1), _ptr(mask2),
+            _ptr(r_share), _ptr(s_share), _ptr(ga), _ptr(gb1), _ptr(gb2), _ptr(l), _ptr(h)))
+        return ga, gb1, gb2, l, h
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.cs_groth16_pk_free(self.h)
+            self.h = None
+
+
+# host-side single-point helpers (run on the host inside the library; no context needed)
+def point_scalar_mul(lib, curve, group, p, s_mont):
+    out = np.zeros_like(p)
+    rc = lib.cs_point_scalar_mul(curve, group, _ptr(np.ascontiguousarray(p)), _ptr(np.ascontiguousarray(s_mont)), _ptr(out))
+    if rc:
+        raise CsError(lib.cs_last_error().decode())
+    return out
+
+
+def point_add(lib, curve, group, p, q):
+    out = np.zeros_like(p)
+    rc = lib.cs_point_add(curve, group, _ptr(np.ascontiguousarray(p)), _ptr(np.ascontiguousarray(q)), _ptr(out))
+    if rc:
+        raise CsError(lib.cs_last_error().decode())
+    return out
+
+
+def point_neg(lib, curve, group, p):
+    out = np.zeros_like(p)
+    rc = lib.cs_point_neg(curve, group, _ptr(np.ascontiguousarray(p)), _ptr(out))
+    if rc:
+        raise CsError(lib.cs_last_error().decode())
+    return out

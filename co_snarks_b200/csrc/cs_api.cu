@@ -1,0 +1,631 @@
+// C-ABI entry points: context, device memory, MSM, NTT, vector kernels, host helpers.
+// (Groth16 entry points live in cs_groth16.cu.)  See include/cosnarks_gpu.h for the contract.
+#include <stdarg.h>
+#include "cs_lib.cuh"
+
+namespace cs {
+
+std::string& last_error() {
+  static thread_local std::string e;
+  return e;
+}
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+uint64_t& launch_counter() {
+  static uint64_t c = 0;
+  return c;
+}
+
+int ctx_fork(cs_ctx* ctx, int nside) {
+  CS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
+  for (int i = 0; i < nside; i++) CS_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
+  return 0;
+}
+int ctx_join(cs_ctx* ctx, int nside) {
+  for (int i = 0; i < nside; i++) {
+    CS_CUDA(cudaEventRecord(ctx->ev_side[i], ctx->side[i]));
+    CS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_side[i], 0));
+  }
+  return 0;
+}
+
+template <class FrP>
+static int ntt_smem_optin() {
+#if !defined(CS_EMU)
+  CS_CUDA(cudaFuncSetAttribute(k_ntt_pass<FrP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CS_CUDA(cudaFuncSetAttribute(k_ntt_pass<FrP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+#endif
+  return 0;
+}
+
+}  // namespace cs
+
+using namespace cs;
+
+#if defined(CS_ENABLE_BLS12_381)
+#define CS_CASE_BLS(...)   \
+  case CS_BLS12_381: {     \
+    typedef Bls381Cfg Cfg; \
+    __VA_ARGS__;           \
+  } break;
+#else
+#define CS_CASE_BLS(...)
+#endif
+
+#define CS_DISPATCH_CURVE(curve, ...)                                        \
+  switch ((int)(curve)) {                                                    \
+    case CS_BN254: {                                                         \
+      typedef Bn254Cfg Cfg;                                                  \
+      __VA_ARGS__;                                                           \
+    } break;                                                                 \
+      CS_CASE_BLS(__VA_ARGS__)                                               \
+    default:                                                                 \
+      return fail(CS_ERR_ARG, "unsupported curve id %d", (int)(curve));      \
+  }
+
+extern "C" {
+
+const char* cs_last_error(void) { return last_error().c_str(); }
+
+const char* cs_version(void) {
+#if defined(CS_EMU)
+  return "cosnarks-b200 0.1 (CPU emulation build -- tests only)";
+#else
+  return "cosnarks-b200 0.1 (sm_100a)";
+#endif
+}
+
+int cs_ctx_create(int device, void* stream, cs_ctx** out) {
+  if (!out) return fail(CS_ERR_ARG, "cs_ctx_create: out is NULL");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(CS_ERR_CUDA, "cs_ctx_create: no CUDA device available (%s); this library has no CPU path",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(CS_ERR_ARG, "cs_ctx_create: device %d out of range (%d devices)", device, ndev);
+  CS_CUDA(cudaSetDevice(device));
+  cs_ctx* ctx = new cs_ctx();
+  ctx->device = device;
+  if (stream) {
+    ctx->stream = (cudaStream_t)stream;
+  } else {
+    CS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  for (int i = 0; i < CS_NSIDE; i++) {
+    CS_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+    CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
+  }
+  CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CS_TRY(ntt_smem_optin<Bn254Fr>());
+#if defined(CS_ENABLE_BLS12_381)
+  CS_TRY(ntt_smem_optin<Bls381Fr>());
+#endif
+  *out = ctx;
+  return 0;
+}
+
+void cs_ctx_destroy(cs_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < CS_NSIDE; i++) {
+    ctx->msm_ws[i].release();
+    if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->ev_side[i]) cudaEventDestroy(ctx->ev_side[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  ctx->io.release();
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int cs_ctx_synchronize(cs_ctx* ctx) {
+  if (!ctx) return fail(CS_ERR_ARG, "ctx is NULL");
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+uint64_t cs_ctx_launch_count(const cs_ctx*) { return launch_counter(); }
+
+int cs_dev_alloc(cs_ctx* ctx, size_t bytes, void** d_out) {
+  if (!ctx || !d_out) return fail(CS_ERR_ARG, "cs_dev_alloc: bad argument");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_CUDA(cudaMalloc(d_out, bytes ? bytes : 1));
+  return 0;
+}
+int cs_dev_free(cs_ctx* ctx, void* d_ptr) {
+  if (!ctx) return fail(CS_ERR_ARG, "ctx is NULL");
+  CS_CUDA(cudaFree(d_ptr));
+  return 0;
+}
+int cs_host_alloc_pinned(size_t bytes, void** h_out) {
+  if (!h_out) return fail(CS_ERR_ARG, "h_out is NULL");
+  CS_CUDA(cudaMallocHost(h_out, bytes ? bytes : 1));
+  return 0;
+}
+int cs_host_free_pinned(void* h_ptr) {
+  CS_CUDA(cudaFreeHost(h_ptr));
+  return 0;
+}
+int cs_memcpy_h2d(cs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes) {
+  if (!ctx) return fail(CS_ERR_ARG, "ctx is NULL");
+  CS_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int cs_memcpy_d2h(cs_ctx* ctx, void* h_dst, const void* d_src, size_t bytes) {
+  if (!ctx) return fail(CS_ERR_ARG, "ctx is NULL");
+  CS_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------- MSM
+namespace cs {
+
+template <class Cfg, int G>
+int bases_upload_t(cs_ctx* ctx, const uint64_t* h_points, size_t n, int window_bits, cs_bases* b) {
+  typedef typename GroupOf<Cfg, G>::F F;
+  unsigned c = window_bits ? (unsigned)window_bits : msm_auto_window(n);
+  if (c < 2 || c > 22) return fail(CS_ERR_ARG, "cs_bases_upload: window_bits %u out of range [2,22]", c);
+  b->sh = msm_shape(Cfg::FR_BITS, c);
+  b->n = n;
+  size_t total = (size_t)b->sh.W * n;
+  if (total >= (1ull << 31)) return fail(CS_ERR_LIMIT, "cs_bases_upload: W*n = %zu exceeds 2^31", total);
+  CS_TRY(b->table.reserve(total * sizeof(Affine<F>)));
+  CS_CUDA(cudaMemcpyAsync(b->table.p, h_points, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, ctx->stream));
+  CS_LAUNCH(k_msm_precompute<F>, ceil_div(n, 128), 128, 0, ctx->stream, b->table.as<Affine<F>>(), (uint32_t)n,
+            b->sh.c, b->sh.W);
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+template <class Cfg, int G>
+int msm_enqueue_t(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,
+                  const uint32_t* d_scalars, unsigned sstride, size_t n, int mont) {
+  typedef typename GroupOf<Cfg, G>::F F;
+  return msm_enqueue<F, typename Cfg::FrP>(ctx->msm_ws[slot], b->table.as<Affine<F>>(), (uint32_t)b->n, b->sh,
+                                           (uint32_t)offset, d_scalars, sstride, (uint32_t)n, mont, st);
+}
+
+// After the stream has drained: XYZZ (pinned) -> affine on the host.
+template <class Cfg, int G>
+void msm_finish_t(cs_ctx* ctx, int slot, uint64_t* out_affine, int* out_inf) {
+  typedef typename GroupOf<Cfg, G>::HF HF;
+  const host::HXyzz<HF>* r = reinterpret_cast<const host::HXyzz<HF>*>(ctx->msm_ws[slot].h_result);
+  host::HAffine<HF> a = host::haffine(*r);
+  memcpy(out_affine, &a, sizeof(a));
+  if (out_inf) *out_inf = a.is_inf() ? 1 : 0;
+}
+
+int msm_enqueue_dyn(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,
+                    const uint32_t* d_scalars, unsigned sstride, size_t n, int mont) {
+  CS_DISPATCH_CURVE(b->curve, {
+    if (b->group == CS_G1) return msm_enqueue_t<Cfg, 0>(ctx, slot, st, b, offset, d_scalars, sstride, n, mont);
+    return msm_enqueue_t<Cfg, 1>(ctx, slot, st, b, offset, d_scalars, sstride, n, mont);
+  });
+  return 0;
+}
+int msm_finish_dyn(cs_ctx* ctx, int slot, const cs_bases* b, uint64_t* out_affine, int* out_inf) {
+  CS_DISPATCH_CURVE(b->curve, {
+    if (b->group == CS_G1) msm_finish_t<Cfg, 0>(ctx, slot, out_affine, out_inf);
+    else msm_finish_t<Cfg, 1>(ctx, slot, out_affine, out_inf);
+  });
+  return 0;
+}
+
+}  // namespace cs
+
+extern "C" {
+
+int cs_bases_upload(cs_ctx* ctx, cs_curve curve, cs_group group, const uint64_t* h_points_mont, size_t n,
+                    int window_bits, cs_bases** out) {
+  if (!ctx || !h_points_mont || !out) return fail(CS_ERR_ARG, "cs_bases_upload: NULL argument");
+  if (n == 0) return fail(CS_ERR_ARG, "cs_bases_upload: empty base set");
+  if (group != CS_G1 && group != CS_G2) return fail(CS_ERR_ARG, "cs_bases_upload: bad group %d", (int)group);
+  CS_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<cs_bases> b(new cs_bases());
+  b->curve = curve;
+  b->group = group;
+  CS_DISPATCH_CURVE(curve, {
+    if (group == CS_G1) CS_TRY((bases_upload_t<Cfg, 0>(ctx, h_points_mont, n, window_bits, b.get())));
+    else CS_TRY((bases_upload_t<Cfg, 1>(ctx, h_points_mont, n, window_bits, b.get())));
+  });
+  *out = b.release();
+  return 0;
+}
+
+void cs_bases_free(cs_bases* b) {
+  if (!b) return;
+  b->table.release();
+  delete b;
+}
+
+size_t cs_bases_len(const cs_bases* b) { return b ? b->n : 0; }
+
+int cs_msm_device(cs_ctx* ctx, const cs_bases* b, size_t offset, const uint64_t* d_scalars, size_t n,
+                  int scalars_montgomery, uint64_t* h_out, int* out_inf) {
+  if (!ctx || !b || !h_out) return fail(CS_ERR_ARG, "cs_msm: NULL argument");
+  if (offset + n > b->n) return fail(CS_ERR_ARG, "cs_msm: offset %zu + n %zu exceeds the %zu uploaded bases", offset, n, b->n);
+  size_t plimbs = point_limbs64(b->curve, b->group);
+  if (n == 0) {
+    memset(h_out, 0, plimbs * 8);
+    if (out_inf) *out_inf = 1;
+    return 0;
+  }
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->stream, b, offset, reinterpret_cast<const uint32_t*>(d_scalars), 1, n,
+                         scalars_montgomery));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return msm_finish_dyn(ctx, 0, b, h_out, out_inf);
+}
+
+int cs_msm(cs_ctx* ctx, const cs_bases* b, size_t offset, const uint64_t* h_scalars, size_t n,
+           int scalars_montgomery, uint64_t* h_out, int* out_inf) {
+  if (!ctx || !b || !h_out) return fail(CS_ERR_ARG, "cs_msm: NULL argument");
+  if (n && !h_scalars) return fail(CS_ERR_ARG, "cs_msm: scalars is NULL");
+  if (n == 0) return cs_msm_device(ctx, b, offset, nullptr, 0, scalars_montgomery, h_out, out_inf);
+  CS_CUDA(cudaSetDevice(ctx->device));
+  MsmWorkspace& ws = ctx->msm_ws[0];
+  CS_TRY(ws.scal.reserve(n * 32));
+  CS_CUDA(cudaMemcpyAsync(ws.scal.p, h_scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  return cs_msm_device(ctx, b, offset, ws.scal.as<uint64_t>(), n, scalars_montgomery, h_out, out_inf);
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------- NTT
+namespace cs {
+
+template <class Cfg>
+int domain_create_t(cs_ctx* ctx, unsigned log_n, const uint64_t* gen_mont, cs_domain* d) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HF;
+  if (log_n > Cfg::TWO_ADICITY) return fail(CS_ERR_ARG, "Polynomial Degree too large");  // reduction.rs:87-89
+  HF g;
+  if (gen_mont) {
+    memcpy(g.l, gen_mont, sizeof(g.l));
+  } else {
+    // Domain::new: arkworks' get_root_of_unity(n) = (GENERATOR^TRACE)^(2^(s - log_n)); GENERATOR = 5
+    // (BN254 Fr) / 7 (BLS12-381 Fr).  Computed as GENERATOR^((r-1) >> log_n).
+    uint64_t e[HF::N];
+    for (int i = 0; i < HF::N; i++) e[i] = HF::modl(i);
+    e[0] -= 1;
+    for (unsigned s = 0; s < log_n; s++) {
+      for (int i = 0; i < HF::N; i++) e[i] = (e[i] >> 1) | (i + 1 < HF::N ? (e[i + 1] << 63) : 0);
+    }
+    g = HF::from_u64(std::is_same<Cfg, Bn254Cfg>::value ? 5 : 7).pow(e, HF::N);
+  }
+  // sanity: g^(2^log_n) == 1 and g^(2^(log_n-1)) == -1
+  {
+    HF t = g;
+    for (unsigned s = 0; s + 1 < log_n; s++) t = t.sqr();
+    if (log_n >= 1) {
+      if (t + HF::one() != HF::zero()) return fail(CS_ERR_ARG, "cs_domain_create: group_gen is not a primitive 2^%u-th root of unity", log_n);
+    } else if (g != HF::one()) {
+      return fail(CS_ERR_ARG, "cs_domain_create: group_gen must be 1 for a size-1 domain");
+    }
+  }
+  d->log_n = log_n;
+  d->group_gen.assign(g.l, g.l + HF::N);
+  const size_t n = (size_t)1 << log_n;
+  HF ninv = HF::from_u64(n).inverse();
+  CS_TRY(d->inv_n.reserve(sizeof(HF)));
+  CS_CUDA(cudaMemcpyAsync(d->inv_n.p, ninv.l, sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+  if (log_n >= 1) {
+    const size_t half = n >> 1;
+    HF ginv = g.inverse();
+    std::vector<HF> pw(2 * 32);
+    HF a = g, b = ginv;
+    for (unsigned j = 0; j < 32; j++) {
+      pw[j] = a;
+      pw[32 + j] = b;
+      a = a.sqr();
+      b = b.sqr();
+    }
+    DevBuf dpw;
+    CS_TRY(dpw.reserve(pw.size() * sizeof(HF)));
+    CS_CUDA(cudaMemcpyAsync(dpw.p, pw.data(), pw.size() * sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+    CS_TRY(d->tw_fwd.reserve(half * sizeof(HF)));
+    CS_TRY(d->tw_inv.reserve(half * sizeof(HF)));
+    CS_LAUNCH(k_ntt_twiddles<FrP>, ceil_div(half, 256), 256, 0, ctx->stream, dpw.as<uint32_t>(), (uint32_t)half,
+              d->tw_fwd.as<uint32_t>());
+    CS_LAUNCH(k_ntt_twiddles<FrP>, ceil_div(half, 256), 256, 0, ctx->stream, dpw.as<uint32_t>() + 32 * FrP::N,
+              (uint32_t)half, d->tw_inv.as<uint32_t>());
+    CS_CUDA(cudaGetLastError());
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    dpw.release();
+  } else {
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return 0;
+}
+
+int ntt_run(cs_ctx* ctx, const cs_domain* d, uint32_t* d_data, unsigned batch, bool inverse_in_to_out,
+            const uint32_t* d_post, cudaStream_t st) {
+  if (batch != 1 && batch != 2) return fail(CS_ERR_ARG, "ntt: batch must be 1 or 2");
+  if (d->log_n == 0) return 0;
+  CS_DISPATCH_CURVE(d->curve, {
+    typedef typename Cfg::FrP FrP;
+    if (inverse_in_to_out)
+      return ntt_enqueue<FrP>(d_data, d->tw_inv.as<uint32_t>(), d->log_n, batch, false, d_post,
+                              d_post ? nullptr : d->inv_n.as<uint32_t>(), st);
+    return ntt_enqueue<FrP>(d_data, d->tw_fwd.as<uint32_t>(), d->log_n, batch, true, d_post, nullptr, st);
+  });
+  return 0;
+}
+
+}  // namespace cs
+
+extern "C" {
+
+int cs_domain_create(cs_ctx* ctx, cs_curve curve, unsigned log_n, const uint64_t* group_gen_mont, cs_domain** out) {
+  if (!ctx || !out) return fail(CS_ERR_ARG, "cs_domain_create: NULL argument");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<cs_domain> d(new cs_domain());
+  d->curve = curve;
+  CS_DISPATCH_CURVE(curve, { CS_TRY(domain_create_t<Cfg>(ctx, log_n, group_gen_mont, d.get())); });
+  *out = d.release();
+  return 0;
+}
+
+void cs_domain_free(cs_domain* d) {
+  if (!d) return;
+  d->tw_fwd.release();
+  d->tw_inv.release();
+  d->inv_n.release();
+  delete d;
+}
+
+size_t cs_domain_size(const cs_domain* d) { return d ? ((size_t)1 << d->log_n) : 0; }
+
+int cs_ifft_in_to_out(cs_ctx* ctx, const cs_domain* d, uint64_t* d_data, unsigned batch) {
+  if (!ctx || !d || !d_data) return fail(CS_ERR_ARG, "cs_ifft_in_to_out: NULL argument");
+  return ntt_run(ctx, d, reinterpret_cast<uint32_t*>(d_data), batch, true, nullptr, ctx->stream);
+}
+int cs_fft_out_to_in(cs_ctx* ctx, const cs_domain* d, uint64_t* d_data, unsigned batch) {
+  if (!ctx || !d || !d_data) return fail(CS_ERR_ARG, "cs_fft_out_to_in: NULL argument");
+  return ntt_run(ctx, d, reinterpret_cast<uint32_t*>(d_data), batch, false, nullptr, ctx->stream);
+}
+
+int cs_bit_reverse(cs_ctx* ctx, cs_curve curve, uint64_t* d_data, unsigned log_n, unsigned batch) {
+  if (!ctx || !d_data) return fail(CS_ERR_ARG, "cs_bit_reverse: NULL argument");
+  if (log_n > 31) return fail(CS_ERR_ARG, "cs_bit_reverse: log_n too large");
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_bit_reverse<typename Cfg::FrP>, ceil_div((size_t)1 << log_n, 256), 256, 0, ctx->stream,
+              reinterpret_cast<uint32_t*>(d_data), log_n, batch);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int ntt_host(cs_ctx* ctx, const cs_domain* d, uint64_t* h_data, unsigned batch, bool inv) {
+  if (!ctx || !d || !h_data) return fail(CS_ERR_ARG, "ntt host wrapper: NULL argument");
+  size_t bytes = ((size_t)1 << d->log_n) * batch * 32;
+  CS_TRY(ctx->io.reserve(bytes));
+  CS_CUDA(cudaMemcpyAsync(ctx->io.p, h_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CS_TRY(ntt_run(ctx, d, ctx->io.as<uint32_t>(), batch, inv, nullptr, ctx->stream));
+  CS_CUDA(cudaMemcpyAsync(h_data, ctx->io.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int cs_ifft_in_to_out_host(cs_ctx* ctx, const cs_domain* d, uint64_t* h_data, unsigned batch) {
+  return ntt_host(ctx, d, h_data, batch, true);
+}
+int cs_fft_out_to_in_host(cs_ctx* ctx, const cs_domain* d, uint64_t* h_data, unsigned batch) {
+  return ntt_host(ctx, d, h_data, batch, false);
+}
+
+// ------------------------------------------------------------------------------------------- vec
+static int vec_binop(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n, int op) {
+  if (!ctx || !a || !b || !out) return fail(CS_ERR_ARG, "vec op: NULL argument");
+  if (n == 0) return 0;
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_vec_binop<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, reinterpret_cast<const uint32_t*>(a),
+              reinterpret_cast<const uint32_t*>(b), reinterpret_cast<uint32_t*>(out), n, op);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+int cs_vec_mul(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return vec_binop(ctx, curve, a, b, out, n, VEC_MUL);
+}
+int cs_vec_add(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return vec_binop(ctx, curve, a, b, out, n, VEC_ADD);
+}
+int cs_vec_sub(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+  return vec_binop(ctx, curve, a, b, out, n, VEC_SUB);
+}
+
+int cs_vec_scale_table(cs_ctx* ctx, cs_curve curve, uint64_t* x, const uint64_t* table, size_t n, unsigned batch) {
+  if (!ctx || !x || !table) return fail(CS_ERR_ARG, "cs_vec_scale_table: NULL argument");
+  if (batch != 1 && batch != 2) return fail(CS_ERR_ARG, "cs_vec_scale_table: batch must be 1 or 2");
+  if (n == 0) return 0;
+  unsigned blocks = ceil_div(n * batch, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_vec_scale_table<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, reinterpret_cast<uint32_t*>(x),
+              reinterpret_cast<const uint32_t*>(table), n, batch);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_rep3_local_mul_vec(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const uint64_t* b, const uint64_t* mask,
+                          uint64_t* out, size_t n) {
+  if (!ctx || !a || !b || !out) return fail(CS_ERR_ARG, "cs_rep3_local_mul_vec: NULL argument");
+  if (n == 0) return 0;
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_local_mul<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, reinterpret_cast<const uint32_t*>(a),
+              reinterpret_cast<const uint32_t*>(b), reinterpret_cast<const uint32_t*>(mask),
+              (const uint32_t*)nullptr, reinterpret_cast<uint32_t*>(out), n);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_rep3_to_shamir(cs_ctx* ctx, cs_curve curve, const uint64_t* x, const uint64_t* h_ca, const uint64_t* h_cb,
+                      uint64_t* out, size_t n) {
+  if (!ctx || !x || !h_ca || !h_cb || !out) return fail(CS_ERR_ARG, "cs_rep3_to_shamir: NULL argument");
+  if (n == 0) return 0;
+  CS_TRY(ctx->io.reserve(64));
+  CS_CUDA(cudaMemcpyAsync(ctx->io.p, h_ca, 32, cudaMemcpyHostToDevice, ctx->stream));
+  CS_CUDA(cudaMemcpyAsync((char*)ctx->io.p + 32, h_cb, 32, cudaMemcpyHostToDevice, ctx->stream));
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_to_shamir<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, reinterpret_cast<const uint32_t*>(x),
+              ctx->io.as<uint32_t>(), ctx->io.as<uint32_t>() + 8, reinterpret_cast<uint32_t*>(out), n);
+  });
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));  // io staging is reused by later calls
+  return 0;
+}
+
+// ---------------------------------------------------------------------------- host-side helpers
+}  // extern "C"
+
+namespace cs {
+
+template <class Cfg, int G>
+int point_scalar_mul_t(const uint64_t* p, const uint64_t* s_mont, uint64_t* out) {
+  typedef typename GroupOf<Cfg, G>::HF HF;
+  typedef host::HFp<typename Cfg::FrP> HR;
+  host::HAffine<HF> a;
+  memcpy(&a, p, sizeof(a));
+  HR s;
+  memcpy(s.l, s_mont, sizeof(s.l));
+  HR sc = s.from_mont();
+  host::HAffine<HF> r = host::haffine(host::hmul(host::HXyzz<HF>::from_affine(a), sc.l, HR::N));
+  memcpy(out, &r, sizeof(r));
+  return 0;
+}
+template <class Cfg, int G>
+int point_add_t(const uint64_t* p, const uint64_t* q, uint64_t* out) {
+  typedef typename GroupOf<Cfg, G>::HF HF;
+  host::HAffine<HF> a, b;
+  memcpy(&a, p, sizeof(a));
+  memcpy(&b, q, sizeof(b));
+  host::HAffine<HF> r = host::haffine(host::hadd(host::HXyzz<HF>::from_affine(a), host::HXyzz<HF>::from_affine(b)));
+  memcpy(out, &r, sizeof(r));
+  return 0;
+}
+template <class Cfg, int G>
+int point_neg_t(const uint64_t* p, uint64_t* out) {
+  typedef typename GroupOf<Cfg, G>::HF HF;
+  host::HAffine<HF> a;
+  memcpy(&a, p, sizeof(a));
+  a.y = a.y.neg();
+  memcpy(out, &a, sizeof(a));
+  return 0;
+}
+template <class P>
+int field_conv(const uint64_t* in, uint64_t* out, size_t n, bool to_mont) {
+  typedef host::HFp<P> HF;
+  for (size_t i = 0; i < n; i++) {
+    HF v;
+    memcpy(v.l, in + i * HF::N, sizeof(v.l));
+    HF r = to_mont ? v.to_mont() : v.from_mont();
+    memcpy(out + i * HF::N, r.l, sizeof(r.l));
+  }
+  return 0;
+}
+
+// co-groth16/src/groth16.rs:60-100
+template <class Cfg>
+int roots_of_unity_t(unsigned pow, uint64_t* out_gen, uint64_t* out_shift) {
+  typedef host::HFp<typename Cfg::FrP> HF;
+  if (pow > Cfg::TWO_ADICITY) return fail(CS_ERR_ARG, "Polynomial Degree too large");
+  // smallest quadratic non-residue: q^((r-1)/2) == -1
+  uint64_t half[HF::N], trace[HF::N];
+  for (int i = 0; i < HF::N; i++) half[i] = HF::modl(i);
+  half[0] -= 1;
+  memcpy(trace, half, sizeof(half));
+  for (int i = 0; i < HF::N; i++) half[i] = (half[i] >> 1) | (i + 1 < HF::N ? (half[i + 1] << 63) : 0);
+  for (unsigned s = 0; s < Cfg::TWO_ADICITY; s++)
+    for (int i = 0; i < HF::N; i++) trace[i] = (trace[i] >> 1) | (i + 1 < HF::N ? (trace[i + 1] << 63) : 0);
+  HF minus_one = HF::zero() - HF::one();
+  uint64_t qv = 1;
+  HF q = HF::from_u64(qv);
+  while (q.pow(half, HF::N) != minus_one) q = HF::from_u64(++qv);
+  // roots[k] = z^(2^(s-k)), z = q^TRACE
+  HF z = q.pow(trace, HF::N);
+  HF gen = z, shift;
+  for (unsigned k = 0; k < Cfg::TWO_ADICITY - pow; k++) gen = gen.sqr();  // roots[pow]
+  if (pow == Cfg::TWO_ADICITY) {
+    shift = q.sqr();
+  } else {
+    shift = z;
+    for (unsigned k = 0; k < Cfg::TWO_ADICITY - pow - 1; k++) shift = shift.sqr();  // roots[pow + 1]
+  }
+  memcpy(out_gen, gen.l, sizeof(gen.l));
+  memcpy(out_shift, shift.l, sizeof(shift.l));
+  return 0;
+}
+
+}  // namespace cs
+
+extern "C" {
+
+int cs_point_scalar_mul(cs_curve curve, cs_group group, const uint64_t* p, const uint64_t* s, uint64_t* out) {
+  if (!p || !s || !out) return fail(CS_ERR_ARG, "cs_point_scalar_mul: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    if (group == CS_G1) return point_scalar_mul_t<Cfg, 0>(p, s, out);
+    return point_scalar_mul_t<Cfg, 1>(p, s, out);
+  });
+  return 0;
+}
+int cs_point_add(cs_curve curve, cs_group group, const uint64_t* p, const uint64_t* q, uint64_t* out) {
+  if (!p || !q || !out) return fail(CS_ERR_ARG, "cs_point_add: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    if (group == CS_G1) return point_add_t<Cfg, 0>(p, q, out);
+    return point_add_t<Cfg, 1>(p, q, out);
+  });
+  return 0;
+}
+int cs_point_neg(cs_curve curve, cs_group group, const uint64_t* p, uint64_t* out) {
+  if (!p || !out) return fail(CS_ERR_ARG, "cs_point_neg: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    if (group == CS_G1) return point_neg_t<Cfg, 0>(p, out);
+    return point_neg_t<Cfg, 1>(p, out);
+  });
+  return 0;
+}
+int cs_fr_to_mont(cs_curve curve, const uint64_t* in, uint64_t* out, size_t n) {
+  CS_DISPATCH_CURVE(curve, { return field_conv<typename Cfg::FrP>(in, out, n, true); });
+  return 0;
+}
+int cs_fr_from_mont(cs_curve curve, const uint64_t* in, uint64_t* out, size_t n) {
+  CS_DISPATCH_CURVE(curve, { return field_conv<typename Cfg::FrP>(in, out, n, false); });
+  return 0;
+}
+int cs_fq_to_mont(cs_curve curve, const uint64_t* in, uint64_t* out, size_t n) {
+  CS_DISPATCH_CURVE(curve, { return field_conv<typename Cfg::FqP>(in, out, n, true); });
+  return 0;
+}
+int cs_fq_from_mont(cs_curve curve, const uint64_t* in, uint64_t* out, size_t n) {
+  CS_DISPATCH_CURVE(curve, { return field_conv<typename Cfg::FqP>(in, out, n, false); });
+  return 0;
+}
+int cs_groth16_roots_of_unity(cs_curve curve, unsigned pow, uint64_t* out_gen, uint64_t* out_shift) {
+  if (!out_gen || !out_shift) return fail(CS_ERR_ARG, "cs_groth16_roots_of_unity: NULL argument");
+  CS_DISPATCH_CURVE(curve, { return roots_of_unity_t<Cfg>(pow, out_gen, out_shift); });
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// Prime-field arithmetic in Montgomery form on 32-bit limbs (device side).
+//
+// Replaces the arkworks `Fp<MontBackend<_, N>>` arithmetic that every reference function on the
+// hot path bottoms out in (field elements are `[u64; N]` little-endian Montgomery limbs with
+// R = 2^(64 N); a `[u64; N]` is bit-identical to our `uint32_t[2 N]`, so buffers cross the C ABI
+// without conversion).  SURVEY.md 8(a): "F_r element = 32 B ... Montgomery form, R = 2^256".
+//
+// mul(): word-serial Montgomery product with the even/odd accumulator split, so every
+// 32x32->64 partial product is one IMAD.WIDE in a single carry chain (no carry-save fix-ups).
+// All results are fully reduced to [0, p), which the exact equality tests in the point formulas need.
+#pragma once
+#include "cs_prims.cuh"
+
+namespace cs {
+
+// ---- generic N-limb helpers ---------------------------------------------------------------------
+template <int N>
+CS_D void mul_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+  CS_UNROLL
+  for (int j = 0; j < N; j += 2) {
+    acc[j] = mul_lo(a[j], bi);
+    acc[j + 1] = mul_hi(a[j], bi);
+  }
+}
+
+// acc[0..N) += (a[0], a[2], ...) * bi   (pairs (lo,hi) land on (j, j+1)); carry-out stays in CC.
+template <int N>
+CS_D void cmad_n(uint32_t* acc, const uint32_t* a, uint32_t bi) {
+  acc[0] = mad_lo_cc(a[0], bi, acc[0]);
+  acc[1] = madc_hi_cc(a[0], bi, acc[1]);
+  CS_UNROLL
+  for (int j = 2; j < N; j += 2) {
+    acc[j] = madc_lo_cc(a[j], bi, acc[j]);
+    acc[j + 1] = madc_hi_cc(a[j], bi, acc[j + 1]);
+  }
+}
+
+// odd = (odd >> 64) + (a[0], a[2], ...) * bi + CC      (no carry-out possible)
+template <int N>
+CS_D void madc_n_rshift(uint32_t* odd, const uint32_t* a, uint32_t bi) {
+  CS_UNROLL
+  for (int j = 0; j < N - 2; j += 2) {
+    odd[j] = madc_lo_cc(a[j], bi, odd[j + 2]);
+    odd[j + 1] = madc_hi_cc(a[j], bi, odd[j + 3]);
+  }
+  odd[N - 2] = madc_lo_cc(a[N - 2], bi, 0);
+  odd[N - 1] = madc_hi(a[N - 2], bi, 0);
+}
+
+// One row of the interleaved Montgomery product.  X is the accumulator aligned with bit 0 of the
+// running value T, Y the one aligned 32 bits up (T = X + Y * 2^32); the roles swap every row.
+template <class P, bool FIRST>
+CS_D void mad_n_redc(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+  constexpr int N = P::N;
+  if (FIRST) {
+    mul_n<N>(Y, a + 1, bi);
+    mul_n<N>(X, a, bi);
+  } else {
+    X[0] = add_cc(X[0], Y[1]);
+    madc_n_rshift<N>(Y, a + 1, bi);
+    cmad_n<N>(X, a, bi);
+    Y[N - 1] = addc(Y[N - 1], 0);
+  }
+  uint32_t mi = mul_lo(X[0], P::M0);
+  uint32_t mod[N];
+  CS_UNROLL
+  for (int i = 0; i < N; i++) mod[i] = P::mod(i);
+  cmad_n<N>(Y, mod + 1, mi);
+  cmad_n<N>(X, mod, mi);
+  Y[N - 1] = addc(Y[N - 1], 0);
+}
+
+template <class P>
+struct Fp {
+  static constexpr int N = P::N;
+  uint32_t l[N];
+
+  // ---- constants
+  static CS_D Fp zero() { Fp r; CS_UNROLL for (int i = 0; i < N; i++) r.l[i] = 0; return r; }
+  static CS_D Fp one() { Fp r; CS_UNROLL for (int i = 0; i < N; i++) r.l[i] = P::one(i); return r; }
+  static CS_D Fp r2() { Fp r; CS_UNROLL for (int i = 0; i < N; i++) r.l[i] = P::r2(i); return r; }
+
+  CS_D bool is_zero() const {
+    uint32_t o = 0;
+    CS_UNROLL
+    for (int i = 0; i < N; i++) o |= l[i];
+    return o == 0;
+  }
+  CS_D bool operator==(const Fp& b) const {
+    uint32_t o = 0;
+    CS_UNROLL
+    for (int i = 0; i < N; i++) o |= l[i] ^ b.l[i];
+    return o == 0;
+  }
+  CS_D bool operator!=(const Fp& b) const { return !(*this == b); }
+
+  // r = (r >= p) ? r - p : r
+  CS_D void final_sub() {
+    uint32_t t[N];
+    t[0] = sub_cc(l[0], P::mod(0));
+    CS_UNROLL
+    for (int i = 1; i < N; i++) t[i] = subc_cc(l[i], P::mod(i));
+    uint32_t borrow = subc(0, 0);  // 0xffffffff if l < p
+    CS_UNROLL
+    for (int i = 0; i < N; i++) l[i] = borrow ? l[i] : t[i];
+  }
+
+  friend CS_D Fp operator+(const Fp& a, const Fp& b) {
+    Fp r;
+    r.l[0] = add_cc(a.l[0], b.l[0]);
+    CS_UNROLL
+    for (int i = 1; i < N; i++) r.l[i] = addc_cc(a.l[i], b.l[i]);
+    // p has at least one spare top bit (254/255/381-bit moduli), so no carry-out here
+    r.final_sub();
+    return r;
+  }
+  friend CS_D Fp operator-(const Fp& a, const Fp& b) {
+    Fp r;
+    r.l[0] = sub_cc(a.l[0], b.l[0]);
+    CS_UNROLL
+    for (int i = 1; i < N; i++) r.l[i] = subc_cc(a.l[i], b.l[i]);
+    uint32_t borrow = subc(0, 0);
+    r.l[0] = add_cc(r.l[0], borrow & P::mod(0));
+    CS_UNROLL
+    for (int i = 1; i < N; i++) r.l[i] = addc_cc(r.l[i], borrow & P::mod(i));
+    return r;
+  }
+  CS_D Fp neg() const { return is_zero() ? *this : (zero() - *this); }
+  CS_D Fp dbl() const { return *this + *this; }
+
+  friend CS_D Fp operator*(const Fp& a, const Fp& b) {
+    uint32_t even[N], odd[N];
+    mad_n_redc<P, true>(even, odd, a.l, b.l[0]);
+    mad_n_redc<P, false>(odd, even, a.l, b.l[1]);
+    CS_UNROLL
+    for (int i = 2; i < N; i += 2) {
+      mad_n_redc<P, false>(even, odd, a.l, b.l[i]);
+      mad_n_redc<P, false>(odd, even, a.l, b.l[i + 1]);
+    }
+    // result = even + (odd >> 32)
+    Fp r;
+    r.l[0] = add_cc(even[0], odd[1]);
+    CS_UNROLL
+    for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(even[i], odd[i + 1]);
+    r.l[N - 1] = addc(even[N - 1], 0);
+    r.final_sub();
+    return r;
+  }
+  CS_D Fp sqr() const { return (*this) * (*this); }
+
+  // Montgomery <-> canonical
+  CS_D Fp to_mont() const { return (*this) * r2(); }
+  CS_D Fp from_mont() const {
+    Fp o = zero();
+    o.l[0] = 1;
+    return (*this) * o;
+  }
+
+  // a^(p-2); only used off the per-proof path (table precomputation)
+  CS_D Fp inverse() const {
+    Fp res = one();
+    Fp base = *this;
+    for (int i = 0; i < N; i++) {
+      uint32_t e = P::mod(i);
+      if (i == 0) e -= 2;  // all supported moduli have mod[0] >= 2 (they are odd and > 2)
+      for (int b = 0; b < 32; b++) {
+        if ((e >> b) & 1) res = res * base;
+        base = base.sqr();
+      }
+    }
+    return res;
+  }
+};
+
+}  // namespace cs

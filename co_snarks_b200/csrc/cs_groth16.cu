@@ -1,0 +1,378 @@
+// Groth16 prover hot path: device-resident proving key, CircomReduction witness map, the five MSMs
+// and the proof assembly.
+//
+// Mirrors co-circom/co-groth16/src/groth16.rs:125-338 (prove_inner, calculate_coeff,
+// create_proof_with_assignment) and groth16/reduction.rs:77-193 (CircomReduction) for the Plain and
+// Rep3 drivers (mpc/plain.rs, mpc/rep3.rs).  Everything between the witness upload and the five MSM
+// results stays in HBM; only points come back.  Single-point work (scalar_mul_public_point_hs,
+// add_assign_points_public_hs, the public-input MSM over query[1..=pub], the final sums) runs on
+// the host while the GPU works -- it is latency-only in the reference too.
+#include "cs_lib.cuh"
+
+using namespace cs;
+
+struct cs_groth16_pk {
+  int curve = 0;
+  size_t nc = 0, ni = 0, nw = 0, n = 0;
+  unsigned log_n = 0;
+  DevBuf a_rowptr, a_col, a_coeff, b_rowptr, b_col, b_coeff;
+  cs_bases *a_query = nullptr, *b_g1 = nullptr, *b_g2 = nullptr, *l_query = nullptr, *h_query = nullptr;
+  std::vector<uint64_t> alpha_g1, beta_g1, beta_g2, delta_g1, delta_g2;
+  std::vector<uint64_t> a_head, b1_head, b2_head;  // query[0..ni] host copies
+  cs_domain* dom = nullptr;
+  DevBuf coset_tab;  // shift^bitrev(p) / n
+  DevBuf d_pub, d_wit, d_a, d_b, d_c, d_m1, d_m2, d_pubscal;
+};
+
+namespace {
+
+// ---- host-side point helpers on raw limb buffers (Montgomery affine) --------------------------
+template <class Cfg, int G>
+struct HostGroup {
+  typedef typename GroupOf<Cfg, G>::HF HF;
+  typedef host::HXyzz<HF> X;
+  typedef host::HAffine<HF> A;
+  typedef host::HFp<typename Cfg::FrP> HR;
+  static X load(const uint64_t* p) {
+    A a;
+    memcpy(&a, p, sizeof(a));
+    return X::from_affine(a);
+  }
+  static void store(uint64_t* out, const X& x) {
+    A a = host::haffine(x);
+    memcpy(out, &a, sizeof(a));
+  }
+  // scalar in Montgomery form
+  static X mul(const X& p, const uint64_t* s_mont) {
+    HR s;
+    memcpy(s.l, s_mont, sizeof(s.l));
+    HR c = s.from_mont();
+    return host::hmul(p, c.l, HR::N);
+  }
+};
+
+template <class Cfg>
+int build_coset_table(cs_ctx* ctx, cs_groth16_pk* pk) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HF;
+  uint64_t gen[HF::N], shift[HF::N];
+  CS_TRY(cs_groth16_roots_of_unity((cs_curve)pk->curve, pk->log_n, gen, shift));
+  CS_TRY(cs_domain_create(ctx, (cs_curve)pk->curve, pk->log_n, gen, &pk->dom));
+  if (pk->log_n == 0) return 0;
+  HF s;
+  memcpy(s.l, shift, sizeof(s.l));
+  std::vector<HF> pw(33);
+  for (int j = 0; j < 32; j++) {
+    pw[j] = s;
+    s = s.sqr();
+  }
+  pw[32] = HF::from_u64(pk->n).inverse();  // scale = 1/n
+  DevBuf dpw;
+  CS_TRY(dpw.reserve(pw.size() * sizeof(HF)));
+  CS_CUDA(cudaMemcpyAsync(dpw.p, pw.data(), pw.size() * sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+  CS_TRY(pk->coset_tab.reserve(pk->n * sizeof(HF)));
+  CS_LAUNCH(k_ntt_coset_table<FrP>, ceil_div(pk->n, 256), 256, 0, ctx->stream, dpw.as<uint32_t>(),
+            dpw.as<uint32_t>() + 32 * FrP::N, pk->log_n, pk->coset_tab.as<uint32_t>());
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  dpw.release();
+  return 0;
+}
+
+int upload(cs_ctx* ctx, DevBuf& buf, const void* src, size_t bytes) {
+  CS_TRY(buf.reserve(bytes ? bytes : 4));
+  if (bytes) CS_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+// CircomReduction::witness_map_from_matrices on the device.  Leaves h (n half shares) in pk->d_c.
+// d_pub / d_wit must already hold the inputs; masks (Rep3) in d_m1 / d_m2 or null.
+template <class Cfg>
+int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, bool have_m1, bool have_m2,
+                       cudaStream_t st) {
+  typedef typename Cfg::FrP FrP;
+  const unsigned batch = kind == CS_REP3 ? 2 : 1;
+  const int pub_comp = kind == CS_REP3 ? (party == 0 ? 0 : (party == 1 ? 1 : -1)) : 0;
+  const uint32_t n = (uint32_t)pk->n;
+  CS_TRY(pk->d_a.reserve((size_t)n * batch * 32));
+  CS_TRY(pk->d_b.reserve((size_t)n * batch * 32));
+  CS_TRY(pk->d_c.reserve((size_t)n * 32));
+  // a = A w (+ promoted public rows, reduction.rs:104-113), b = B w   (evaluate_constraint)
+  CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->a_rowptr.as<uint32_t>(), pk->a_col.as<uint32_t>(),
+            pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, pk->d_wit.as<uint32_t>(), batch,
+            pub_comp, (uint32_t)pk->nc, (uint32_t)pk->ni, n, pk->d_a.as<uint32_t>());
+  CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->b_rowptr.as<uint32_t>(), pk->b_col.as<uint32_t>(),
+            pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, pk->d_wit.as<uint32_t>(), batch,
+            pub_comp, (uint32_t)pk->nc, 0u, n, pk->d_b.as<uint32_t>());
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  // c = local_mul_vec(a, b)   (reduction.rs:160)
+  if (kind == CS_REP3)
+    CS_LAUNCH(k_rep3_local_mul<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
+              have_m1 ? pk->d_m1.as<uint32_t>() : (const uint32_t*)nullptr, (const uint32_t*)nullptr,
+              pk->d_c.as<uint32_t>(), (size_t)n);
+  else
+    CS_LAUNCH(k_plain_mul_sub<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
+              (const uint32_t*)nullptr, pk->d_c.as<uint32_t>(), (size_t)n);
+  // each of a, b, c: ifft_in_to_out -> * coset table -> fft_out_to_in   (reduction.rs:135-178);
+  // the table multiply and the 1/n are fused into the last iNTT pass.
+  const uint32_t* post = pk->log_n ? pk->coset_tab.as<uint32_t>() : nullptr;
+  CS_TRY(ntt_run(ctx, pk->dom, pk->d_a.as<uint32_t>(), batch, true, post, st));
+  CS_TRY(ntt_run(ctx, pk->dom, pk->d_a.as<uint32_t>(), batch, false, nullptr, st));
+  CS_TRY(ntt_run(ctx, pk->dom, pk->d_b.as<uint32_t>(), batch, true, post, st));
+  CS_TRY(ntt_run(ctx, pk->dom, pk->d_b.as<uint32_t>(), batch, false, nullptr, st));
+  CS_TRY(ntt_run(ctx, pk->dom, pk->d_c.as<uint32_t>(), 1, true, post, st));
+  CS_TRY(ntt_run(ctx, pk->dom, pk->d_c.as<uint32_t>(), 1, false, nullptr, st));
+  // h = local_mul_vec(a', b') - c'   (reduction.rs:182-190), in place over c
+  if (kind == CS_REP3)
+    CS_LAUNCH(k_rep3_local_mul<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
+              have_m2 ? pk->d_m2.as<uint32_t>() : (const uint32_t*)nullptr, pk->d_c.as<uint32_t>(),
+              pk->d_c.as<uint32_t>(), (size_t)n);
+  else
+    CS_LAUNCH(k_plain_mul_sub<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
+              pk->d_c.as<uint32_t>(), pk->d_c.as<uint32_t>(), (size_t)n);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int upload_inputs(cs_ctx* ctx, cs_groth16_pk* pk, int kind, const uint64_t* h_pub, const uint64_t* h_wit,
+                  const uint64_t* h_m1, const uint64_t* h_m2) {
+  const unsigned batch = kind == CS_REP3 ? 2 : 1;
+  CS_TRY(upload(ctx, pk->d_pub, h_pub, pk->ni * 32));
+  CS_TRY(upload(ctx, pk->d_wit, h_wit, pk->nw * batch * 32));
+  if (kind == CS_REP3 && h_m1) CS_TRY(upload(ctx, pk->d_m1, h_m1, pk->n * 32));
+  if (kind == CS_REP3 && h_m2) CS_TRY(upload(ctx, pk->d_m2, h_m2, pk->n * 32));
+  return 0;
+}
+
+// The local, GPU-heavy part shared by plain_prove and the Rep3 party: witness map + five MSMs.
+// r_hs / s_hs: half shares (Montgomery Fr) of r and s.  add_public: plain driver or Rep3 party 0
+// (add_assign_points_public_hs, mpc/rep3.rs:108-118).  Outputs are affine Montgomery points.
+template <class Cfg>
+int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint64_t* h_pub, const uint64_t* h_wit,
+                const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
+                uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h) {
+  typedef HostGroup<Cfg, 0> H1;
+  typedef HostGroup<Cfg, 1> H2;
+  const unsigned batch = kind == CS_REP3 ? 2 : 1;
+  const bool add_public = (kind == CS_PLAIN) || party == 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, h_m1, h_m2));
+  // fork: A, B1, B2, L need only the witness; the witness map + H run on the main stream.
+  CS_TRY(ctx_fork(ctx, 4));
+  const uint32_t* wit = pk->d_wit.as<uint32_t>();
+  const bool have_aux = pk->nw > 0;
+  if (have_aux) {
+    // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
+    CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
+    CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
+    CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1));
+    CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
+  }
+  CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+  CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
+  CS_TRY(ctx_join(ctx, 4));
+
+  // ---- host work overlapped with the GPU: scalar_mul_public_point_hs + public parts (groth16.rs:232-276)
+  typename H1::X a_acc = H1::mul(H1::load(pk->delta_g1.data()), r_hs);
+  typename H1::X b1_acc = H1::mul(H1::load(pk->delta_g1.data()), s_hs);
+  typename H2::X b2_acc = H2::mul(H2::load(pk->delta_g2.data()), s_hs);
+  if (add_public) {
+    const size_t g1l = 2 * H1::HF::N, g2l = 4 * H1::HF::N;
+    a_acc = host::hadd(a_acc, H1::load(pk->a_head.data()));
+    a_acc = host::hadd(a_acc, H1::load(pk->alpha_g1.data()));
+    b1_acc = host::hadd(b1_acc, H1::load(pk->b1_head.data()));
+    b1_acc = host::hadd(b1_acc, H1::load(pk->beta_g1.data()));
+    b2_acc = host::hadd(b2_acc, H2::load(pk->b2_head.data()));
+    b2_acc = host::hadd(b2_acc, H2::load(pk->beta_g2.data()));
+    // msm_unchecked(&query[1..=pub_len], input_assignment) with input_assignment = public_inputs[1..]
+    for (size_t k = 1; k < pk->ni; k++) {
+      const uint64_t* sc = h_pub + k * 4;
+      a_acc = host::hadd(a_acc, H1::mul(H1::load(pk->a_head.data() + k * g1l), sc));
+      b1_acc = host::hadd(b1_acc, H1::mul(H1::load(pk->b1_head.data() + k * g1l), sc));
+      b2_acc = host::hadd(b2_acc, H2::mul(H2::load(pk->b2_head.data() + k * g2l), sc));
+    }
+  }
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  uint64_t tmp[24];
+  int inf = 0;
+  if (have_aux) {
+    CS_TRY(msm_finish_dyn(ctx, 0, pk->a_query, tmp, &inf));
+    a_acc = host::hadd(a_acc, H1::load(tmp));
+    CS_TRY(msm_finish_dyn(ctx, 1, pk->b_g1, tmp, &inf));
+    b1_acc = host::hadd(b1_acc, H1::load(tmp));
+    CS_TRY(msm_finish_dyn(ctx, 2, pk->b_g2, tmp, &inf));
+    b2_acc = host::hadd(b2_acc, H2::load(tmp));
+    CS_TRY(msm_finish_dyn(ctx, 3, pk->l_query, out_l, &inf));
+  } else {
+    memset(out_l, 0, 2 * H1::HF::N * 8);
+  }
+  CS_TRY(msm_finish_dyn(ctx, 4, pk->h_query, out_h, &inf));
+  H1::store(out_a, a_acc);
+  H1::store(out_b1, b1_acc);
+  H2::store(out_b2, b2_acc);
+  return 0;
+}
+
+template <class Cfg>
+int prove_plain_t(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* r,
+                  const uint64_t* s, uint64_t* out_a, uint64_t* out_b, uint64_t* out_c) {
+  typedef HostGroup<Cfg, 0> H1;
+  typedef host::HFp<typename Cfg::FrP> HR;
+  uint64_t a[12], b1[12], l[12], h[12];
+  CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, nullptr, nullptr, r, s, a, b1, out_b, l, h)));
+  // groth16.rs:296-322 with the plain driver: C = s*A + r*B1 - (r s)*delta1 + L + H
+  HR rr, ss;
+  memcpy(rr.l, r, sizeof(rr.l));
+  memcpy(ss.l, s, sizeof(ss.l));
+  HR rs = rr * ss;
+  typename H1::X A = H1::load(a);
+  typename H1::X c = H1::mul(A, s);
+  c = host::hadd(c, H1::mul(H1::load(b1), r));
+  c = host::hadd(c, host::hneg(H1::mul(H1::load(pk->delta_g1.data()), rs.l)));
+  c = host::hadd(c, H1::load(l));
+  c = host::hadd(c, H1::load(h));
+  memcpy(out_a, a, 2 * H1::HF::N * 8);
+  H1::store(out_c, c);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* d, cs_groth16_pk** out) {
+  if (!ctx || !d || !out) return fail(CS_ERR_ARG, "cs_groth16_pk_create: NULL argument");
+  if (d->curve != CS_BN254
+#if defined(CS_ENABLE_BLS12_381)
+      && d->curve != CS_BLS12_381
+#endif
+  )
+    return fail(CS_ERR_ARG, "cs_groth16_pk_create: unsupported curve %d", (int)d->curve);
+  const size_t nc = d->num_constraints, ni = d->num_instance_variables, nw = d->num_witness_variables;
+  if (ni == 0) return fail(CS_ERR_ARG, "cs_groth16_pk_create: num_instance_variables must be >= 1");
+  // lengths the prover indexes (groth16.rs:190-200, 283, 290)
+  if (d->a_query_len != ni + nw || d->b_g1_query_len != ni + nw || d->b_g2_query_len != ni + nw)
+    return fail(CS_ERR_ARG, "cs_groth16_pk_create: a/b query length must be %zu", ni + nw);
+  if (d->l_query_len != nw) return fail(CS_ERR_ARG, "cs_groth16_pk_create: l_query length must be %zu", nw);
+  CS_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<cs_groth16_pk> pk(new cs_groth16_pk());
+  pk->curve = d->curve;
+  pk->nc = nc; pk->ni = ni; pk->nw = nw;
+  size_t n = 1;
+  unsigned lg = 0;
+  while (n < nc + ni) { n <<= 1; lg++; }  // next_power_of_two (reduction.rs:85)
+  pk->n = n;
+  pk->log_n = lg;
+  if (d->h_query_len < n) return fail(CS_ERR_ARG, "cs_groth16_pk_create: h_query has %zu points, domain needs %zu", d->h_query_len, n);
+  const unsigned max_adicity = d->curve == CS_BN254 ? 28 : 32;
+  if (lg > max_adicity) return fail(CS_ERR_ARG, "Polynomial Degree too large");  // reduction.rs:87-89
+  const size_t fq = fq_limbs64(d->curve), g1b = 2 * fq * 8, g2b = 4 * fq * 8;
+  CS_TRY(upload(ctx, pk->a_rowptr, d->a_row_ptr, (nc + 1) * 4));
+  CS_TRY(upload(ctx, pk->a_col, d->a_col, d->a_nnz * 4));
+  CS_TRY(upload(ctx, pk->a_coeff, d->a_coeff, d->a_nnz * 32));
+  CS_TRY(upload(ctx, pk->b_rowptr, d->b_row_ptr, (nc + 1) * 4));
+  CS_TRY(upload(ctx, pk->b_col, d->b_col, d->b_nnz * 4));
+  CS_TRY(upload(ctx, pk->b_coeff, d->b_coeff, d->b_nnz * 32));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  pk->alpha_g1.assign(d->alpha_g1, d->alpha_g1 + 2 * fq);
+  pk->beta_g1.assign(d->beta_g1, d->beta_g1 + 2 * fq);
+  pk->beta_g2.assign(d->beta_g2, d->beta_g2 + 4 * fq);
+  pk->delta_g1.assign(d->delta_g1, d->delta_g1 + 2 * fq);
+  pk->delta_g2.assign(d->delta_g2, d->delta_g2 + 4 * fq);
+  pk->a_head.assign(d->a_query, d->a_query + ni * 2 * fq);
+  pk->b1_head.assign(d->b_g1_query, d->b_g1_query + ni * 2 * fq);
+  pk->b2_head.assign(d->b_g2_query, d->b_g2_query + ni * 4 * fq);
+  (void)g1b; (void)g2b;
+  const int wb = d->window_bits;
+  CS_TRY(cs_bases_upload(ctx, d->curve, CS_G1, d->a_query, d->a_query_len, wb, &pk->a_query));
+  CS_TRY(cs_bases_upload(ctx, d->curve, CS_G1, d->b_g1_query, d->b_g1_query_len, wb, &pk->b_g1));
+  CS_TRY(cs_bases_upload(ctx, d->curve, CS_G2, d->b_g2_query, d->b_g2_query_len, wb, &pk->b_g2));
+  if (nw) CS_TRY(cs_bases_upload(ctx, d->curve, CS_G1, d->l_query, d->l_query_len, wb, &pk->l_query));
+  CS_TRY(cs_bases_upload(ctx, d->curve, CS_G1, d->h_query, n, wb, &pk->h_query));
+  switch (d->curve) {
+    case CS_BN254: CS_TRY(build_coset_table<Bn254Cfg>(ctx, pk.get())); break;
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: CS_TRY(build_coset_table<Bls381Cfg>(ctx, pk.get())); break;
+#endif
+    default: break;
+  }
+  *out = pk.release();
+  return 0;
+}
+
+void cs_groth16_pk_free(cs_groth16_pk* pk) {
+  if (!pk) return;
+  DevBuf* bufs[] = {&pk->a_rowptr, &pk->a_col, &pk->a_coeff, &pk->b_rowptr, &pk->b_col, &pk->b_coeff, &pk->coset_tab,
+                    &pk->d_pub, &pk->d_wit, &pk->d_a, &pk->d_b, &pk->d_c, &pk->d_m1, &pk->d_m2, &pk->d_pubscal};
+  for (DevBuf* b : bufs) b->release();
+  cs_bases_free(pk->a_query);
+  cs_bases_free(pk->b_g1);
+  cs_bases_free(pk->b_g2);
+  cs_bases_free(pk->l_query);
+  cs_bases_free(pk->h_query);
+  cs_domain_free(pk->dom);
+  delete pk;
+}
+
+size_t cs_groth16_domain_size(const cs_groth16_pk* pk) { return pk ? pk->n : 0; }
+
+int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party, const uint64_t* h_pub,
+                           const uint64_t* h_wit, const uint64_t* h_m1, const uint64_t* h_m2, uint64_t* h_out) {
+  if (!ctx || !pk || !h_pub || (pk->nw && !h_wit)) return fail(CS_ERR_ARG, "cs_groth16_witness_map: NULL argument");
+  if (kind != CS_PLAIN && kind != CS_REP3) return fail(CS_ERR_ARG, "cs_groth16_witness_map: bad share kind");
+  if (kind == CS_REP3 && (party < 0 || party > 2)) return fail(CS_ERR_ARG, "cs_groth16_witness_map: party must be 0..2");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, h_m1, h_m2));
+  switch (pk->curve) {
+    case CS_BN254:
+      CS_TRY((witness_map_device<Bn254Cfg>(ctx, pk, kind, party, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+      break;
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381:
+      CS_TRY((witness_map_device<Bls381Cfg>(ctx, pk, kind, party, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+      break;
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+  if (h_out) CS_CUDA(cudaMemcpyAsync(h_out, pk->d_c.p, pk->n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int cs_groth16_prove_plain(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const uint64_t* h_wit,
+                           const uint64_t* r, const uint64_t* s, uint64_t* out_a, uint64_t* out_b, uint64_t* out_c) {
+  if (!ctx || !pk || !h_pub || (pk->nw && !h_wit) || !r || !s || !out_a || !out_b || !out_c)
+    return fail(CS_ERR_ARG, "cs_groth16_prove_plain: NULL argument");
+  switch (pk->curve) {
+    case CS_BN254: return prove_plain_t<Bn254Cfg>(ctx, pk, h_pub, h_wit, r, s, out_a, out_b, out_c);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: return prove_plain_t<Bls381Cfg>(ctx, pk, h_pub, h_wit, r, s, out_a, out_b, out_c);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
+int cs_groth16_rep3_local(cs_ctx* ctx, cs_groth16_pk* pk, int party, const uint64_t* h_pub,
+                          const uint64_t* h_wit_shares, const uint64_t* h_m1, const uint64_t* h_m2,
+                          const uint64_t* r_share, const uint64_t* s_share, uint64_t* out_g_a, uint64_t* out_g1_b,
+                          uint64_t* out_g2_b, uint64_t* out_l, uint64_t* out_h) {
+  if (!ctx || !pk || !h_pub || (pk->nw && !h_wit_shares) || !r_share || !s_share || !out_g_a || !out_g1_b ||
+      !out_g2_b || !out_l || !out_h)
+    return fail(CS_ERR_ARG, "cs_groth16_rep3_local: NULL argument");
+  if (party < 0 || party > 2) return fail(CS_ERR_ARG, "cs_groth16_rep3_local: party must be 0..2");
+  // to_half_share = the `a` component (mpc/rep3.rs:120-122): first Fr of the share
+  switch (pk->curve) {
+    case CS_BN254:
+      return local_phase<Bn254Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, h_m1, h_m2, r_share, s_share,
+                                   out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381:
+      return local_phase<Bls381Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, h_m1, h_m2, r_share, s_share,
+                                    out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,356 @@
+// Multi-scalar multiplication  sum_i s_i * P_i  on sm_100a.
+//
+// Replaces `taceo_ark_algebra::msm::{msm_unchecked, msm_bigint}` (taceo-ark-algebra 0.1.0, not
+// vendored; call sites co-groth16/src/mpc/{plain.rs:66-74, rep3.rs:124-132, shamir.rs:111-119},
+// co-groth16/src/groth16.rs:190-200, mpc-core/src/protocols/rep3/pointshare.rs:201-222).
+//
+// B200-first design (DESIGN.md "MSM"):
+//  * The base set is a proving key / SRS: it is uploaded once and expanded to a table of
+//    2^(c w) * P_i for every window w (180 GB of HBM makes W x the key size affordable).  All
+//    windows then share ONE bucket set, so there is no per-window reduction and no window-combine
+//    doubling chain on the per-proof path.
+//  * Per MSM: signed c-bit digits -> counting sort by bucket (histogram, scan, scatter) -> bucket
+//    accumulation as a load-balanced segmented reduction over fixed-size slices of the sorted entry
+//    list (robust to skewed scalars) -> weighted bucket reduction sum_b b * S_b.
+//  * Arithmetic is exact 256/381-bit Montgomery on the integer pipe; no tensor cores.
+#pragma once
+#include "cs_common.cuh"
+#include "cs_curve.cuh"
+
+namespace cs {
+
+constexpr unsigned MSM_SLICE = 32;      // entries per slice (levels 0 and 1 of the segmented reduction)
+constexpr unsigned MSM_RED_SEG = 16;    // buckets per thread in the weighted bucket reduction
+constexpr unsigned MSM_SIGN = 0x80000000u;
+
+// --------------------------------------------------------------------------- digits + histogram
+// One thread per scalar: optional Montgomery -> canonical, signed c-bit recoding, histogram.
+template <class FrP>
+CS_GLOBAL void k_msm_digits(const uint32_t* __restrict__ scalars, uint32_t sstride, uint32_t n, int mont,
+                            uint32_t c, uint32_t W, uint32_t* __restrict__ dig, uint32_t* __restrict__ count) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<FrP> s;
+  // sstride = elements between consecutive scalars (2 reads the `a` component of Rep3 shares in place)
+  const uint4* src = reinterpret_cast<const uint4*>(scalars) + (size_t)i * sstride * (FrP::N / 4);
+  CS_UNROLL
+  for (int k = 0; k < FrP::N / 4; k++) {
+    uint4 v = src[k];
+    s.l[4 * k] = v.x; s.l[4 * k + 1] = v.y; s.l[4 * k + 2] = v.z; s.l[4 * k + 3] = v.w;
+  }
+  if (mont) s = s.from_mont();
+  uint32_t lim[FrP::N + 1];
+  CS_UNROLL
+  for (int k = 0; k < FrP::N; k++) lim[k] = s.l[k];
+  lim[FrP::N] = 0;
+  const uint32_t half = 1u << (c - 1);
+  const uint32_t mask = (1u << c) - 1;
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < W; w++) {
+    uint32_t pos = w * c;
+    uint32_t li = pos >> 5, sh = pos & 31;
+    uint32_t lo = li < FrP::N ? lim[li] : 0;
+    uint32_t hi = li + 1 < FrP::N ? lim[li + 1] : 0;
+    uint32_t d = (__funnelshift_r(lo, hi, sh) & mask) + carry;
+    uint32_t out;
+    if (d > half) {
+      out = ((1u << c) - d) | MSM_SIGN;
+      carry = 1;
+    } else {
+      out = d;
+      carry = 0;
+    }
+    dig[(size_t)w * n + i] = out;
+    uint32_t b = out & ~MSM_SIGN;
+    if (b) atomicAdd(&count[b], 1u);
+  }
+}
+
+// --------------------------------------------------------------------------- scans (one block)
+// From count[0..B]: start = exclusive scan of count; ns0[b] = ceil(count[b]/S), ns1 = ceil(ns0/S);
+// sstart0 / sstart1 = exclusive scans.  Arrays have B + 2 entries (last = total).
+static CS_GLOBAL void k_msm_scan(const uint32_t* __restrict__ count, uint32_t nb1 /* B + 1 */,
+                          uint32_t* __restrict__ start, uint32_t* __restrict__ sstart0,
+                          uint32_t* __restrict__ sstart1) {
+  __shared__ uint32_t sm[3][1024];
+  const uint32_t T = blockDim.x, t = threadIdx.x;
+  const uint32_t per = (nb1 + T - 1) / T;
+  const uint32_t lo = t * per, hi = (lo + per < nb1) ? lo + per : nb1;
+  uint32_t a = 0, b = 0, cc = 0;
+  for (uint32_t k = lo; k < hi; k++) {
+    uint32_t cnt = k ? count[k] : 0;  // bucket 0 (zero digits) is dropped
+    uint32_t n0 = (cnt + MSM_SLICE - 1) / MSM_SLICE;
+    uint32_t n1 = (n0 + MSM_SLICE - 1) / MSM_SLICE;
+    a += cnt; b += n0; cc += n1;
+  }
+  sm[0][t] = a; sm[1][t] = b; sm[2][t] = cc;
+  __syncthreads();
+  if (t < 3) {
+    uint32_t run = 0;
+    for (uint32_t k = 0; k < T; k++) {
+      uint32_t v = sm[t][k];
+      sm[t][k] = run;
+      run += v;
+    }
+  }
+  __syncthreads();
+  a = sm[0][t]; b = sm[1][t]; cc = sm[2][t];
+  for (uint32_t k = lo; k < hi; k++) {
+    uint32_t cnt = k ? count[k] : 0;
+    uint32_t n0 = (cnt + MSM_SLICE - 1) / MSM_SLICE;
+    uint32_t n1 = (n0 + MSM_SLICE - 1) / MSM_SLICE;
+    start[k] = a; sstart0[k] = b; sstart1[k] = cc;
+    a += cnt; b += n0; cc += n1;
+  }
+  if (hi == nb1 && lo < hi) { start[nb1] = a; sstart0[nb1] = b; sstart1[nb1] = cc; }
+}
+
+// --------------------------------------------------------------------------- scatter
+// grid.y = window.  sorted[pos] = table index | sign, grouped by bucket.
+static CS_GLOBAL void k_msm_scatter(const uint32_t* __restrict__ dig, uint32_t n, uint32_t nbases,
+                             uint32_t offset, const uint32_t* __restrict__ start,
+                             uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t w = blockIdx.y;
+  if (i >= n) return;
+  uint32_t d = dig[(size_t)w * n + i];
+  uint32_t b = d & ~MSM_SIGN;
+  if (!b) return;
+  uint32_t pos = start[b] + atomicAdd(&cursor[b], 1u);
+  sorted[pos] = (w * nbases + offset + i) | (d & MSM_SIGN);
+}
+
+// largest b in [0, nb1) with arr[b] <= s   (arr non-decreasing, arr[0] = 0)
+CS_D uint32_t find_bucket(const uint32_t* __restrict__ arr, uint32_t nb1, uint32_t s) {
+  uint32_t lo = 0, hi = nb1;  // invariant arr[lo] <= s < arr[hi]  (arr[nb1] = total > s)
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (arr[mid] <= s) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// --------------------------------------------------------------------------- accumulation level 0
+// One thread per slice of <= MSM_SLICE sorted entries of ONE bucket: mixed additions from the table.
+template <class F>
+CS_GLOBAL void __launch_bounds__(128) k_msm_accum0(const Affine<F>* __restrict__ table,
+                                                   const uint32_t* __restrict__ sorted,
+                                                   const uint32_t* __restrict__ count,
+                                                   const uint32_t* __restrict__ start,
+                                                   const uint32_t* __restrict__ sstart0, uint32_t nb1,
+                                                   Xyzz<F>* __restrict__ part0) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= sstart0[nb1]) return;
+  uint32_t b = find_bucket(sstart0, nb1, s);
+  uint32_t j = s - sstart0[b];
+  uint32_t beg = start[b] + j * MSM_SLICE;
+  uint32_t end = start[b] + count[b];
+  if (end > beg + MSM_SLICE) end = beg + MSM_SLICE;
+  Xyzz<F> acc = Xyzz<F>::inf();
+  uint32_t e = sorted[beg];
+  Affine<F> p = table[e & ~MSM_SIGN];
+  for (uint32_t k = beg; k < end; k++) {
+    uint32_t e_cur = e;
+    Affine<F> p_cur = p;
+    if (k + 1 < end) {  // prefetch the next point while this addition runs
+      e = sorted[k + 1];
+      p = table[e & ~MSM_SIGN];
+    }
+    madd(acc, p_cur, (e_cur & MSM_SIGN) != 0);
+  }
+  part0[s] = acc;
+}
+
+// --------------------------------------------------------------------------- accumulation level 1
+template <class F>
+CS_GLOBAL void __launch_bounds__(128) k_msm_accum1(const Xyzz<F>* __restrict__ part0,
+                                                   const uint32_t* __restrict__ sstart0,
+                                                   const uint32_t* __restrict__ sstart1, uint32_t nb1,
+                                                   Xyzz<F>* __restrict__ part1) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= sstart1[nb1]) return;
+  uint32_t b = find_bucket(sstart1, nb1, s);
+  uint32_t j = s - sstart1[b];
+  uint32_t beg = sstart0[b] + j * MSM_SLICE;
+  uint32_t end = sstart0[b + 1];
+  if (end > beg + MSM_SLICE) end = beg + MSM_SLICE;
+  Xyzz<F> acc = part0[beg];
+  for (uint32_t k = beg + 1; k < end; k++) padd(acc, part0[k]);
+  part1[s] = acc;
+}
+
+// --------------------------------------------------------------------------- accumulation level 2
+// One thread per bucket: fold the (normally single) level-1 partial(s) into the bucket sum.
+template <class F>
+CS_GLOBAL void __launch_bounds__(128) k_msm_accum2(const Xyzz<F>* __restrict__ part1,
+                                                   const uint32_t* __restrict__ sstart1, uint32_t nb1,
+                                                   Xyzz<F>* __restrict__ bucket) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb1) return;
+  uint32_t beg = sstart1[b], end = sstart1[b + 1];
+  Xyzz<F> acc = Xyzz<F>::inf();
+  if (beg < end) {
+    acc = part1[beg];
+    for (uint32_t k = beg + 1; k < end; k++) padd(acc, part1[k]);
+  }
+  bucket[b] = acc;
+}
+
+// --------------------------------------------------------------------------- bucket reduction
+// Thread t owns buckets (t L, (t+1) L]:  out[t] = sum_{b} b * S_b  over its segment
+//   = tot + (t L) * acc,   acc = sum S_b,  tot = sum (b - t L) S_b  by a running sum.
+template <class F>
+CS_GLOBAL void __launch_bounds__(128) k_msm_reduce_seg(const Xyzz<F>* __restrict__ bucket, uint32_t B,
+                                                       uint32_t L, Xyzz<F>* __restrict__ red) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t lo = t * L;
+  if (lo >= B) return;
+  uint32_t hi = lo + L < B ? lo + L : B;
+  Xyzz<F> acc = Xyzz<F>::inf(), tot = Xyzz<F>::inf();
+  for (uint32_t b = hi; b > lo; b--) {
+    padd(acc, bucket[b]);
+    padd(tot, acc);
+  }
+  // tot += lo * acc   (double-and-add, lo < 2^31)
+  if (lo != 0 && !acc.is_inf()) {
+    Xyzz<F> m = Xyzz<F>::inf();
+    int top = 31 - __clz(lo);
+    for (int bit = top; bit >= 0; bit--) {
+      m = dbl_xyzz(m);
+      if ((lo >> bit) & 1) padd(m, acc);
+    }
+    padd(tot, m);
+  }
+  red[t] = tot;
+}
+
+// Single block: sum `cnt` points into out[0].
+template <class F>
+CS_GLOBAL void k_msm_final_sum(const Xyzz<F>* __restrict__ red, uint32_t cnt,
+                                                      Xyzz<F>* __restrict__ out) {
+  CS_DYN_SMEM(Xyzz<F>, sm);
+  const uint32_t T = blockDim.x, t = threadIdx.x;
+  Xyzz<F> acc = Xyzz<F>::inf();
+  for (uint32_t k = t; k < cnt; k += T) padd(acc, red[k]);
+  sm[t] = acc;
+  __syncthreads();
+  for (uint32_t step = T >> 1; step > 0; step >>= 1) {
+    if (t < step) {
+      Xyzz<F> a = sm[t];
+      padd(a, sm[t + step]);
+      sm[t] = a;
+    }
+    __syncthreads();
+  }
+  if (t == 0) out[0] = sm[0];
+}
+
+// --------------------------------------------------------------------------- table precomputation
+// table[w * n + i] = 2^(c w) * P_i  (affine), w = 0..W-1.  One thread per base point; runs once per
+// proving key (cs_bases_upload), off the per-proof path.
+template <class F>
+CS_GLOBAL void __launch_bounds__(128) k_msm_precompute(Affine<F>* __restrict__ table, uint32_t n,
+                                                       uint32_t c, uint32_t W) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<F> p = table[i];
+  Xyzz<F> cur = Xyzz<F>::from_affine(p);
+  for (uint32_t w = 1; w < W; w++) {
+    for (uint32_t k = 0; k < c; k++) cur = dbl_xyzz(cur);
+    Affine<F> a = to_affine(cur);
+    table[(size_t)w * n + i] = a;
+    cur = Xyzz<F>::from_affine(a);  // keeps ZZ = ZZZ = 1 so the next doublings stay cheap
+  }
+}
+
+// --------------------------------------------------------------------------- host driver
+struct MsmShape {
+  uint32_t c, W, B;  // window bits, windows, buckets (1..B)
+};
+
+static inline MsmShape msm_shape(uint32_t scalar_bits, uint32_t c) {
+  MsmShape s;
+  s.c = c;
+  s.W = (scalar_bits + 1 + c - 1) / c;  // top window keeps <= c-1 bits so the signed recoding never overflows
+  s.B = 1u << (c - 1);
+  return s;
+}
+
+static inline uint32_t msm_auto_window(size_t n) {
+  int lg = 0;
+  while ((1ull << (lg + 1)) <= n) lg++;
+  int c = lg - 4;
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  return (uint32_t)c;
+}
+
+struct MsmWorkspace {
+  DevBuf dig, sorted, meta, part0, part1, bucket, red, scal, result;
+  void* h_result = nullptr;  // pinned, holds one Xyzz
+  size_t h_result_cap = 0;
+  void release() {
+    dig.release(); sorted.release(); meta.release(); part0.release(); part1.release();
+    bucket.release(); red.release(); scal.release(); result.release();
+    if (h_result) cudaFreeHost(h_result);
+    h_result = nullptr;
+    h_result_cap = 0;
+  }
+};
+
+// Enqueue one MSM on `st`.  d_scalars: device, n elements of Fr (8 x u32).  The XYZZ result lands in
+// ws.h_result (pinned) after the stream drains.
+template <class F, class FrP>
+int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, uint32_t nbases, MsmShape sh, uint32_t offset,
+                const uint32_t* d_scalars, uint32_t sstride, uint32_t n, int mont, cudaStream_t st) {
+  const uint32_t nb1 = sh.B + 1;
+  const size_t nent = (size_t)sh.W * n;
+  if (nent >= (1ull << 31) || (size_t)sh.W * nbases >= (1ull << 31))
+    return fail(-3, "msm: W*n = %zu exceeds 2^31 entries", nent);
+  const size_t max_s0 = nent / MSM_SLICE + nb1;
+  const size_t max_s1 = max_s0 / MSM_SLICE + nb1;
+  CS_TRY(ws.dig.reserve(nent * 4));
+  CS_TRY(ws.sorted.reserve(nent * 4));
+  // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1]
+  const size_t meta_words = 2 * (size_t)nb1 + 3 * ((size_t)nb1 + 1);
+  CS_TRY(ws.meta.reserve(meta_words * 4));
+  CS_TRY(ws.part0.reserve(max_s0 * sizeof(Xyzz<F>)));
+  CS_TRY(ws.part1.reserve(max_s1 * sizeof(Xyzz<F>)));
+  CS_TRY(ws.bucket.reserve((size_t)nb1 * sizeof(Xyzz<F>)));
+  const uint32_t L = sh.B < MSM_RED_SEG ? sh.B : MSM_RED_SEG;
+  const uint32_t nseg = (sh.B + L - 1) / L;
+  CS_TRY(ws.red.reserve((size_t)nseg * sizeof(Xyzz<F>)));
+  CS_TRY(ws.result.reserve(sizeof(Xyzz<F>)));
+  const uint32_t fs_threads = sizeof(Xyzz<F>) > 128 ? 128 : 256;  // <= 32 KB of dynamic shared memory
+  if (ws.h_result_cap < sizeof(Xyzz<F>)) {
+    if (ws.h_result) cudaFreeHost(ws.h_result);
+    CS_CUDA(cudaMallocHost(&ws.h_result, sizeof(Xyzz<F>)));
+    ws.h_result_cap = sizeof(Xyzz<F>);
+  }
+  uint32_t* count = ws.meta.as<uint32_t>();
+  uint32_t* cursor = count + nb1;
+  uint32_t* start = cursor + nb1;
+  uint32_t* sstart0 = start + nb1 + 1;
+  uint32_t* sstart1 = sstart0 + nb1 + 1;
+  CS_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nb1 * 4, st));
+  CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W,
+            ws.dig.as<uint32_t>(), count);
+  CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, start, sstart0, sstart1);
+  CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
+            offset, start, cursor, ws.sorted.as<uint32_t>());
+  CS_LAUNCH(k_msm_accum0<F>, ceil_div(max_s0, 128), 128, 0, st, table, ws.sorted.as<uint32_t>(), count,
+            start, sstart0, nb1, ws.part0.as<Xyzz<F>>());
+  CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,
+            nb1, ws.part1.as<Xyzz<F>>());
+  CS_LAUNCH(k_msm_accum2<F>, ceil_div(nb1, 128), 128, 0, st, ws.part1.as<Xyzz<F>>(), sstart1, nb1,
+            ws.bucket.as<Xyzz<F>>());
+  CS_LAUNCH(k_msm_reduce_seg<F>, ceil_div(nseg, 128), 128, 0, st, ws.bucket.as<Xyzz<F>>(), sh.B, L,
+            ws.red.as<Xyzz<F>>());
+  CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
+                 ws.result.as<Xyzz<F>>());
+  CS_CUDA(cudaMemcpyAsync(ws.h_result, ws.result.p, sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cs

@@ -1,0 +1,142 @@
+// Share-wise element kernels and the R1CS sparse matrix-vector product.
+//
+// Replaces, on n-sized vectors (n = domain size):
+//  * `T::local_mul_vec` -> `rep3::arithmetic::local_mul_vec`
+//    (mpc-core/src/protocols/rep3/arithmetic.rs:132-146; share product ops.rs:69-76):
+//        z_i = a_i.a*b_i.a + a_i.a*b_i.b + a_i.b*b_i.a + mask_i          (Rep3)
+//        z_i = a_i * b_i                                                  (plain / Shamir)
+//  * `T::distribute_powers_and_mul_by_const` (co-groth16/src/mpc/rep3.rs:95-106, plain.rs:91-98)
+//    and the inline c-scaling (reduction.rs:166-171):   x_i *= table_i   per share component
+//  * the final `ab -= c` (reduction.rs:185-190)
+//  * `evaluate_constraint` (co-groth16/src/mpc/rep3.rs:31-49, plain.rs:29-43; driver
+//    reduction.rs:196-210) incl. the public rows re-inserted at reduction.rs:111-113
+//  * the Rep3 -> Shamir bridge a*x + b*y (mpc-core/src/protocols/bridges/rep3_to_shamir.rs:43-63)
+// All of these stream each operand once; they sit at the HBM/IMAD ridge (1-3 mulmods per 64-192 B).
+#pragma once
+#include "cs_common.cuh"
+#include "cs_field.cuh"
+#include "cs_ntt.cuh"  // ld_fr / st_fr
+
+namespace cs {
+
+enum VecOp { VEC_MUL = 0, VEC_ADD = 1, VEC_SUB = 2 };
+
+// out = a (op) b, elementwise on n field elements
+template <class FrP>
+CS_GLOBAL void k_vec_binop(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                           uint32_t* __restrict__ out, size_t n, int op) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    Fp<FrP> x = ld_fr<FrP>(a + i * FrP::N), y = ld_fr<FrP>(b + i * FrP::N), z;
+    if (op == VEC_MUL) z = x * y;
+    else if (op == VEC_ADD) z = x + y;
+    else z = x - y;
+    st_fr<FrP>(out + i * FrP::N, z);
+  }
+}
+
+// x[i*batch + c] *= tab[i]     (distribute_powers_and_mul_by_const on plain values or shares)
+template <class FrP>
+CS_GLOBAL void k_vec_scale_table(uint32_t* __restrict__ x, const uint32_t* __restrict__ tab, size_t n,
+                                 uint32_t batch) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n * batch; i += step) {
+    size_t e = i / batch;
+    Fp<FrP> v = ld_fr<FrP>(x + i * FrP::N) * ld_fr<FrP>(tab + e * FrP::N);
+    st_fr<FrP>(x + i * FrP::N, v);
+  }
+}
+
+// Rep3 local multiplication.  a, b: n shares {a,b} (2 x Fr each); mask: n Fr (nullable = 0);
+// sub: n Fr (nullable) subtracted afterwards (fuses reduction.rs:182-190: ab = local_mul_vec(a,b) - c).
+template <class FrP>
+CS_GLOBAL void k_rep3_local_mul(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                                const uint32_t* __restrict__ mask, const uint32_t* __restrict__ sub,
+                                uint32_t* __restrict__ out, size_t n) {
+  constexpr int NW = FrP::N;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    Fp<FrP> aa = ld_fr<FrP>(a + (2 * i) * NW), ab = ld_fr<FrP>(a + (2 * i + 1) * NW);
+    Fp<FrP> ba = ld_fr<FrP>(b + (2 * i) * NW), bb = ld_fr<FrP>(b + (2 * i + 1) * NW);
+    // a.a*b.a + a.a*b.b + a.b*b.a  ==  a.a*(b.a + b.b) + a.b*b.a   (exact in the field)
+    Fp<FrP> z = aa * (ba + bb) + ab * ba;
+    if (mask) z = z + ld_fr<FrP>(mask + i * NW);
+    if (sub) z = z - ld_fr<FrP>(sub + i * NW);
+    st_fr<FrP>(out + i * NW, z);
+  }
+}
+
+// Plain / Shamir local multiplication with the same optional fused subtraction: out = a*b - sub
+template <class FrP>
+CS_GLOBAL void k_plain_mul_sub(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b,
+                               const uint32_t* __restrict__ sub, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    Fp<FrP> z = ld_fr<FrP>(a + i * FrP::N) * ld_fr<FrP>(b + i * FrP::N);
+    if (sub) z = z - ld_fr<FrP>(sub + i * FrP::N);
+    st_fr<FrP>(out + i * FrP::N, z);
+  }
+}
+
+// Rep3 -> Shamir(t=1) translation: out_i = ca * x_i.a + cb * x_i.b  (rep3_to_shamir.rs:43-63)
+template <class FrP>
+CS_GLOBAL void k_rep3_to_shamir(const uint32_t* __restrict__ x, const uint32_t* __restrict__ ca,
+                                const uint32_t* __restrict__ cb, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  Fp<FrP> fa = ld_fr<FrP>(ca), fb = ld_fr<FrP>(cb);
+  for (; i < n; i += step) {
+    Fp<FrP> z = ld_fr<FrP>(x + 2 * i * FrP::N) * fa + ld_fr<FrP>(x + (2 * i + 1) * FrP::N) * fb;
+    st_fr<FrP>(out + i * FrP::N, z);
+  }
+}
+
+// evaluate_constraint over CSR rows.  One thread per row.
+//   wit: n_wit entries of `batch` components (1: plain value / half share; 2: Rep3 share {a,b})
+//   pub: n_pub public inputs (pub[0] = 1).  Column index < n_pub selects a public input.
+//   pub_comp: component that receives public terms (Rep3: 0 for party 0, 1 for party 1, -1 for
+//             party 2; plain: 0)   -- arithmetic.rs:52-58
+//   Rows [nrows, nrows + n_pubrows) get the promoted public inputs (reduction.rs:111-113) when
+//   n_pubrows > 0; rows beyond that up to `domain` are zero-filled (reduction.rs:208).
+template <class FrP>
+CS_GLOBAL void k_spmv(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                      const uint32_t* __restrict__ coeff, const uint32_t* __restrict__ pub, uint32_t n_pub,
+                      const uint32_t* __restrict__ wit, uint32_t batch, int pub_comp, uint32_t nrows,
+                      uint32_t n_pubrows, uint32_t domain, uint32_t* __restrict__ out) {
+  constexpr int NW = FrP::N;
+  uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= domain) return;
+  Fp<FrP> acc[2];
+  acc[0] = Fp<FrP>::zero();
+  acc[1] = Fp<FrP>::zero();
+  if (r < nrows) {
+    uint32_t beg = row_ptr[r], end = row_ptr[r + 1];
+    for (uint32_t k = beg; k < end; k++) {
+      uint32_t cidx = col[k];
+      Fp<FrP> cf = ld_fr<FrP>(coeff + (size_t)k * NW);
+      if (cidx < n_pub) {
+        if (pub_comp >= 0) {
+          Fp<FrP> t = cf * ld_fr<FrP>(pub + (size_t)cidx * NW);
+          if (pub_comp == 0) acc[0] = acc[0] + t; else acc[1] = acc[1] + t;
+        }
+      } else {
+        size_t wi = (size_t)(cidx - n_pub) * batch;
+        acc[0] = acc[0] + cf * ld_fr<FrP>(wit + wi * NW);
+        if (batch == 2) acc[1] = acc[1] + cf * ld_fr<FrP>(wit + (wi + 1) * NW);
+      }
+    }
+  } else if (r < nrows + n_pubrows) {
+    if (pub_comp >= 0) {
+      Fp<FrP> v = ld_fr<FrP>(pub + (size_t)(r - nrows) * NW);
+      if (pub_comp == 0) acc[0] = v; else acc[1] = v;
+    }
+  }
+  st_fr<FrP>(out + (size_t)r * batch * NW, acc[0]);
+  if (batch == 2) st_fr<FrP>(out + ((size_t)r * batch + 1) * NW, acc[1]);
+}
+
+}  // namespace cs

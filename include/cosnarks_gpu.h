@@ -1,0 +1,197 @@
+/* cosnarks_gpu.h -- C ABI of libcosnarks_gpu.so, the B200 (sm_100a) backend for the co-snarks hot path.
+ *
+ * The reference (TaceoLabs/co-snarks @ 2b4592e) is pure Rust and has no FFI; its seams for this path
+ * are (1) the crate `taceo-ark-algebra 0.1.0` (msm + fft), (2) the `R1CSToQAP` trait and (3) the
+ * `CircomGroth16Prover` driver trait.  Each entry point below names the reference interface it
+ * replaces; INTEGRATION.md shows the Rust `extern "C"` bindings a maintainer would add.
+ *
+ * Conventions
+ *  - Field elements are little-endian arrays of 64-bit limbs in MONTGOMERY form with R = 2^(64*limbs),
+ *    i.e. byte-identical to arkworks' `Fp<MontBackend<_, N>>.0.0` ([u64; N]): BN254 Fr/Fq and
+ *    BLS12-381 Fr = 4 limbs, BLS12-381 Fq = 6 limbs.  "canonical" = the plain integer (BigInt).
+ *  - G1 affine = x || y ; G2 affine = x.c0 || x.c1 || y.c0 || y.c1 ; the all-zero encoding is the
+ *    point at infinity (same marker as snarkjs .zkey files).
+ *  - Rep3 share = a || b (Rep3PrimeFieldShare, mpc-core/src/protocols/rep3/arithmetic/types.rs:21-28).
+ *  - All functions return 0 on success and a negative code on failure; cs_last_error() gives the
+ *    message for the calling thread.  No exceptions cross the boundary.  There is no CPU fallback:
+ *    without a CUDA device every compute call fails with CS_ERR_CUDA.
+ *  - `h_` pointers are host memory (pinned or pageable), `d_` pointers are device memory of the
+ *    context's device.  Calls on one cs_ctx are serialised by the caller; use one ctx per host thread
+ *    for concurrency (the reference calls msm/fft from several rayon workers, groth16.rs:227).
+ */
+#ifndef COSNARKS_GPU_H
+#define COSNARKS_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CS_OK 0
+#define CS_ERR_ARG (-1)
+#define CS_ERR_CUDA (-2)
+#define CS_ERR_LIMIT (-3)
+#define CS_ERR_STATE (-4)
+
+typedef enum { CS_BN254 = 0, CS_BLS12_381 = 1 } cs_curve;
+typedef enum { CS_G1 = 0, CS_G2 = 1 } cs_group;
+typedef enum { CS_NTT_IN_TO_OUT = 0, CS_NTT_OUT_TO_IN = 1 } cs_ntt_order;
+typedef enum { CS_PLAIN = 0, CS_REP3 = 1 } cs_share_kind;
+
+typedef struct cs_ctx cs_ctx;
+typedef struct cs_bases cs_bases;
+typedef struct cs_domain cs_domain;
+typedef struct cs_groth16_pk cs_groth16_pk;
+
+/* ---- library / context ------------------------------------------------------------------------ */
+const char* cs_last_error(void);
+/* version string, e.g. "cosnarks-b200 0.1 (sm_100a)" */
+const char* cs_version(void);
+/* `stream` = an existing cudaStream_t the context should run on (e.g. torch's current stream), or NULL
+ * to let the context create its own. */
+int cs_ctx_create(int device, void* stream, cs_ctx** out);
+void cs_ctx_destroy(cs_ctx* ctx);
+int cs_ctx_synchronize(cs_ctx* ctx);
+/* kernels launched by this context since creation (bench.py's "gpu_launches") */
+uint64_t cs_ctx_launch_count(const cs_ctx* ctx);
+
+/* device memory helpers so a host language needs no CUDA binding of its own */
+int cs_dev_alloc(cs_ctx* ctx, size_t bytes, void** d_out);
+int cs_dev_free(cs_ctx* ctx, void* d_ptr);
+int cs_host_alloc_pinned(size_t bytes, void** h_out);
+int cs_host_free_pinned(void* h_ptr);
+int cs_memcpy_h2d(cs_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int cs_memcpy_d2h(cs_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+
+/* ---- MSM: taceo_ark_algebra::msm::{msm_unchecked, msm_bigint} --------------------------------------
+ * Reference call sites: co-groth16/src/mpc/plain.rs:66-74, rep3.rs:124-132, shamir.rs:111-119,
+ * co-groth16/src/groth16.rs:194, mpc-core/src/protocols/rep3/pointshare.rs:201-222,
+ * co-noir/co-noir-common/src/honk_curve.rs:81-83.
+ *
+ * cs_bases_upload: upload `n` affine points (Montgomery) once per proving key / SRS; the library
+ * expands them into the per-window table it keeps resident in HBM.  window_bits = 0 picks a default.
+ * cs_msm: sum_{i<n} scalars[i] * bases[offset + i]; the reference "chops to the shorter slice"
+ * (honk_curve.rs:33-34) -- pass n = min(len).  scalars_montgomery = 1 for `&[Fr]` (msm_unchecked),
+ * 0 for canonical `&[BigInt]` (msm_bigint; must be < r).  Result: affine point (Montgomery), all-zero
+ * + *out_is_infinity = 1 for the identity. */
+int cs_bases_upload(cs_ctx* ctx, cs_curve curve, cs_group group, const uint64_t* h_points_mont, size_t n,
+                    int window_bits, cs_bases** out);
+void cs_bases_free(cs_bases* bases);
+size_t cs_bases_len(const cs_bases* bases);
+int cs_msm(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* h_scalars, size_t n,
+           int scalars_montgomery, uint64_t* h_out_affine_mont, int* out_is_infinity);
+int cs_msm_device(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* d_scalars, size_t n,
+                  int scalars_montgomery, uint64_t* h_out_affine_mont, int* out_is_infinity);
+
+/* ---- NTT: taceo_ark_algebra::fft::{Domain, bit_reverse} ---------------------------------------------
+ * Domain::with_group_gen(size, gen) (co-groth16/src/groth16/reduction.rs:93), ::new (:249), size()
+ * (:251), ifft_in_to_out / fft_out_to_in (:141-175, :270-327), bit_reverse (:58, :328).
+ * `batch` = interleaved components per element: 1 for Fr / half shares, 2 for Rep3 shares
+ * (DomainCoeff impl, rep3/arithmetic/ops.rs:5-114).  The inverse includes the 1/n scaling.
+ * group_gen (Montgomery) must be a primitive 2^log_n-th root of unity; NULL selects arkworks' default
+ * generator for the field (Domain::new). */
+int cs_domain_create(cs_ctx* ctx, cs_curve curve, unsigned log_n, const uint64_t* group_gen_mont,
+                     cs_domain** out);
+void cs_domain_free(cs_domain* dom);
+size_t cs_domain_size(const cs_domain* dom);
+int cs_ifft_in_to_out(cs_ctx* ctx, const cs_domain* dom, uint64_t* d_data, unsigned batch);
+int cs_fft_out_to_in(cs_ctx* ctx, const cs_domain* dom, uint64_t* d_data, unsigned batch);
+int cs_bit_reverse(cs_ctx* ctx, cs_curve curve, uint64_t* d_data, unsigned log_n, unsigned batch);
+/* host-buffer convenience wrappers (copy in, transform, copy out) -- what a drop-in for the
+ * `&mut [T]` signatures of the reference binds to */
+int cs_ifft_in_to_out_host(cs_ctx* ctx, const cs_domain* dom, uint64_t* h_data, unsigned batch);
+int cs_fft_out_to_in_host(cs_ctx* ctx, const cs_domain* dom, uint64_t* h_data, unsigned batch);
+
+/* ---- share-wise vector kernels ------------------------------------------------------------------
+ * cs_vec_mul/add/sub: elementwise on Fr (plain driver local_mul_vec, co-groth16/src/mpc/plain.rs:83-89;
+ *   `ab -= c`, reduction.rs:185-190).
+ * cs_vec_scale_table: x[i] *= table[i] per component (distribute_powers_and_mul_by_const,
+ *   co-groth16/src/mpc/rep3.rs:95-106; reduction.rs:166-171).
+ * cs_rep3_local_mul_vec: rep3::arithmetic::local_mul_vec (mpc-core/.../rep3/arithmetic.rs:132-146):
+ *   out_i = a_i.a*b_i.a + a_i.a*b_i.b + a_i.b*b_i.a + mask_i; d_mask may be NULL (zero masks);
+ *   the masks themselves come from the caller's Rep3Rand (rngs.rs:137-156).
+ * cs_rep3_to_shamir: bridges/rep3_to_shamir.rs:43-63, out_i = ca*x_i.a + cb*x_i.b. */
+int cs_vec_mul(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n);
+int cs_vec_add(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n);
+int cs_vec_sub(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b, uint64_t* d_out, size_t n);
+int cs_vec_scale_table(cs_ctx* ctx, cs_curve curve, uint64_t* d_x, const uint64_t* d_table, size_t n, unsigned batch);
+int cs_rep3_local_mul_vec(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b,
+                          const uint64_t* d_mask, uint64_t* d_out, size_t n);
+int cs_rep3_to_shamir(cs_ctx* ctx, cs_curve curve, const uint64_t* d_x, const uint64_t* h_ca_mont,
+                      const uint64_t* h_cb_mont, uint64_t* d_out, size_t n);
+
+/* ---- Groth16: R1CSToQAP::witness_map_from_matrices + CoGroth16::prove ------------------------------
+ * cs_groth16_pk_create uploads ark_groth16::ProvingKey + ConstraintMatrices once
+ * (fields used by the prover: co-groth16/src/groth16.rs:219-225,234-290; lib.rs:262-272).
+ *   matrices in CSR: row_ptr[num_constraints+1], col[nnz] (variable index, publics first), coeff[nnz]
+ *   (Fr Montgomery).  Query arrays are affine Montgomery points.
+ * cs_groth16_witness_map = CircomReduction::witness_map_from_matrices (reduction.rs:77-193):
+ *   kind = CS_PLAIN: witness = Fr values, masks ignored;  kind = CS_REP3: witness = shares {a,b},
+ *   party = 0..2, h_mask1/h_mask2 = the two local_mul_vec mask vectors (NULL = zero).  Output: the
+ *   `domain_size` half shares of h, left on the device inside the pk scratch and (if h_out != NULL)
+ *   copied to the host. */
+typedef struct {
+  cs_curve curve;
+  size_t num_constraints, num_instance_variables, num_witness_variables;
+  const uint32_t* a_row_ptr; const uint32_t* a_col; const uint64_t* a_coeff; size_t a_nnz;
+  const uint32_t* b_row_ptr; const uint32_t* b_col; const uint64_t* b_coeff; size_t b_nnz;
+  const uint64_t* alpha_g1; const uint64_t* beta_g1; const uint64_t* beta_g2;
+  const uint64_t* delta_g1; const uint64_t* delta_g2;
+  const uint64_t* a_query; size_t a_query_len;
+  const uint64_t* b_g1_query; size_t b_g1_query_len;
+  const uint64_t* b_g2_query; size_t b_g2_query_len;
+  const uint64_t* l_query; size_t l_query_len;
+  const uint64_t* h_query; size_t h_query_len;
+  int window_bits; /* 0 = default */
+} cs_groth16_key_desc;
+
+int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* desc, cs_groth16_pk** out);
+void cs_groth16_pk_free(cs_groth16_pk* pk);
+size_t cs_groth16_domain_size(const cs_groth16_pk* pk);
+
+int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party,
+                           const uint64_t* h_public_inputs, const uint64_t* h_witness,
+                           const uint64_t* h_mask1, const uint64_t* h_mask2, uint64_t* h_out);
+
+/* Groth16::plain_prove (co-groth16/src/groth16.rs:484-490) with the randomness (r, s) supplied by
+ * the caller (the reference draws it from thread_rng, mpc/plain.rs:23-26).  public_inputs includes
+ * the leading 1; witness = the private part.  Outputs: proof A (G1), B (G2), C (G1) affine Montgomery. */
+int cs_groth16_prove_plain(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_public_inputs,
+                           const uint64_t* h_witness, const uint64_t* h_r_mont, const uint64_t* h_s_mont,
+                           uint64_t* out_a, uint64_t* out_b, uint64_t* out_c);
+
+/* One party's LOCAL part of Rep3CoGroth16::prove up to the first network round
+ * (groth16.rs:151-163 + the rayon_join5 block :227-294): witness map, then the five MSMs.
+ *   r_share/s_share: this party's Rep3 shares {a,b} of r and s (T::rand, mpc/rep3.rs:27-29).
+ * Outputs (affine Montgomery half shares): g_a = r_g1, g1_b = s_g1 (G1), g2_b = s_g2 (G2),
+ * l_acc, h_acc (G1).  The two network legs and the final sums (groth16.rs:296-337) are run by the
+ * host-side driver (co_snarks_b200/rep3.py <-> mpc-net Network). */
+int cs_groth16_rep3_local(cs_ctx* ctx, cs_groth16_pk* pk, int party, const uint64_t* h_public_inputs,
+                          const uint64_t* h_witness_shares, const uint64_t* h_mask1, const uint64_t* h_mask2,
+                          const uint64_t* h_r_share, const uint64_t* h_s_share,
+                          uint64_t* out_g_a, uint64_t* out_g1_b, uint64_t* out_g2_b,
+                          uint64_t* out_l_acc, uint64_t* out_h_acc);
+
+/* ---- single-point helpers used by the host-side protocol code (latency-only, run on the host) -----
+ * scalar_mul_public_point_hs (mpc/rep3.rs:141-146), point addition / negation for
+ * open_half_point (pointshare.rs:152-155) and the final sums (groth16.rs:314-322).
+ * scalar is Fr in Montgomery form. */
+int cs_point_scalar_mul(cs_curve curve, cs_group group, const uint64_t* point_affine_mont,
+                        const uint64_t* scalar_mont, uint64_t* out_affine_mont);
+int cs_point_add(cs_curve curve, cs_group group, const uint64_t* p_affine_mont, const uint64_t* q_affine_mont,
+                 uint64_t* out_affine_mont);
+int cs_point_neg(cs_curve curve, cs_group group, const uint64_t* p_affine_mont, uint64_t* out_affine_mont);
+/* Fr helpers: Montgomery <-> canonical, multiplication, and the snarkjs roots of unity
+ * (groth16_roots_of_unity, co-groth16/src/groth16.rs:91-100). */
+int cs_fr_to_mont(cs_curve curve, const uint64_t* in_canonical, uint64_t* out_mont, size_t n);
+int cs_fr_from_mont(cs_curve curve, const uint64_t* in_mont, uint64_t* out_canonical, size_t n);
+int cs_fq_to_mont(cs_curve curve, const uint64_t* in_canonical, uint64_t* out_mont, size_t n);
+int cs_fq_from_mont(cs_curve curve, const uint64_t* in_mont, uint64_t* out_canonical, size_t n);
+int cs_groth16_roots_of_unity(cs_curve curve, unsigned pow, uint64_t* out_group_gen_mont,
+                              uint64_t* out_coset_shift_mont);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COSNARKS_GPU_H */
