@@ -60,6 +60,9 @@ SIGNATURES = {
     "cs_bases_len": (C.c_size_t, [C.c_void_p]),
     "cs_msm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "cs_msm_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "cs_msm_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "cs_msm_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cs_fixed_base_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cs_domain_create": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cs_domain_free": (None, [C.c_void_p]),
     "cs_domain_size": (C.c_size_t, [C.c_void_p]),
@@ -79,6 +82,7 @@ SIGNATURES = {
     "cs_groth16_domain_size": (C.c_size_t, [C.c_void_p]),
     "cs_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_groth16_prove_plain_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_rep3_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 11),
     "cs_point_scalar_mul": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_point_add": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -233,6 +237,23 @@ class Context:
                                         _ptr(out), C.byref(inf)))
         return out, bool(inf.value)
 
+    def msm_profile(self, enable=True):
+        self._check(self.lib.cs_msm_profile(self.h, int(enable)))
+
+    def msm_stage_ms(self):
+        arr = (C.c_float * 5)()
+        self._check(self.lib.cs_msm_stage_ms(self.h, arr))
+        return [float(x) for x in arr]
+
+    def fixed_base_mul(self, curve, group, base_mont, scalars, montgomery=True):
+        scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
+        base_mont = np.ascontiguousarray(base_mont, dtype=np.uint64)
+        n = scalars.shape[0]
+        out = np.zeros((n, base_mont.size), dtype=np.uint64)
+        self._check(self.lib.cs_fixed_base_mul(self.h, curve, group, _ptr(base_mont), _ptr(scalars), n,
+                                               int(montgomery), _ptr(out)))
+        return out
+
     # ---- NTT
     def domain(self, curve, log_n, group_gen_mont=None):
         h = C.c_void_p()
@@ -352,6 +373,15 @@ class Groth16Key:
         c = np.zeros(2 * self.fq, dtype=np.uint64)
         self.ctx._check(self.ctx.lib.cs_groth16_prove_plain(
             self.ctx.h, self.h, _ptr(public_inputs), _ptr(witness), _ptr(r_mont), _ptr(s_mont),
+            _ptr(a), _ptr(b), _ptr(c)))
+        return a, b, c
+
+    def prove_plain_device(self, public_inputs, d_witness, r_mont, s_mont):
+        a = np.zeros(2 * self.fq, dtype=np.uint64)
+        b = np.zeros(4 * self.fq, dtype=np.uint64)
+        c = np.zeros(2 * self.fq, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_groth16_prove_plain_device(
+            self.ctx.h, self.h, _ptr(public_inputs), C.c_void_p(d_witness), _ptr(r_mont), _ptr(s_mont),
             _ptr(a), _ptr(b), _ptr(c)))
         return a, b, c
 

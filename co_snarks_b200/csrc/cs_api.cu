@@ -283,6 +283,60 @@ int cs_msm(cs_ctx* ctx, const cs_bases* b, size_t offset, const uint64_t* h_scal
   return cs_msm_device(ctx, b, offset, ws.scal.as<uint64_t>(), n, scalars_montgomery, h_out, out_inf);
 }
 
+int cs_msm_profile(cs_ctx* ctx, int enable) {
+  if (!ctx) return fail(CS_ERR_ARG, "ctx is NULL");
+  for (int i = 0; i < CS_NSIDE; i++) ctx->msm_ws[i].profile = enable != 0;
+  return 0;
+}
+
+int cs_msm_stage_ms(cs_ctx* ctx, float* out_ms) {
+  if (!ctx || !out_ms) return fail(CS_ERR_ARG, "cs_msm_stage_ms: NULL argument");
+  MsmWorkspace& ws = ctx->msm_ws[0];
+  if (!ws.profile || !ws.ev[MSM_NSTAGE]) return fail(CS_ERR_STATE, "cs_msm_stage_ms: no profiled MSM has run");
+  for (int i = 0; i < MSM_NSTAGE; i++) {
+#if defined(CS_EMU)
+    out_ms[i] = 0.f;
+#else
+    CS_CUDA(cudaEventElapsedTime(&out_ms[i], ws.ev[i], ws.ev[i + 1]));
+#endif
+  }
+  return 0;
+}
+
+int cs_fixed_base_mul(cs_ctx* ctx, cs_curve curve, cs_group group, const uint64_t* h_base, const uint64_t* h_scalars,
+                      size_t n, int scalars_montgomery, uint64_t* h_out) {
+  if (!ctx || !h_base || !h_out || (n && !h_scalars)) return fail(CS_ERR_ARG, "cs_fixed_base_mul: NULL argument");
+  if (n == 0) return 0;
+  if (n >= (1ull << 31)) return fail(CS_ERR_LIMIT, "cs_fixed_base_mul: n too large");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  const size_t pbytes = point_limbs64(curve, group) * 8;
+  DevBuf dbase, dscal, dout;
+  CS_TRY(dbase.reserve(pbytes));
+  CS_TRY(dscal.reserve(n * 32));
+  CS_TRY(dout.reserve(n * pbytes));
+  CS_CUDA(cudaMemcpyAsync(dbase.p, h_base, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+  CS_CUDA(cudaMemcpyAsync(dscal.p, h_scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+  CS_DISPATCH_CURVE(curve, {
+    typedef typename Cfg::FrP FrP;
+    if (group == CS_G1) {
+      typedef typename GroupOf<Cfg, 0>::F F;
+      CS_LAUNCH(k_fixed_base_mul<F COMMA FrP>, ceil_div(n, 128), 128, 0, ctx->stream, dbase.as<Affine<F>>(),
+                dscal.as<uint32_t>(), (uint32_t)n, scalars_montgomery, dout.as<Affine<F>>());
+    } else {
+      typedef typename GroupOf<Cfg, 1>::F F;
+      CS_LAUNCH(k_fixed_base_mul<F COMMA FrP>, ceil_div(n, 128), 128, 0, ctx->stream, dbase.as<Affine<F>>(),
+                dscal.as<uint32_t>(), (uint32_t)n, scalars_montgomery, dout.as<Affine<F>>());
+    }
+  });
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaMemcpyAsync(h_out, dout.p, n * pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  dbase.release();
+  dscal.release();
+  dout.release();
+  return 0;
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------- NTT

@@ -88,8 +88,8 @@ int upload(cs_ctx* ctx, DevBuf& buf, const void* src, size_t bytes) {
 // CircomReduction::witness_map_from_matrices on the device.  Leaves h (n half shares) in pk->d_c.
 // d_pub / d_wit must already hold the inputs; masks (Rep3) in d_m1 / d_m2 or null.
 template <class Cfg>
-int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, bool have_m1, bool have_m2,
-                       cudaStream_t st) {
+int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint32_t* d_wit, bool have_m1,
+                       bool have_m2, cudaStream_t st) {
   typedef typename Cfg::FrP FrP;
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
   const int pub_comp = kind == CS_REP3 ? (party == 0 ? 0 : (party == 1 ? 1 : -1)) : 0;
@@ -99,10 +99,10 @@ int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, bool
   CS_TRY(pk->d_c.reserve((size_t)n * 32));
   // a = A w (+ promoted public rows, reduction.rs:104-113), b = B w   (evaluate_constraint)
   CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->a_rowptr.as<uint32_t>(), pk->a_col.as<uint32_t>(),
-            pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, pk->d_wit.as<uint32_t>(), batch,
+            pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch,
             pub_comp, (uint32_t)pk->nc, (uint32_t)pk->ni, n, pk->d_a.as<uint32_t>());
   CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->b_rowptr.as<uint32_t>(), pk->b_col.as<uint32_t>(),
-            pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, pk->d_wit.as<uint32_t>(), batch,
+            pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch,
             pub_comp, (uint32_t)pk->nc, 0u, n, pk->d_b.as<uint32_t>());
   unsigned blocks = ceil_div(n, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -139,7 +139,7 @@ int upload_inputs(cs_ctx* ctx, cs_groth16_pk* pk, int kind, const uint64_t* h_pu
                   const uint64_t* h_m1, const uint64_t* h_m2) {
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
   CS_TRY(upload(ctx, pk->d_pub, h_pub, pk->ni * 32));
-  CS_TRY(upload(ctx, pk->d_wit, h_wit, pk->nw * batch * 32));
+  if (h_wit) CS_TRY(upload(ctx, pk->d_wit, h_wit, pk->nw * batch * 32));
   if (kind == CS_REP3 && h_m1) CS_TRY(upload(ctx, pk->d_m1, h_m1, pk->n * 32));
   if (kind == CS_REP3 && h_m2) CS_TRY(upload(ctx, pk->d_m2, h_m2, pk->n * 32));
   return 0;
@@ -150,7 +150,7 @@ int upload_inputs(cs_ctx* ctx, cs_groth16_pk* pk, int kind, const uint64_t* h_pu
 // (add_assign_points_public_hs, mpc/rep3.rs:108-118).  Outputs are affine Montgomery points.
 template <class Cfg>
 int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint64_t* h_pub, const uint64_t* h_wit,
-                const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
+                const uint64_t* d_wit_in, const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
                 uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h) {
   typedef HostGroup<Cfg, 0> H1;
   typedef HostGroup<Cfg, 1> H2;
@@ -160,7 +160,8 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
   CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, h_m1, h_m2));
   // fork: A, B1, B2, L need only the witness; the witness map + H run on the main stream.
   CS_TRY(ctx_fork(ctx, 4));
-  const uint32_t* wit = pk->d_wit.as<uint32_t>();
+  // witness either uploaded from the host just above, or already resident in HBM (d_wit_in)
+  const uint32_t* wit = d_wit_in ? reinterpret_cast<const uint32_t*>(d_wit_in) : pk->d_wit.as<uint32_t>();
   const bool have_aux = pk->nw > 0;
   if (have_aux) {
     // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
@@ -169,7 +170,7 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
     CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1));
     CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
   }
-  CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+  CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
   CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
   CS_TRY(ctx_join(ctx, 4));
 
@@ -215,12 +216,13 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
 }
 
 template <class Cfg>
-int prove_plain_t(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* r,
-                  const uint64_t* s, uint64_t* out_a, uint64_t* out_b, uint64_t* out_c) {
+int prove_plain_t(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const uint64_t* h_wit,
+                  const uint64_t* d_wit, const uint64_t* r, const uint64_t* s, uint64_t* out_a, uint64_t* out_b,
+                  uint64_t* out_c) {
   typedef HostGroup<Cfg, 0> H1;
   typedef host::HFp<typename Cfg::FrP> HR;
   uint64_t a[12], b1[12], l[12], h[12];
-  CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, nullptr, nullptr, r, s, a, b1, out_b, l, h)));
+  CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, d_wit, nullptr, nullptr, r, s, a, b1, out_b, l, h)));
   // groth16.rs:296-322 with the plain driver: C = s*A + r*B1 - (r s)*delta1 + L + H
   HR rr, ss;
   memcpy(rr.l, r, sizeof(rr.l));
@@ -326,11 +328,13 @@ int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, i
   CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, h_m1, h_m2));
   switch (pk->curve) {
     case CS_BN254:
-      CS_TRY((witness_map_device<Bn254Cfg>(ctx, pk, kind, party, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+      CS_TRY((witness_map_device<Bn254Cfg>(ctx, pk, kind, party, pk->d_wit.as<uint32_t>(), h_m1 != nullptr,
+                                           h_m2 != nullptr, ctx->stream)));
       break;
 #if defined(CS_ENABLE_BLS12_381)
     case CS_BLS12_381:
-      CS_TRY((witness_map_device<Bls381Cfg>(ctx, pk, kind, party, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+      CS_TRY((witness_map_device<Bls381Cfg>(ctx, pk, kind, party, pk->d_wit.as<uint32_t>(), h_m1 != nullptr,
+                                            h_m2 != nullptr, ctx->stream)));
       break;
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");
@@ -345,9 +349,23 @@ int cs_groth16_prove_plain(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub
   if (!ctx || !pk || !h_pub || (pk->nw && !h_wit) || !r || !s || !out_a || !out_b || !out_c)
     return fail(CS_ERR_ARG, "cs_groth16_prove_plain: NULL argument");
   switch (pk->curve) {
-    case CS_BN254: return prove_plain_t<Bn254Cfg>(ctx, pk, h_pub, h_wit, r, s, out_a, out_b, out_c);
+    case CS_BN254: return prove_plain_t<Bn254Cfg>(ctx, pk, h_pub, h_wit, nullptr, r, s, out_a, out_b, out_c);
 #if defined(CS_ENABLE_BLS12_381)
-    case CS_BLS12_381: return prove_plain_t<Bls381Cfg>(ctx, pk, h_pub, h_wit, r, s, out_a, out_b, out_c);
+    case CS_BLS12_381: return prove_plain_t<Bls381Cfg>(ctx, pk, h_pub, h_wit, nullptr, r, s, out_a, out_b, out_c);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
+int cs_groth16_prove_plain_device(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const uint64_t* d_wit,
+                                  const uint64_t* r, const uint64_t* s, uint64_t* out_a, uint64_t* out_b,
+                                  uint64_t* out_c) {
+  if (!ctx || !pk || !h_pub || (pk->nw && !d_wit) || !r || !s || !out_a || !out_b || !out_c)
+    return fail(CS_ERR_ARG, "cs_groth16_prove_plain_device: NULL argument");
+  switch (pk->curve) {
+    case CS_BN254: return prove_plain_t<Bn254Cfg>(ctx, pk, h_pub, nullptr, d_wit, r, s, out_a, out_b, out_c);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: return prove_plain_t<Bls381Cfg>(ctx, pk, h_pub, nullptr, d_wit, r, s, out_a, out_b, out_c);
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");
   }
@@ -364,11 +382,11 @@ int cs_groth16_rep3_local(cs_ctx* ctx, cs_groth16_pk* pk, int party, const uint6
   // to_half_share = the `a` component (mpc/rep3.rs:120-122): first Fr of the share
   switch (pk->curve) {
     case CS_BN254:
-      return local_phase<Bn254Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, h_m1, h_m2, r_share, s_share,
+      return local_phase<Bn254Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, nullptr, h_m1, h_m2, r_share, s_share,
                                    out_g_a, out_g1_b, out_g2_b, out_l, out_h);
 #if defined(CS_ENABLE_BLS12_381)
     case CS_BLS12_381:
-      return local_phase<Bls381Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, h_m1, h_m2, r_share, s_share,
+      return local_phase<Bls381Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, nullptr, h_m1, h_m2, r_share, s_share,
                                     out_g_a, out_g1_b, out_g2_b, out_l, out_h);
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");

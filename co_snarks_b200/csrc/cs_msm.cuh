@@ -263,6 +263,35 @@ CS_GLOBAL void __launch_bounds__(128) k_msm_precompute(Affine<F>* __restrict__ t
   }
 }
 
+// --------------------------------------------------------------------------- fixed-base batch mul
+// out[i] = scalars[i] * base  (affine).  Used to synthesise proving keys / SRS (a trusted setup is n
+// fixed-base multiplications); off the per-proof path.
+template <class F, class FrP>
+CS_GLOBAL void __launch_bounds__(128) k_fixed_base_mul(const Affine<F>* __restrict__ base,
+                                                       const uint32_t* __restrict__ scalars, uint32_t n,
+                                                       int mont, Affine<F>* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<FrP> s;
+  const uint4* src = reinterpret_cast<const uint4*>(scalars) + (size_t)i * (FrP::N / 4);
+  CS_UNROLL
+  for (int k = 0; k < FrP::N / 4; k++) {
+    uint4 v = src[k];
+    s.l[4 * k] = v.x; s.l[4 * k + 1] = v.y; s.l[4 * k + 2] = v.z; s.l[4 * k + 3] = v.w;
+  }
+  if (mont) s = s.from_mont();
+  uint32_t lim[FrP::N];
+  CS_UNROLL
+  for (int k = 0; k < FrP::N; k++) lim[k] = s.l[k];
+  Affine<F> b = base[0];
+  Xyzz<F> acc = Xyzz<F>::inf();
+  for (int bit = FrP::N * 32 - 1; bit >= 0; bit--) {
+    acc = dbl_xyzz(acc);
+    if ((lim[bit >> 5] >> (bit & 31)) & 1) madd(acc, b, false);
+  }
+  out[i] = to_affine(acc);
+}
+
 // --------------------------------------------------------------------------- host driver
 struct MsmShape {
   uint32_t c, W, B;  // window bits, windows, buckets (1..B)
@@ -285,11 +314,24 @@ static inline uint32_t msm_auto_window(size_t n) {
   return (uint32_t)c;
 }
 
+constexpr int MSM_NSTAGE = 5;  // digits | scan+scatter | accum0 | accum1+2 | reduce+final
 struct MsmWorkspace {
   DevBuf dig, sorted, meta, part0, part1, bucket, red, scal, result;
   void* h_result = nullptr;  // pinned, holds one Xyzz
   size_t h_result_cap = 0;
+  bool profile = false;      // record CUDA events at the stage boundaries (bench.py roofline)
+  cudaEvent_t ev[MSM_NSTAGE + 1] = {};
+  int mark(int i, cudaStream_t st) {
+    if (!profile) return 0;
+    if (!ev[i]) CS_CUDA(cudaEventCreateWithFlags(&ev[i], 0));
+    CS_CUDA(cudaEventRecord(ev[i], st));
+    return 0;
+  }
   void release() {
+    for (int i = 0; i <= MSM_NSTAGE; i++) {
+      if (ev[i]) cudaEventDestroy(ev[i]);
+      ev[i] = nullptr;
+    }
     dig.release(); sorted.release(); meta.release(); part0.release(); part1.release();
     bucket.release(); red.release(); scal.release(); result.release();
     if (h_result) cudaFreeHost(h_result);
@@ -332,22 +374,28 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, uint32_t nbases, MsmSh
   uint32_t* start = cursor + nb1;
   uint32_t* sstart0 = start + nb1 + 1;
   uint32_t* sstart1 = sstart0 + nb1 + 1;
+  CS_TRY(ws.mark(0, st));
   CS_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nb1 * 4, st));
   CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W,
             ws.dig.as<uint32_t>(), count);
+  CS_TRY(ws.mark(1, st));
   CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, start, sstart0, sstart1);
   CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
             offset, start, cursor, ws.sorted.as<uint32_t>());
+  CS_TRY(ws.mark(2, st));
   CS_LAUNCH(k_msm_accum0<F>, ceil_div(max_s0, 128), 128, 0, st, table, ws.sorted.as<uint32_t>(), count,
             start, sstart0, nb1, ws.part0.as<Xyzz<F>>());
+  CS_TRY(ws.mark(3, st));
   CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,
             nb1, ws.part1.as<Xyzz<F>>());
   CS_LAUNCH(k_msm_accum2<F>, ceil_div(nb1, 128), 128, 0, st, ws.part1.as<Xyzz<F>>(), sstart1, nb1,
             ws.bucket.as<Xyzz<F>>());
+  CS_TRY(ws.mark(4, st));
   CS_LAUNCH(k_msm_reduce_seg<F>, ceil_div(nseg, 128), 128, 0, st, ws.bucket.as<Xyzz<F>>(), sh.B, L,
             ws.red.as<Xyzz<F>>());
   CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
                  ws.result.as<Xyzz<F>>());
+  CS_TRY(ws.mark(5, st));
   CS_CUDA(cudaMemcpyAsync(ws.h_result, ws.result.p, sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
   CS_CUDA(cudaGetLastError());
   return 0;

@@ -84,6 +84,18 @@ int cs_msm(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* h_
 int cs_msm_device(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* d_scalars, size_t n,
                   int scalars_montgomery, uint64_t* h_out_affine_mont, int* out_is_infinity);
 
+/* Measurement hooks (bench.py): when enabled, cs_msm / cs_msm_device record CUDA events at the five stage
+ * boundaries of the MSM on its launching stream; cs_msm_stage_ms returns the last MSM's stage durations
+ * {digits+histogram, scan+scatter, bucket accumulation (k_msm_accum0), partial folding, bucket reduction}. */
+int cs_msm_profile(cs_ctx* ctx, int enable);
+int cs_msm_stage_ms(cs_ctx* ctx, float* out_ms5);
+
+/* out[i] = scalars[i] * base (affine Montgomery), i < n.  No counterpart on the reference's prover path:
+ * it is the fixed-base multiplication a Groth16/KZG setup performs, provided so that tests and bench.py
+ * can synthesise proving keys of any size on the device. */
+int cs_fixed_base_mul(cs_ctx* ctx, cs_curve curve, cs_group group, const uint64_t* h_base_affine_mont,
+                      const uint64_t* h_scalars, size_t n, int scalars_montgomery, uint64_t* h_out_points);
+
 /* ---- NTT: taceo_ark_algebra::fft::{Domain, bit_reverse} ---------------------------------------------
  * Domain::with_group_gen(size, gen) (co-groth16/src/groth16/reduction.rs:93), ::new (:249), size()
  * (:251), ifft_in_to_out / fft_out_to_in (:141-175, :270-327), bit_reverse (:58, :328).
@@ -160,6 +172,12 @@ int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, i
 int cs_groth16_prove_plain(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_public_inputs,
                            const uint64_t* h_witness, const uint64_t* h_r_mont, const uint64_t* h_s_mont,
                            uint64_t* out_a, uint64_t* out_b, uint64_t* out_c);
+
+/* Same with the private witness already resident in device memory (e.g. left there by a GPU witness
+ * extension); public inputs stay on the host (they feed the host-side public-input MSM). */
+int cs_groth16_prove_plain_device(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_public_inputs,
+                                  const uint64_t* d_witness, const uint64_t* h_r_mont, const uint64_t* h_s_mont,
+                                  uint64_t* out_a, uint64_t* out_b, uint64_t* out_c);
 
 /* One party's LOCAL part of Rep3CoGroth16::prove up to the first network round
  * (groth16.rs:151-163 + the rayon_join5 block :227-294): witness map, then the five MSMs.

@@ -1,0 +1,288 @@
+"""Parity checks shared by the GPU tests (-m gpu, through libcosnarks_gpu.so) and the CPU-emulation
+tests (tests/emu build of the same kernels).  Every check compares the C-ABI result with the oracle
+or with a committed golden vector; integer work => bit-exact equality."""
+import random
+
+import numpy as np
+
+from co_snarks_b200 import binding as B
+from helpers import Conv, golden_groth16, gp1, ih, load_golden, make_key
+from oracle import groth16 as OG
+from oracle import ntt as ON
+from oracle.ec import g1 as og1, g2 as og2
+from oracle.fields import BN254, groth16_roots_of_unity
+from oracle.pairing_bn254 import groth16_verify
+
+
+def check_field_ops(ctx, n=257, seed=1):
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    a = [rng.randrange(r) for _ in range(n)]
+    b = [rng.randrange(r) for _ in range(n)]
+    # edge values
+    edge = [0, 1, r - 1, r - 2, (r - 1) // 2, 2 ** 253, 2 ** 128 - 1]
+    for i, e in enumerate(edge):
+        a[i] = e
+        b[len(edge) - 1 - i] = e
+    da, db = ctx.to_device(cv.fr(a)), ctx.to_device(cv.fr(b))
+    do = ctx.alloc(n * 32)
+    lib = ctx.lib
+    for name, f in (("mul", lambda x, y: x * y % r), ("add", lambda x, y: (x + y) % r), ("sub", lambda x, y: (x - y) % r)):
+        ctx._check(getattr(lib, "cs_vec_" + name)(ctx.h, cv.id, da, db, do, n))
+        got = cv.fr_back(ctx.d2h(do, (n, 4)))
+        assert got == [f(x, y) for x, y in zip(a, b)], "cs_vec_" + name
+    # Montgomery conversion helpers and canonical round trip
+    can = B.ints_to_limbs(a, 4)
+    mont = np.zeros_like(can)
+    ctx._check(lib.cs_fr_to_mont(cv.id, B._ptr(can), B._ptr(mont), n))
+    assert (mont == cv.fr(a)).all()
+    back = np.zeros_like(can)
+    ctx._check(lib.cs_fr_from_mont(cv.id, B._ptr(mont), B._ptr(back), n))
+    assert (back == can).all()
+    for d in (da, db, do):
+        ctx.free(d)
+
+
+def check_share_kernels(ctx, n=300, seed=2):
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    lib = ctx.lib
+    a = [(rng.randrange(r), rng.randrange(r)) for _ in range(n)]
+    b = [(rng.randrange(r), rng.randrange(r)) for _ in range(n)]
+    mask = [rng.randrange(r) for _ in range(n)]
+    da = ctx.to_device(cv.fr([x for s in a for x in s]))
+    db = ctx.to_device(cv.fr([x for s in b for x in s]))
+    dm = ctx.to_device(cv.fr(mask))
+    do = ctx.alloc(n * 32)
+    ctx._check(lib.cs_rep3_local_mul_vec(ctx.h, cv.id, da, db, dm, do, n))
+    assert cv.fr_back(ctx.d2h(do, (n, 4))) == OG.local_mul_vec_rep3(a, b, mask, r)
+    ctx._check(lib.cs_rep3_local_mul_vec(ctx.h, cv.id, da, db, None, do, n))
+    assert cv.fr_back(ctx.d2h(do, (n, 4))) == OG.local_mul_vec_rep3(a, b, [0] * n, r)
+    # distribute_powers on shares (batch 2) and plain (batch 1)
+    tab = [rng.randrange(r) for _ in range(n)]
+    dt = ctx.to_device(cv.fr(tab))
+    ctx._check(lib.cs_vec_scale_table(ctx.h, cv.id, da, dt, n, 2))
+    got = cv.fr_back(ctx.d2h(da, (2 * n, 4)))
+    assert got == [x * t % r for s, t in zip(a, tab) for x in s]
+    ctx._check(lib.cs_vec_scale_table(ctx.h, cv.id, dm, dt, n, 1))
+    assert cv.fr_back(ctx.d2h(dm, (n, 4))) == [x * t % r for x, t in zip(mask, tab)]
+    # rep3 -> shamir bridge
+    ca, cb = rng.randrange(r), rng.randrange(r)
+    ctx._check(lib.cs_rep3_to_shamir(ctx.h, cv.id, db, B._ptr(cv.fr([ca])), B._ptr(cv.fr([cb])), do, n))
+    assert cv.fr_back(ctx.d2h(do, (n, 4))) == [(ca * x + cb * y) % r for x, y in b]
+    for d in (da, db, dm, do, dt):
+        ctx.free(d)
+
+
+def check_roots(ctx):
+    cv = Conv("bn254")
+    for power in (0, 1, 2, 8, 20, 27, 28):
+        gen, shift = ctx.roots_of_unity(cv.id, power)
+        eg, es = groth16_roots_of_unity(cv.r, power)
+        assert cv.fr_back(gen) == [eg] and cv.fr_back(shift) == [es], power
+
+
+def check_ntt(ctx, log_sizes, seed=3):
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    for lg in log_sizes:
+        n = 1 << lg
+        g, _ = groth16_roots_of_unity(r, lg)
+        dom = ctx.domain(cv.id, lg, cv.fr([g]))
+        assert dom.size() == n
+        for batch in (1, 2):
+            v = [rng.randrange(r) for _ in range(n * batch)]
+            arr = cv.fr(v)
+            dom.ifft_in_to_out(arr, batch)
+            exp = [None] * (n * batch)
+            for c in range(batch):
+                exp[c::batch] = ON.ifft_in_to_out(v[c::batch], g, r)
+            assert cv.fr_back(arr) == exp, ("ifft_in_to_out", lg, batch)
+            dom.fft_out_to_in(arr, batch)
+            assert cv.fr_back(arr) == v, ("fft_out_to_in", lg, batch)
+        # bit_reverse
+        v = [rng.randrange(r) for _ in range(n)]
+        d = ctx.to_device(cv.fr(v))
+        ctx._check(ctx.lib.cs_bit_reverse(ctx.h, cv.id, d, lg, 1))
+        assert cv.fr_back(ctx.d2h(d, (n, 4))) == ON.bit_reverse_perm(v)
+        ctx.free(d)
+        dom.free()
+
+
+def _edge_case_inputs(G, gen, n, r, rng):
+    pts = [G.mul(gen, rng.randrange(1, r)) for _ in range(n)]
+    sc = [rng.randrange(r) for _ in range(n)]
+    if n >= 12:
+        pts[5] = None           # infinity base
+        pts[7] = pts[6]         # duplicate base, equal scalars -> P + P inside a bucket
+        pts[9] = G.neg(pts[8])  # negated base, equal scalars -> P + (-P)
+        sc[0], sc[1], sc[2] = 0, 1, r - 1
+        sc[6] = sc[7] = 12345
+        sc[8] = sc[9] = 777
+    return pts, sc
+
+
+def check_msm(ctx, group, n, window_bits=(0,), seed=4):
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed + group)
+    G = og1(BN254) if group == 0 else og2(BN254)
+    gen = BN254.g1 if group == 0 else BN254.g2
+    to_arr = cv.g1 if group == 0 else cv.g2
+    to_pt = cv.pt1 if group == 0 else cv.pt2
+    pts, sc = _edge_case_inputs(G, gen, n, r, rng)
+    exp = G.msm(pts, sc)
+    for wb in window_bits:
+        bases = ctx.bases_upload(cv.id, group, to_arr(pts), wb)
+        assert len(bases) == n
+        out, inf = ctx.msm(bases, cv.fr(sc), montgomery=True)      # msm_unchecked(&[Fr])
+        assert to_pt(out) == exp and inf == (exp is None), ("msm mont", group, wb)
+        out, inf = ctx.msm(bases, cv.fr_canonical(sc), montgomery=False)  # msm_bigint
+        assert to_pt(out) == exp, ("msm bigint", group, wb)
+        # sub-slice (query[1 + pub ..]) and ragged n
+        for off, cnt in ((1, n - 1), (3, 1), (n // 3, n // 2)):
+            out, inf = ctx.msm(bases, cv.fr(sc[off:off + cnt]), offset=off)
+            assert to_pt(out) == G.msm(pts[off:off + cnt], sc[off:off + cnt]), ("slice", off, cnt)
+        # empty input -> identity
+        out, inf = ctx.msm(bases, np.zeros((0, 4), dtype=np.uint64))
+        assert inf and to_pt(out) is None
+        # all-zero scalars -> identity
+        out, inf = ctx.msm(bases, cv.fr([0] * n))
+        assert inf and to_pt(out) is None
+        # heavy skew: every scalar equal (one bucket per window takes all points)
+        out, inf = ctx.msm(bases, cv.fr([3] * n))
+        assert to_pt(out) == G.msm(pts, [3] * n)
+        if n >= 12:
+            out, inf = ctx.msm(bases, cv.fr([5, 5]), offset=8)  # P + (-P)
+            assert inf
+        bases.free()
+
+
+def check_msm_crs(ctx):
+    """MSM over real Ignition CRS points (co-noir-common/src/crs/bn254_g1.dat, first 1024)."""
+    cv = Conv("bn254")
+    g = load_golden("crs_bn254_g1_first1024")
+    pts = [gp1(P) for P in g["points"]]
+    assert pts[0] == (1, 2)
+    rng = random.Random(11)
+    sc = [rng.randrange(cv.r) for _ in pts]
+    bases = ctx.bases_upload(cv.id, 0, cv.g1(pts))
+    out, _ = ctx.msm(bases, cv.fr(sc))
+    assert cv.pt1(out) == og1(BN254).msm(pts, sc)
+    bases.free()
+
+
+def check_fixed_base_mul(ctx, n=40):
+    cv = Conv("bn254")
+    rng = random.Random(6)
+    sc = [rng.randrange(cv.r) for _ in range(n)]
+    sc[0], sc[1] = 0, 1
+    for group, G, gen, to_arr, to_pt in ((0, og1(BN254), BN254.g1, cv.g1, cv.pt1), (1, og2(BN254), BN254.g2, cv.g2, cv.pt2)):
+        out = ctx.fixed_base_mul(cv.id, group, to_arr([gen])[0], cv.fr(sc))
+        assert [to_pt(o) for o in out] == [G.mul(gen, s) for s in sc]
+
+
+def check_plonk_round1_kat(ctx, curve="bn254", name="multiplier2"):
+    """GPU iNTT + MSM against the REFERENCE'S known answers (co-plonk/src/round1.rs:351-371)."""
+    g = load_golden("plonk_round1_%s_%s" % (curve, name))
+    cv = Conv(curve)
+    n = g["domain_size"]
+    lg = n.bit_length() - 1
+    gen = ih(g["group_gen"])
+    dom = ctx.domain(cv.id, lg, cv.fr([gen]))
+    p_tau = [gp1(P) for P in g["p_tau"]]
+    bases = ctx.bases_upload(cv.id, 0, cv.g1(p_tau))
+    for wire, exp in zip(g["wires"], g["expected_commitments"]):
+        buf = [ih(x) for x in wire["buffer"]]
+        # ifft (natural -> natural) = ifft_in_to_out followed by bit_reverse
+        d = ctx.to_device(cv.fr(buf))
+        dom.ifft_in_to_out(d, 1)
+        ctx._check(ctx.lib.cs_bit_reverse(ctx.h, cv.id, d, lg, 1))
+        poly = cv.fr_back(ctx.d2h(d, (n, 4)))
+        ctx.free(d)
+        assert poly == [ih(x) for x in wire["poly"]]
+        blinded = [ih(x) for x in wire["blinded"]]
+        out, _ = ctx.msm(bases, cv.fr(blinded), n=len(blinded))
+        assert cv.pt1(out) == gp1(exp), "commitment differs from the reference KAT"
+    bases.free()
+    dom.free()
+
+
+def check_groth16_fixture(ctx, name, rep3=True, window_bits=0):
+    cv = Conv("bn254")
+    r = cv.r
+    z, m, w, g = golden_groth16(name)
+    ni = m["num_instance_variables"]
+    pk = make_key(ctx, cv, z, m, window_bits)
+    assert pk.domain_size() == g["domain_size"]
+    pub, wit = cv.fr(w[:ni]), cv.fr(w[ni:])
+    h_exp = [ih(x) for x in g["h"]]
+    assert cv.fr_back(pk.witness_map(pub, wit)) == h_exp, "witness map"
+    vk = OG.vk_from_zkey(z)
+    public = [ih(x) for x in g["public"]]
+    for pr in g["oracle_proofs"]:
+        A, Bp, Cp = pk.prove_plain(pub, wit, cv.fr([ih(pr["r"])]), cv.fr([ih(pr["s"])]))
+        proof = (cv.pt1(A), cv.pt2(Bp), cv.pt1(Cp))
+        from oracle.formats import proof_to_json
+        assert proof_to_json(*proof) == pr["json"], "proof bytes differ from the oracle for fixed (r, s)"
+        assert groth16_verify(vk, public, proof)
+    if rep3:
+        check_groth16_rep3_local(ctx, pk, cv, z, m, w, h_exp, vk, public)
+    pk.free()
+
+
+def check_groth16_rep3_local(ctx, pk, cv, z, m, w, h_exp, vk, public, seed=5):
+    """Three parties' local phases on one context, then the reference's two network legs emulated in
+    the test (groth16.rs:296-337): the opened proof must equal the plain proof for r = sum r_i.a."""
+    r = cv.r
+    rng = random.Random(seed)
+    ni = m["num_instance_variables"]
+    n = pk.domain_size()
+    lib = ctx.lib
+    wsh = OG.share_rep3(w[ni:], r, rng)
+
+    def zero_masks(k):
+        prf = [[rng.randrange(r) for _ in range(k)] for _ in range(3)]
+        return [[(prf[i][j] - prf[(i + 2) % 3][j]) % r for j in range(k)] for i in range(3)]
+
+    m1, m2 = zero_masks(n), zero_masks(n)
+    rsh = OG.share_rep3([rng.randrange(r)], r, rng)
+    ssh = OG.share_rep3([rng.randrange(r)], r, rng)
+    rs_mask = zero_masks(1)
+    pub = cv.fr(w[:ni])
+    loc = []
+    h_tot = [0] * n
+    for i in range(3):
+        sh = cv.fr([x for ab in wsh[i] for x in ab])
+        hh = pk.witness_map(pub, sh, B.CS_REP3, i, cv.fr(m1[i]), cv.fr(m2[i]))
+        h_i = cv.fr_back(hh)
+        assert h_i == OG.witness_map_rep3(i, m, w[:ni], wsh[i], m1[i], m2[i], r, 28)
+        h_tot = [(x + y) % r for x, y in zip(h_tot, h_i)]
+        loc.append(pk.rep3_local(i, pub, sh, cv.fr(m1[i]), cv.fr(m2[i]), cv.fr(list(rsh[i][0])), cv.fr(list(ssh[i][0]))))
+    assert h_tot == h_exp
+    G1, G2 = og1(BN254), og2(BN254)
+    # open_half_point(A)
+    A = None
+    for i in range(3):
+        A = G1.add(A, cv.pt1(loc[i][0]))
+    gC = []
+    for i in range(3):
+        pa, pb = cv.pt1(loc[i][1]), cv.pt1(loc[(i + 2) % 3][1])
+        ra, rb = rsh[i][0]
+        r_b1 = G1.add(G1.add(G1.mul(pa, ra), G1.mul(pa, rb)), G1.mul(pb, ra))  # EC masks omitted: they cancel
+        rs_i = OG.local_mul_vec_rep3([rsh[i][0]], [ssh[i][0]], [rs_mask[i][0]], r)[0]
+        c = G1.add(G1.mul(A, ssh[i][0][0]), r_b1)
+        c = G1.add(c, G1.neg(G1.mul(z["delta_g1"], rs_i)))
+        c = G1.add(G1.add(c, cv.pt1(loc[i][3])), cv.pt1(loc[i][4]))
+        gC.append(c)
+    C, Bp = None, None
+    for i in range(3):
+        C = G1.add(C, gC[i])
+        Bp = G2.add(Bp, cv.pt2(loc[i][2]))
+    r_tot = sum(x[0][0] for x in rsh) % r
+    s_tot = sum(x[0][0] for x in ssh) % r
+    assert (A, Bp, C) == OG.prove_plain(z, m, w, r_tot, s_tot)
+    assert groth16_verify(vk, public, (A, Bp, C))

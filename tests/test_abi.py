@@ -1,0 +1,67 @@
+"""CPU-only: the C-ABI library loads, exports every symbol include/cosnarks_gpu.h declares, binds them in
+co_snarks_b200/binding.py, and FAILS LOUDLY without a GPU (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+from co_snarks_b200 import binding as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cosnarks_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cs_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_and_library_exports_every_symbol():
+    lib = B.load()
+    syms = header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), "libcosnarks_gpu.so does not export " + s
+        assert s in B.SIGNATURES, "binding.py has no signature for " + s
+    for s in B.SIGNATURES:
+        assert s in syms, "binding.py binds %s which the header does not declare" % s
+
+
+def test_version_string():
+    lib = B.load()
+    assert b"sm_100a" in lib.cs_version()
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(B.CsError) as e:
+        B.Context(0)
+    assert "no CUDA device" in str(e.value) or "CUDA error" in str(e.value)
+
+
+def test_host_helpers_work_without_gpu():
+    """Single-point helpers and Montgomery conversion run on the host inside the library."""
+    from helpers import Conv
+    from oracle.ec import g1
+    from oracle.fields import BN254, groth16_roots_of_unity
+    lib = B.load()
+    cv = Conv("bn254")
+    G = g1(BN254)
+    P = G.mul(BN254.g1, 1234567)
+    k = 987654321987654321
+    out = B.point_scalar_mul(lib, cv.id, B.CS_G1, cv.g1([P])[0], cv.fr([k])[0])
+    assert cv.pt1(out) == G.mul(P, k)
+    out = B.point_add(lib, cv.id, B.CS_G1, cv.g1([P])[0], cv.g1([G.neg(P)])[0])
+    assert cv.pt1(out) is None
+    out = B.point_add(lib, cv.id, B.CS_G1, cv.g1([P])[0], cv.g1([P])[0])
+    assert cv.pt1(out) == G.mul(P, 2)
+    import numpy as np
+    gen = np.zeros(4, dtype=np.uint64)
+    shift = np.zeros(4, dtype=np.uint64)
+    assert lib.cs_groth16_roots_of_unity(cv.id, 20, B._ptr(gen), B._ptr(shift)) == 0
+    eg, es = groth16_roots_of_unity(cv.r, 20)
+    assert cv.fr_back(gen) == [eg] and cv.fr_back(shift) == [es]
+    assert lib.cs_groth16_roots_of_unity(cv.id, 29, B._ptr(gen), B._ptr(shift)) != 0
+    assert b"Polynomial Degree too large" in lib.cs_last_error()

@@ -1,0 +1,40 @@
+"""CPU-only: the exact device algorithms (csrc/*.cu compiled by tests/emu with -DCS_EMU) against the
+oracle and the golden vectors, at sizes that finish in seconds.  This is host-side verification of
+the kernels' logic; the GPU parity tests proper are tests/test_gpu_parity.py."""
+import kernel_checks as K
+
+
+def test_emu_field_ops(emu_ctx):
+    K.check_field_ops(emu_ctx, n=97)
+
+
+def test_emu_share_kernels(emu_ctx):
+    K.check_share_kernels(emu_ctx, n=50)
+
+
+def test_emu_roots(emu_ctx):
+    K.check_roots(emu_ctx)
+
+
+def test_emu_ntt(emu_ctx):
+    K.check_ntt(emu_ctx, [0, 1, 2, 5, 11])
+
+
+def test_emu_msm_g1(emu_ctx):
+    K.check_msm(emu_ctx, 0, 120, window_bits=(0, 7))
+
+
+def test_emu_msm_g2(emu_ctx):
+    K.check_msm(emu_ctx, 1, 40, window_bits=(0,))
+
+
+def test_emu_fixed_base_mul(emu_ctx):
+    K.check_fixed_base_mul(emu_ctx, n=6)
+
+
+def test_emu_plonk_round1_kat(emu_ctx):
+    K.check_plonk_round1_kat(emu_ctx)
+
+
+def test_emu_groth16_multiplier2(emu_ctx):
+    K.check_groth16_fixture(emu_ctx, "multiplier2")

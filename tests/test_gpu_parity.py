@@ -1,0 +1,59 @@
+"""GPU parity tests (run with -m gpu on a B200 via gpurun): libcosnarks_gpu.so through the C ABI against
+the oracle / golden vectors.  Bit-exact: all arithmetic is integer."""
+import pytest
+
+import kernel_checks as K
+
+pytestmark = pytest.mark.gpu
+
+
+def test_field_ops(gpu_ctx):
+    K.check_field_ops(gpu_ctx, n=4099)
+
+
+def test_share_kernels(gpu_ctx):
+    K.check_share_kernels(gpu_ctx, n=3001)
+
+
+def test_roots(gpu_ctx):
+    K.check_roots(gpu_ctx)
+
+
+def test_ntt_small(gpu_ctx):
+    K.check_ntt(gpu_ctx, [0, 1, 2, 3, 7, 10, 11])
+
+
+def test_ntt_multi_pass(gpu_ctx):
+    K.check_ntt(gpu_ctx, [13, 14])
+
+
+def test_msm_g1(gpu_ctx):
+    K.check_msm(gpu_ctx, 0, 1500, window_bits=(0, 5, 11))
+
+
+def test_msm_g1_tiny(gpu_ctx):
+    K.check_msm(gpu_ctx, 0, 3, window_bits=(0,))
+
+
+def test_msm_g2(gpu_ctx):
+    K.check_msm(gpu_ctx, 1, 300, window_bits=(0, 8))
+
+
+def test_msm_crs_points(gpu_ctx):
+    K.check_msm_crs(gpu_ctx)
+
+
+def test_fixed_base_mul(gpu_ctx):
+    K.check_fixed_base_mul(gpu_ctx, n=70)
+
+
+def test_plonk_round1_kat_bn254(gpu_ctx):
+    K.check_plonk_round1_kat(gpu_ctx)
+
+
+def test_groth16_multiplier2(gpu_ctx):
+    K.check_groth16_fixture(gpu_ctx, "multiplier2")
+
+
+def test_groth16_poseidon(gpu_ctx):
+    K.check_groth16_fixture(gpu_ctx, "poseidon")
