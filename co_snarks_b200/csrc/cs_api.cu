@@ -184,6 +184,9 @@ int bases_upload_t(cs_ctx* ctx, const uint64_t* h_points, size_t n, int window_b
   if (total >= (1ull << 31)) return fail(CS_ERR_LIMIT, "cs_bases_upload: W*n = %zu exceeds 2^31", total);
   CS_TRY(b->table.reserve(total * sizeof(Affine<F>)));
   CS_CUDA(cudaMemcpyAsync(b->table.p, h_points, n * sizeof(Affine<F>), cudaMemcpyHostToDevice, ctx->stream));
+  CS_TRY(b->infmask.reserve(((n + 31) / 32) * 4));
+  CS_LAUNCH(k_msm_infmask<F>, ceil_div((n + 31) / 32, 128), 128, 0, ctx->stream, b->table.as<Affine<F>>(), (uint32_t)n,
+            b->infmask.as<uint32_t>());
   CS_LAUNCH(k_msm_precompute<F>, ceil_div(n, 128), 128, 0, ctx->stream, b->table.as<Affine<F>>(), (uint32_t)n,
             b->sh.c, b->sh.W);
   CS_CUDA(cudaGetLastError());
@@ -195,7 +198,7 @@ template <class Cfg, int G>
 int msm_enqueue_t(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,
                   const uint32_t* d_scalars, unsigned sstride, size_t n, int mont) {
   typedef typename GroupOf<Cfg, G>::F F;
-  return msm_enqueue<F, typename Cfg::FrP>(ctx->msm_ws[slot], b->table.as<Affine<F>>(), (uint32_t)b->n, b->sh,
+  return msm_enqueue<F, typename Cfg::FrP>(ctx->msm_ws[slot], b->table.as<Affine<F>>(), b->infmask.as<uint32_t>(), (uint32_t)b->n, b->sh,
                                            (uint32_t)offset, d_scalars, sstride, (uint32_t)n, mont, st);
 }
 
@@ -249,6 +252,7 @@ int cs_bases_upload(cs_ctx* ctx, cs_curve curve, cs_group group, const uint64_t*
 void cs_bases_free(cs_bases* b) {
   if (!b) return;
   b->table.release();
+  b->infmask.release();
   delete b;
 }
 

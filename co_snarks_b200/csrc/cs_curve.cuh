@@ -24,7 +24,9 @@ struct Fp2 {
   CS_D bool operator!=(const Fp2& b) const { return !(*this == b); }
   friend CS_D Fp2 operator+(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = a.c0 + b.c0; r.c1 = a.c1 + b.c1; return r; }
   friend CS_D Fp2 operator-(const Fp2& a, const Fp2& b) { Fp2 r; r.c0 = a.c0 - b.c0; r.c1 = a.c1 - b.c1; return r; }
-  friend CS_D Fp2 operator*(const Fp2& a, const Fp2& b) {
+  // mul / sqr are out-of-line (one copy per kernel) to keep the G2 point formulas in the I-cache.
+  friend CS_D Fp2 operator*(const Fp2& a, const Fp2& b) { return mul_ool(a, b); }
+  static CS_DN Fp2 mul_ool(Fp2 a, Fp2 b) {
     // Karatsuba: 3 base multiplications
     F v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
     Fp2 r;
@@ -32,11 +34,12 @@ struct Fp2 {
     r.c0 = v0 - v1;
     return r;
   }
-  CS_D Fp2 sqr() const {
+  CS_D Fp2 sqr() const { return sqr_ool(*this); }
+  static CS_DN Fp2 sqr_ool(Fp2 a) {
     // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u
     Fp2 r;
-    F t = c0 * c1;
-    r.c0 = (c0 + c1) * (c0 - c1);
+    F t = a.c0 * a.c1;
+    r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
     r.c1 = t + t;
     return r;
   }

@@ -128,7 +128,11 @@ struct Fp {
   CS_D Fp neg() const { return is_zero() ? *this : (zero() - *this); }
   CS_D Fp dbl() const { return *this + *this; }
 
-  friend CS_D Fp operator*(const Fp& a, const Fp& b) {
+  // Out-of-line on purpose: one ~230-instruction copy per kernel keeps the point formulas (10-42
+  // multiplications each) inside the instruction cache; operands travel by value in registers.
+  friend CS_D Fp operator*(const Fp& a, const Fp& b) { return mul_ool(a, b); }
+  static CS_DN Fp mul_ool(Fp a, Fp b) { return mul_inline(a, b); }
+  static CS_D Fp mul_inline(const Fp& a, const Fp& b) {
     uint32_t even[N], odd[N];
     mad_n_redc<P, true>(even, odd, a.l, b.l[0]);
     mad_n_redc<P, false>(odd, even, a.l, b.l[1]);

@@ -59,7 +59,8 @@ struct cs_bases {
   int curve = 0, group = 0;
   size_t n = 0;
   cs::MsmShape sh{};
-  cs::DevBuf table;  // W * n affine points
+  cs::DevBuf table;    // W * n affine points
+  cs::DevBuf infmask;  // 1 bit per base: point at infinity
 };
 
 struct cs_domain {

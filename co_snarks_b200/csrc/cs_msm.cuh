@@ -27,9 +27,16 @@ constexpr unsigned MSM_SIGN = 0x80000000u;
 // One thread per scalar: optional Montgomery -> canonical, signed c-bit recoding, histogram.
 template <class FrP>
 CS_GLOBAL void k_msm_digits(const uint32_t* __restrict__ scalars, uint32_t sstride, uint32_t n, int mont,
-                            uint32_t c, uint32_t W, uint32_t* __restrict__ dig, uint32_t* __restrict__ count) {
+                            uint32_t c, uint32_t W, const uint32_t* __restrict__ infmask, uint32_t offset,
+                            uint32_t* __restrict__ dig, uint32_t* __restrict__ count) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  // bases at infinity (sparse Groth16 B-queries: B_i(tau) = 0 for variables absent from B) contribute
+  // nothing: drop their entries before the sort instead of carrying them through the accumulation
+  if ((infmask[(offset + i) >> 5] >> ((offset + i) & 31)) & 1) {
+    for (uint32_t w = 0; w < W; w++) dig[(size_t)w * n + i] = 0;
+    return;
+  }
   Fp<FrP> s;
   // sstride = elements between consecutive scalars (2 reads the `a` component of Rep3 shares in place)
   const uint4* src = reinterpret_cast<const uint4*>(scalars) + (size_t)i * sstride * (FrP::N / 4);
@@ -64,6 +71,17 @@ CS_GLOBAL void k_msm_digits(const uint32_t* __restrict__ scalars, uint32_t sstri
     uint32_t b = out & ~MSM_SIGN;
     if (b) atomicAdd(&count[b], 1u);
   }
+}
+
+// infmask bit i = (base i is the point at infinity); one thread per 32 bases, once per upload
+template <class F>
+CS_GLOBAL void k_msm_infmask(const Affine<F>* __restrict__ table, uint32_t n, uint32_t* __restrict__ mask) {
+  uint32_t wd = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wd * 32 >= n) return;
+  uint32_t m = 0;
+  for (uint32_t k = 0; k < 32 && wd * 32 + k < n; k++)
+    if (table[wd * 32 + k].is_inf()) m |= 1u << k;
+  mask[wd] = m;
 }
 
 // --------------------------------------------------------------------------- scans (one block)
@@ -343,7 +361,8 @@ struct MsmWorkspace {
 // Enqueue one MSM on `st`.  d_scalars: device, n elements of Fr (8 x u32).  The XYZZ result lands in
 // ws.h_result (pinned) after the stream drains.
 template <class F, class FrP>
-int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, uint32_t nbases, MsmShape sh, uint32_t offset,
+int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmask, uint32_t nbases, MsmShape sh,
+                uint32_t offset,
                 const uint32_t* d_scalars, uint32_t sstride, uint32_t n, int mont, cudaStream_t st) {
   const uint32_t nb1 = sh.B + 1;
   const size_t nent = (size_t)sh.W * n;
@@ -376,7 +395,7 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, uint32_t nbases, MsmSh
   uint32_t* sstart1 = sstart0 + nb1 + 1;
   CS_TRY(ws.mark(0, st));
   CS_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nb1 * 4, st));
-  CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W,
+  CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W, infmask, offset,
             ws.dig.as<uint32_t>(), count);
   CS_TRY(ws.mark(1, st));
   CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, start, sstart0, sstart1);

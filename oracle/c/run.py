@@ -1,0 +1,181 @@
+"""ctypes front-end of oracle/c/liboracle.so (oracle; test infrastructure / CPU baseline only)."""
+import ctypes as C
+import os
+import subprocess
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "liboracle.so")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB):
+            subprocess.check_call(["make", "-s", "-C", HERE])
+        _lib = C.CDLL(LIB)
+        _lib.oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def msm(points_mont, scalars_mont, group=0):
+    L = lib()
+    points_mont = np.ascontiguousarray(points_mont, dtype=np.uint64)
+    scalars_mont = np.ascontiguousarray(scalars_mont, dtype=np.uint64)
+    out = np.zeros(8 if group == 0 else 16, dtype=np.uint64)
+    fn = L.oracle_msm_g1 if group == 0 else L.oracle_msm_g2
+    fn(_p(points_mont), _p(scalars_mont), C.c_size_t(4), C.c_size_t(scalars_mont.shape[0]), _p(out))
+    return out
+
+
+def ifft_in_to_out(data, lg, batch, gen_mont):
+    lib().oracle_ifft_in_to_out(_p(data), C.c_uint(lg), C.c_uint(batch), _p(np.ascontiguousarray(gen_mont)))
+    return data
+
+
+def fft_out_to_in(data, lg, batch, gen_mont):
+    lib().oracle_fft_out_to_in(_p(data), C.c_uint(lg), C.c_uint(batch), _p(np.ascontiguousarray(gen_mont)))
+    return data
+
+
+def key_desc(matrices_csr, points):
+    """Same descriptor as co_snarks_b200.binding.KeyDesc (include/cosnarks_gpu.h: cs_groth16_key_desc)."""
+    from co_snarks_b200.binding import KeyDesc, u32p, u64p  # type definition only
+    d = KeyDesc()
+    keep = []
+    d.curve = 0
+    d.num_constraints = matrices_csr["num_constraints"]
+    d.num_instance_variables = matrices_csr["num_instance_variables"]
+    d.num_witness_variables = matrices_csr["num_witness_variables"]
+    for name in ("a", "b"):
+        rp, col, coeff = (np.ascontiguousarray(x) for x in matrices_csr[name])
+        keep += [rp, col, coeff]
+        setattr(d, name + "_row_ptr", rp.ctypes.data_as(u32p))
+        setattr(d, name + "_col", col.ctypes.data_as(u32p))
+        setattr(d, name + "_coeff", coeff.ctypes.data_as(u64p))
+        setattr(d, name + "_nnz", col.shape[0])
+    for name in ("alpha_g1", "beta_g1", "beta_g2", "delta_g1", "delta_g2", "a_query", "b_g1_query", "b_g2_query",
+                 "l_query", "h_query"):
+        arr = np.ascontiguousarray(points[name], dtype=np.uint64)
+        keep.append(arr)
+        setattr(d, name, arr.ctypes.data_as(u64p))
+        if name.endswith("query"):
+            setattr(d, name + "_len", arr.shape[0])
+    return d, keep
+
+
+def witness_map(desc, kind, party, pub, wit, m1=None, m2=None):
+    n = 1
+    while n < desc.num_constraints + desc.num_instance_variables:
+        n <<= 1
+    out = np.zeros((n, 4), dtype=np.uint64)
+    rc = lib().oracle_witness_map(C.byref(desc), kind, party, _p(pub), _p(wit), _p(m1), _p(m2), _p(out))
+    assert rc == 0
+    return out
+
+
+def prove_plain(desc, pub, wit, r_m, s_m):
+    a = np.zeros(8, dtype=np.uint64)
+    b = np.zeros(16, dtype=np.uint64)
+    c = np.zeros(8, dtype=np.uint64)
+    rc = lib().oracle_groth16_prove_plain(C.byref(desc), _p(pub), _p(wit), _p(r_m), _p(s_m), _p(a), _p(b), _p(c))
+    assert rc == 0
+    return a, b, c
+
+
+# ------------------------------------------------------------------------------------------ bench legs
+def _workload(log_m):
+    """Synthetic R1CS + key for the CPU legs.  The CPU run needs no valid key (timing only), so the
+    query points are i*G built by repeated addition on the host -- no GPU involved."""
+    from workloads.synth_groth16 import make_r1cs, BN254_R, _fr
+    m = 1 << log_m
+    a_rows, b_rows, _, w = make_r1cs(m, 1)
+
+    def csr(rows):
+        rp = np.zeros(len(rows) + 1, dtype=np.uint32)
+        cols, cfs = [], []
+        for i, row in enumerate(rows):
+            for cf, v in row:
+                cols.append(v)
+                cfs.append(cf)
+            rp[i + 1] = len(cols)
+        return rp, np.array(cols, dtype=np.uint32), _fr(cfs)
+
+    mats = dict(num_constraints=m - 2, num_instance_variables=2, num_witness_variables=m - 2, a=csr(a_rows), b=csr(b_rows))
+    return mats, _fr(w[:2]), _fr(w[2:]), m
+
+
+def _points_by_addition(n, group):
+    """n distinct curve points (k*G, k = 1..n) produced by the C library's own msm of unit vectors would
+    be circular; instead use the affine chain P_{k+1} = P_k + G computed with python ints."""
+    from oracle.fields import BN254
+    from oracle.ec import g1, g2
+    from co_snarks_b200.binding import ints_to_limbs, to_mont_ints
+    G = g1(BN254) if group == 0 else g2(BN254)
+    gen = BN254.g1 if group == 0 else BN254.g2
+    # a short chain is tiled: distinctness of bases does not matter for CPU timing
+    base = []
+    P = gen
+    for _ in range(min(n, 2048)):
+        base.append(P)
+        P = G.add(P, gen)
+    flat = []
+    for P in base:
+        flat += [P[0], P[1]] if group == 0 else [P[0][0], P[0][1], P[1][0], P[1][1]]
+    arr = ints_to_limbs(to_mont_ints(flat, BN254.q, 4), 4).reshape(len(base), -1)
+    reps = (n + len(base) - 1) // len(base)
+    return np.tile(arr, (reps, 1))[:n].copy()
+
+
+def time_proof(log_m, steps=1, warmup=0):
+    mats, pub, wit, m = _workload(log_m)
+    g1p = _points_by_addition(m, 0)
+    g2p = _points_by_addition(m, 1)
+    pts = dict(alpha_g1=g1p[:1], beta_g1=g1p[1:2], beta_g2=g2p[:1], delta_g1=g1p[2:3], delta_g2=g2p[1:2],
+               a_query=g1p, b_g1_query=g1p, b_g2_query=g2p, l_query=g1p[:m - 2], h_query=g1p)
+    desc, keep = key_desc(mats, pts)
+    from workloads.synth_groth16 import _fr
+    r_m, s_m = _fr([123456789]), _fr([987654321])
+    for _ in range(warmup):
+        prove_plain(desc, pub, wit, r_m, s_m)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        prove_plain(desc, pub, wit, r_m, s_m)
+    dt = (time.perf_counter() - t0) / steps
+    del keep
+    return dt
+
+
+def cpu_baseline(log_m=20, target_log_m=20):
+    cores = lib().oracle_num_threads()
+    dt = time_proof(log_m, steps=1, warmup=0)
+    scale = (1 << target_log_m) / (1 << log_m)
+    return {"value": 1.0 / (dt * scale), "unit": "proofs/s", "cores": int(cores), "kind": "port",
+            "sample": "1 full Groth16 proof at 2^%d constraints by oracle/c (OpenMP, %d threads), %.2f s%s" % (
+                log_m, cores, dt, "" if scale == 1 else "; scaled linearly x%g to 2^%d" % (scale, target_log_m)),
+            "seconds_per_proof": dt * scale}
+
+
+def reference_arm(log_m=20, target_log_m=20, steps=1, warmup=0):
+    """bench.py --impl reference: the reference's CPU path as restated by oracle/c (the Rust reference
+    cannot be built here: no cargo, crates not vendored), all host threads."""
+    cores = lib().oracle_num_threads()
+    steps = max(1, min(steps, 3))
+    dt = time_proof(log_m, steps=steps, warmup=min(warmup, 1))
+    scale = (1 << target_log_m) / (1 << log_m)
+    v = 1.0 / (dt * scale)
+    sample = "%d Groth16 proof(s) at 2^%d constraints, oracle/c OpenMP port on %d host threads" % (steps, log_m, cores)
+    return {"impl": "reference", "metric": "co-Groth16 proofs/sec (BN254, 2^20 constraints); MSM Mscalar/s",
+            "value": v, "unit": "proofs/s", "n_gpus": 0, "steps": steps, "warmup": min(warmup, 1),
+            "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64x4 (256-bit Montgomery, integer)", "data": "synthetic (same seeded R1CS; timing-only key)",
+            "config": {"workload": "plain Groth16 prover, BN254, synthetic R1CS 2^%d constraints, host CPU" % target_log_m},
+            "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": int(cores), "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
