@@ -361,12 +361,30 @@ int oracle_groth16_prove_plain(const key_desc* d, const u64* pub_, const u64* wi
   fe rc, sc, rs, rsc; fe_from_mont(&rc, (const fe*)r_m, &FR); fe_from_mont(&sc, (const fe*)s_m, &FR);
   fe_mul(&rs, (const fe*)r_m, (const fe*)s_m, &FR); fe_from_mont(&rsc, &rs, &FR);
   g1_xyzz A, B1, L, H, t, dl; g2_xyzz B2, t2, dl2;
-  /* the five MSMs of rayon_join5! (groth16.rs:227-294); OpenMP parallelises inside each */
-  g1_msm(&A, (const g1_aff*)d->a_query + ni, aux, 4, nw);
-  g1_msm(&B1, (const g1_aff*)d->b_g1_query + ni, aux, 4, nw);
-  g2_msm(&B2, (const g2_aff*)d->b_g2_query + ni, aux, 4, nw);
-  g1_msm(&L, (const g1_aff*)d->l_query, aux, 4, nw);
-  g1_msm(&H, (const g1_aff*)d->h_query, hs, 4, n);
+  /* the five MSMs of rayon_join5! (groth16.rs:227-294) as ONE task pool; the G2 tasks (3x longer) go first */
+  {
+    const size_t want = (size_t)omp_get_max_threads() * 3;
+    g1_job ja, jb1, jl, jh; g2_job jb2;
+    g2_msm_plan(&jb2, (const g2_aff*)d->b_g2_query + ni, aux, 4, nw, want / 2);
+    g1_msm_plan(&ja, (const g1_aff*)d->a_query + ni, aux, 4, nw, want / 6);
+    g1_msm_plan(&jb1, (const g1_aff*)d->b_g1_query + ni, aux, 4, nw, want / 6);
+    g1_msm_plan(&jl, (const g1_aff*)d->l_query, aux, 4, nw, want / 6);
+    g1_msm_plan(&jh, (const g1_aff*)d->h_query, hs, 4, n, want / 6);
+    long t2 = (long)g2_msm_ntasks(&jb2), ta = (long)g1_msm_ntasks(&ja), tb = (long)g1_msm_ntasks(&jb1),
+         tl = (long)g1_msm_ntasks(&jl), th = (long)g1_msm_ntasks(&jh);
+    long total = t2 + ta + tb + tl + th;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long t = 0; t < total; t++) {
+      long k = t;
+      if (k < t2) { g2_msm_task(&jb2, (size_t)k); continue; } k -= t2;
+      if (k < ta) { g1_msm_task(&ja, (size_t)k); continue; } k -= ta;
+      if (k < tb) { g1_msm_task(&jb1, (size_t)k); continue; } k -= tb;
+      if (k < tl) { g1_msm_task(&jl, (size_t)k); continue; } k -= tl;
+      g1_msm_task(&jh, (size_t)k);
+    }
+    g1_msm_finish(&ja, &A); g1_msm_finish(&jb1, &B1); g2_msm_finish(&jb2, &B2);
+    g1_msm_finish(&jl, &L); g1_msm_finish(&jh, &H);
+  }
   /* calculate_coeff (groth16.rs:179-203): + query[0] + vk_param + msm(query[1..=pub], inputs) + r*delta */
   g1_msm(&t, (const g1_aff*)d->a_query + 1, pubs + 4, 4, ni - 1); g1_padd(&A, &t);
   g1_from_aff(&t, (const g1_aff*)d->a_query); g1_padd(&A, &t);
