@@ -263,11 +263,17 @@ def run_rep3(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world % 3 == 0, "rep3 mode needs a multiple of 3 ranks (one per party)"
+    gpp = args.gpus_per_party
+    assert gpp in (1, 2) and world % (3 * gpp) == 0, "rep3 mode needs 3 (or 6) ranks per proving group"
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    groups = [dist.new_group(list(range(g * 3, g * 3 + 3))) for g in range(world // 3)]
-    group = groups[rank // 3]
+    blk = 3 * gpp
+    role = rank % gpp  # 0 = the party's protocol GPU, 1 = its helper GPU ({witness map -> H, B2})
+    all_groups = {}
+    for g in range(world // blk):
+        for ro in range(gpp):
+            all_groups[(g, ro)] = dist.new_group([g * blk + p * gpp + ro for p in range(3)])
+    group = all_groups[(rank // blk, role)]
     stream = torch.cuda.Stream()
     ctx = B.Context(local_rank, stream=stream.cuda_stream)
     lg = args.log_m
@@ -278,7 +284,11 @@ def run_rep3(args):
     setup_s = time.time() - t0
     net = Rep3Network(group, device="cuda")
     pid = net.id
-    state = Rep3State(net, seed=4242 + rank)
+    state = Rep3State(net, seed=4242 + (rank // blk) * 3 + pid)  # both GPUs of a party: identical streams
+    link = None
+    if gpp == 2:
+        from co_snarks_b200.rep3 import PairLink
+        link = PairLink(rank + 1 if role == 0 else rank - 1, device="cuda")
     cvid = B.CS_BN254
     lib = ctx.lib
 
@@ -315,8 +325,15 @@ def run_rep3(args):
         dist.all_gather(outs, t, group=group)
         return all(bool((o == outs[0]).all()) for o in outs)
 
-    proof = prover.prove(net, state, pub, shares, delta, masks)
-    same = gather_eq(proof)
+    def one_proof():
+        if role == 1:
+            prover.helper_step(pid, state, pub, shares, link.send, masks)
+            return None
+        return prover.prove(net, state, pub, shares, delta, masks,
+                            pair_recv=(lambda: link.recv(6 * 4)) if link else None)
+
+    proof = one_proof()
+    same = gather_eq(proof) if role == 0 else True
     ok = None
     if rank == 0 and not args.fast_setup and not args.no_verify:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -327,7 +344,7 @@ def run_rep3(args):
         if not ok or not same:
             raise SystemExit("bench rep3: proof invalid or parties disagree")
     for _ in range(args.warmup):
-        prover.prove(net, state, pub, shares, delta, masks)
+        one_proof()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -335,7 +352,7 @@ def run_rep3(args):
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        prover.prove(net, state, pub, shares, delta, masks)
+        one_proof()
     torch.cuda.synchronize()
     dt = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
     dist.all_reduce(dt, op=dist.ReduceOp.MAX)
@@ -343,16 +360,16 @@ def run_rep3(args):
     launches = ctx.launch_count() - l0
     clk = clocks.stop()
     if rank == 0:
-        nproofs = args.steps * (world // 3)
+        nproofs = args.steps * (world // blk)
         h2d = shares.nbytes + pub.nbytes + 2 * masks[0].nbytes
         print(json.dumps({
             "metric": METRIC, "value": nproofs / (ms * 1e-3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery, integer)",
             "data": "synthetic (seeded R1CS + known-toxic-waste key; proof pairing-verified: %s; parties agree: %s)" % (ok, same),
-            "config": {"workload": "co-Groth16 Rep3, BN254, synthetic R1CS 2^%d constraints, 3 parties on 3xB200, "
-                                   "NCCL point exchange (BASELINE.json configs[2])" % lg,
-                       "groups": world // 3, "mask_prf": "masks pre-drawn outside the timed region", "setup_s": round(setup_s, 1),
+            "config": {"workload": "co-Groth16 Rep3, BN254, synthetic R1CS 2^%d constraints, 3 parties x %d GPU(s) on %dxB200, "
+                                   "NCCL point exchange (BASELINE.json configs[2])" % (lg, gpp, blk),
+                       "groups": world // blk, "gpus_per_party": gpp, "mask_prf": "masks pre-drawn outside the timed region", "setup_s": round(setup_s, 1),
                        "l2": "working set exceeds L2"},
             "e2e": {"value": nproofs / (ms * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 1344,
                     "note": "host share/mask buffers uploaded every step; timed by wall clock between synchronisations"},
@@ -397,6 +414,7 @@ def main():
     ap.add_argument("--cpu-log-m", type=int, default=20, help="log2 size of the CPU baseline sample")
     ap.add_argument("--window-bits", type=int, default=0)
     ap.add_argument("--mode", default="plain", choices=["plain", "rep3"])
+    ap.add_argument("--gpus-per-party", type=int, default=1)
     ap.add_argument("--fast-setup", action="store_true", help="random (invalid) key: skips the host-side QAP setup")
     ap.add_argument("--no-verify", action="store_true")
     args = ap.parse_args()

@@ -16,6 +16,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libcosnarks_gpu.so")
 CS_BN254, CS_BLS12_381 = 0, 1
 CS_G1, CS_G2 = 0, 1
 CS_PLAIN, CS_REP3 = 0, 1
+CS_PART_A, CS_PART_B1, CS_PART_B2, CS_PART_L, CS_PART_H, CS_PART_ALL = 1, 2, 4, 8, 16, 31
 
 u64p = C.POINTER(C.c_uint64)
 u32p = C.POINTER(C.c_uint32)
@@ -60,6 +61,7 @@ SIGNATURES = {
     "cs_bases_len": (C.c_size_t, [C.c_void_p]),
     "cs_msm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
     "cs_msm_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.POINTER(C.c_int)]),
+    "cs_msm_rep3_shares": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "cs_msm_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "cs_msm_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "cs_fixed_base_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
@@ -83,6 +85,8 @@ SIGNATURES = {
     "cs_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_groth16_rep3_local_parts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint] + [C.c_void_p] * 11),
+    "cs_groth16_shamir_local": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 9),
     "cs_groth16_rep3_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 11),
     "cs_point_scalar_mul": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_point_add": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -237,6 +241,14 @@ class Context:
                                         _ptr(out), C.byref(inf)))
         return out, bool(inf.value)
 
+    def msm_rep3_shares(self, bases, shares, offset=0):
+        shares = np.ascontiguousarray(shares, dtype=np.uint64)
+        n = shares.shape[0]
+        plimbs = limbs_of(bases.curve, "fq") * (2 if bases.group == CS_G1 else 4)
+        oa, ob = np.zeros(plimbs, dtype=np.uint64), np.zeros(plimbs, dtype=np.uint64)
+        self._check(self.lib.cs_msm_rep3_shares(self.h, bases.h, offset, _ptr(shares) if n else None, n, _ptr(oa), _ptr(ob)))
+        return oa, ob
+
     def msm_profile(self, enable=True):
         self._check(self.lib.cs_msm_profile(self.h, int(enable)))
 
@@ -385,13 +397,21 @@ class Groth16Key:
             _ptr(a), _ptr(b), _ptr(c)))
         return a, b, c
 
-    def rep3_local(self, party, public_inputs, witness_shares, mask1, mask2, r_share, s_share):
-        """-> (g_a, g1_b, g2_b, l_acc, h_acc) affine Montgomery half shares."""
+    def rep3_local(self, party, public_inputs, witness_shares, mask1, mask2, r_share, s_share, parts=31):
+        """-> (g_a, g1_b, g2_b, l_acc, h_acc) affine Montgomery half shares.  parts: CS_PART_* bitmask."""
         g1 = lambda: np.zeros(2 * self.fq, dtype=np.uint64)
         ga, gb1, gb2, l, h = g1(), g1(), np.zeros(4 * self.fq, dtype=np.uint64), g1(), g1()
-        self.ctx._check(self.ctx.lib.cs_groth16_rep3_local(
-            self.ctx.h, self.h, party, _ptr(public_inputs), _ptr(witness_shares), _ptr(mask1), _ptr(mask2),
+        self.ctx._check(self.ctx.lib.cs_groth16_rep3_local_parts(
+            self.ctx.h, self.h, party, parts, _ptr(public_inputs), _ptr(witness_shares), _ptr(mask1), _ptr(mask2),
             _ptr(r_share), _ptr(s_share), _ptr(ga), _ptr(gb1), _ptr(gb2), _ptr(l), _ptr(h)))
+        return ga, gb1, gb2, l, h
+
+    def shamir_local(self, public_inputs, witness_shares, r_share, s_share):
+        g1 = lambda: np.zeros(2 * self.fq, dtype=np.uint64)
+        ga, gb1, gb2, l, h = g1(), g1(), np.zeros(4 * self.fq, dtype=np.uint64), g1(), g1()
+        self.ctx._check(self.ctx.lib.cs_groth16_shamir_local(
+            self.ctx.h, self.h, _ptr(public_inputs), _ptr(witness_shares), _ptr(r_share), _ptr(s_share),
+            _ptr(ga), _ptr(gb1), _ptr(gb2), _ptr(l), _ptr(h)))
         return ga, gb1, gb2, l, h
 
     def free(self):

@@ -287,6 +287,32 @@ int cs_msm(cs_ctx* ctx, const cs_bases* b, size_t offset, const uint64_t* h_scal
   return cs_msm_device(ctx, b, offset, ws.scal.as<uint64_t>(), n, scalars_montgomery, h_out, out_inf);
 }
 
+// rep3::pointshare::msm_public_points (pointshare.rs:201-222): two MSMs over the a and b components of
+// replicated shares, run concurrently on two streams straight from the interleaved share array.
+int cs_msm_rep3_shares(cs_ctx* ctx, const cs_bases* b, size_t offset, const uint64_t* h_shares, size_t n,
+                       uint64_t* h_out_a, uint64_t* h_out_b) {
+  if (!ctx || !b || !h_out_a || !h_out_b || (n && !h_shares)) return fail(CS_ERR_ARG, "cs_msm_rep3_shares: NULL argument");
+  if (offset + n > b->n) return fail(CS_ERR_ARG, "cs_msm_rep3_shares: slice exceeds the uploaded bases");
+  const size_t plimbs = point_limbs64(b->curve, b->group);
+  if (n == 0) {
+    memset(h_out_a, 0, plimbs * 8);
+    memset(h_out_b, 0, plimbs * 8);
+    return 0;
+  }
+  CS_CUDA(cudaSetDevice(ctx->device));
+  MsmWorkspace& ws = ctx->msm_ws[0];
+  CS_TRY(ws.scal.reserve(n * 64));
+  CS_CUDA(cudaMemcpyAsync(ws.scal.p, h_shares, n * 64, cudaMemcpyHostToDevice, ctx->stream));
+  CS_TRY(ctx_fork(ctx, 2));
+  const uint32_t* sc = ws.scal.as<uint32_t>();
+  CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[0], b, offset, sc, 2, n, 1));      // component a
+  CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[1], b, offset, sc + 8, 2, n, 1));  // component b
+  CS_TRY(ctx_join(ctx, 2));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  CS_TRY(msm_finish_dyn(ctx, 1, b, h_out_a, nullptr));
+  return msm_finish_dyn(ctx, 2, b, h_out_b, nullptr);
+}
+
 int cs_msm_profile(cs_ctx* ctx, int enable) {
   if (!ctx) return fail(CS_ERR_ARG, "ctx is NULL");
   for (int i = 0; i < CS_NSIDE; i++) ctx->msm_ws[i].profile = enable != 0;

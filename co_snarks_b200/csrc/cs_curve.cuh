@@ -118,7 +118,7 @@ CS_DN Xyzz<F> dbl_xyzz(const Xyzz<F>& p) {
 
 // acc += p  (madd-2008-s), p affine, optionally negated
 template <class F>
-CS_DN void madd(Xyzz<F>& acc, const Affine<F>& p_in, bool negate) {
+CS_D void madd(Xyzz<F>& acc, const Affine<F>& p_in, bool negate) {
   if (p_in.is_inf()) return;
   Affine<F> p = p_in;
   if (negate) p.y = p.y.neg();
@@ -147,7 +147,7 @@ CS_DN void madd(Xyzz<F>& acc, const Affine<F>& p_in, bool negate) {
 
 // acc += q  (add-2008-s), both XYZZ
 template <class F>
-CS_DN void padd(Xyzz<F>& acc, const Xyzz<F>& q) {
+CS_D void padd(Xyzz<F>& acc, const Xyzz<F>& q) {
   if (q.is_inf()) return;
   if (acc.is_inf()) { acc = q; return; }
   F U1 = acc.x * q.zz;

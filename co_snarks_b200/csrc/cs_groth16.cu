@@ -151,64 +151,78 @@ int upload_inputs(cs_ctx* ctx, cs_groth16_pk* pk, int kind, const uint64_t* h_pu
 template <class Cfg>
 int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint64_t* h_pub, const uint64_t* h_wit,
                 const uint64_t* d_wit_in, const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
-                uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h) {
+                uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h,
+                unsigned parts = CS_PART_ALL) {
   typedef HostGroup<Cfg, 0> H1;
   typedef HostGroup<Cfg, 1> H2;
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
   const bool add_public = (kind == CS_PLAIN) || party == 0;
+  const bool have_aux = pk->nw > 0;
+  const bool do_a = parts & CS_PART_A, do_b1 = parts & CS_PART_B1, do_b2 = parts & CS_PART_B2,
+             do_l = parts & CS_PART_L, do_h = parts & CS_PART_H;
   CS_CUDA(cudaSetDevice(ctx->device));
-  CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, h_m1, h_m2));
+  CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, do_h ? h_m1 : nullptr, do_h ? h_m2 : nullptr));
   // fork: A, B1, B2, L need only the witness; the witness map + H run on the main stream.
   CS_TRY(ctx_fork(ctx, 4));
   // witness either uploaded from the host just above, or already resident in HBM (d_wit_in)
   const uint32_t* wit = d_wit_in ? reinterpret_cast<const uint32_t*>(d_wit_in) : pk->d_wit.as<uint32_t>();
-  const bool have_aux = pk->nw > 0;
   if (have_aux) {
     // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
-    CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
-    CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
-    CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1));
-    CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
+    if (do_a) CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
+    if (do_b1) CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
+    if (do_b2) CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1));
+    if (do_l) CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
   }
-  CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
-  CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
+  if (do_h) {
+    CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+    CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
+  }
   CS_TRY(ctx_join(ctx, 4));
 
   // ---- host work overlapped with the GPU: scalar_mul_public_point_hs + public parts (groth16.rs:232-276)
-  typename H1::X a_acc = H1::mul(H1::load(pk->delta_g1.data()), r_hs);
-  typename H1::X b1_acc = H1::mul(H1::load(pk->delta_g1.data()), s_hs);
-  typename H2::X b2_acc = H2::mul(H2::load(pk->delta_g2.data()), s_hs);
-  if (add_public) {
-    const size_t g1l = 2 * H1::HF::N, g2l = 4 * H1::HF::N;
-    a_acc = host::hadd(a_acc, H1::load(pk->a_head.data()));
-    a_acc = host::hadd(a_acc, H1::load(pk->alpha_g1.data()));
-    b1_acc = host::hadd(b1_acc, H1::load(pk->b1_head.data()));
-    b1_acc = host::hadd(b1_acc, H1::load(pk->beta_g1.data()));
-    b2_acc = host::hadd(b2_acc, H2::load(pk->b2_head.data()));
-    b2_acc = host::hadd(b2_acc, H2::load(pk->beta_g2.data()));
-    // msm_unchecked(&query[1..=pub_len], input_assignment) with input_assignment = public_inputs[1..]
-    for (size_t k = 1; k < pk->ni; k++) {
-      const uint64_t* sc = h_pub + k * 4;
-      a_acc = host::hadd(a_acc, H1::mul(H1::load(pk->a_head.data() + k * g1l), sc));
-      b1_acc = host::hadd(b1_acc, H1::mul(H1::load(pk->b1_head.data() + k * g1l), sc));
-      b2_acc = host::hadd(b2_acc, H2::mul(H2::load(pk->b2_head.data() + k * g2l), sc));
+  const size_t g1l = 2 * H1::HF::N, g2l = 4 * H1::HF::N;
+  typename H1::X a_acc = H1::X::inf(), b1_acc = H1::X::inf();
+  typename H2::X b2_acc = H2::X::inf();
+  if (do_a) {
+    a_acc = H1::mul(H1::load(pk->delta_g1.data()), r_hs);
+    if (add_public) {
+      a_acc = host::hadd(a_acc, H1::load(pk->a_head.data()));
+      a_acc = host::hadd(a_acc, H1::load(pk->alpha_g1.data()));
+      // msm_unchecked(&query[1..=pub_len], input_assignment) with input_assignment = public_inputs[1..]
+      for (size_t k = 1; k < pk->ni; k++)
+        a_acc = host::hadd(a_acc, H1::mul(H1::load(pk->a_head.data() + k * g1l), h_pub + k * 4));
+    }
+  }
+  if (do_b1) {
+    b1_acc = H1::mul(H1::load(pk->delta_g1.data()), s_hs);
+    if (add_public) {
+      b1_acc = host::hadd(b1_acc, H1::load(pk->b1_head.data()));
+      b1_acc = host::hadd(b1_acc, H1::load(pk->beta_g1.data()));
+      for (size_t k = 1; k < pk->ni; k++)
+        b1_acc = host::hadd(b1_acc, H1::mul(H1::load(pk->b1_head.data() + k * g1l), h_pub + k * 4));
+    }
+  }
+  if (do_b2) {
+    b2_acc = H2::mul(H2::load(pk->delta_g2.data()), s_hs);
+    if (add_public) {
+      b2_acc = host::hadd(b2_acc, H2::load(pk->b2_head.data()));
+      b2_acc = host::hadd(b2_acc, H2::load(pk->beta_g2.data()));
+      for (size_t k = 1; k < pk->ni; k++)
+        b2_acc = host::hadd(b2_acc, H2::mul(H2::load(pk->b2_head.data() + k * g2l), h_pub + k * 4));
     }
   }
   CS_CUDA(cudaStreamSynchronize(ctx->stream));
   uint64_t tmp[24];
   int inf = 0;
+  memset(out_l, 0, g1l * 8);
+  memset(out_h, 0, g1l * 8);
   if (have_aux) {
-    CS_TRY(msm_finish_dyn(ctx, 0, pk->a_query, tmp, &inf));
-    a_acc = host::hadd(a_acc, H1::load(tmp));
-    CS_TRY(msm_finish_dyn(ctx, 1, pk->b_g1, tmp, &inf));
-    b1_acc = host::hadd(b1_acc, H1::load(tmp));
-    CS_TRY(msm_finish_dyn(ctx, 2, pk->b_g2, tmp, &inf));
-    b2_acc = host::hadd(b2_acc, H2::load(tmp));
-    CS_TRY(msm_finish_dyn(ctx, 3, pk->l_query, out_l, &inf));
-  } else {
-    memset(out_l, 0, 2 * H1::HF::N * 8);
+    if (do_a) { CS_TRY(msm_finish_dyn(ctx, 0, pk->a_query, tmp, &inf)); a_acc = host::hadd(a_acc, H1::load(tmp)); }
+    if (do_b1) { CS_TRY(msm_finish_dyn(ctx, 1, pk->b_g1, tmp, &inf)); b1_acc = host::hadd(b1_acc, H1::load(tmp)); }
+    if (do_b2) { CS_TRY(msm_finish_dyn(ctx, 2, pk->b_g2, tmp, &inf)); b2_acc = host::hadd(b2_acc, H2::load(tmp)); }
+    if (do_l) CS_TRY(msm_finish_dyn(ctx, 3, pk->l_query, out_l, &inf));
   }
-  CS_TRY(msm_finish_dyn(ctx, 4, pk->h_query, out_h, &inf));
+  if (do_h) CS_TRY(msm_finish_dyn(ctx, 4, pk->h_query, out_h, &inf));
   H1::store(out_a, a_acc);
   H1::store(out_b1, b1_acc);
   H2::store(out_b2, b2_acc);
@@ -371,10 +385,40 @@ int cs_groth16_prove_plain_device(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t
   }
 }
 
+// ShamirGroth16Driver's local computation is the plain driver's, applied to degree-t shares
+// (mpc/shamir.rs:29-103: public terms and public points are added by EVERY party, local_mul_vec = a*b,
+// to_half_share = identity); only rand / degree_reduce_point / open_half_point touch the network.
+int cs_groth16_shamir_local(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const uint64_t* h_wit_shares,
+                            const uint64_t* r_share, const uint64_t* s_share, uint64_t* out_g_a, uint64_t* out_g1_b,
+                            uint64_t* out_g2_b, uint64_t* out_l, uint64_t* out_h) {
+  if (!ctx || !pk || !h_pub || (pk->nw && !h_wit_shares) || !r_share || !s_share || !out_g_a || !out_g1_b ||
+      !out_g2_b || !out_l || !out_h)
+    return fail(CS_ERR_ARG, "cs_groth16_shamir_local: NULL argument");
+  switch (pk->curve) {
+    case CS_BN254:
+      return local_phase<Bn254Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit_shares, nullptr, nullptr, nullptr, r_share,
+                                   s_share, out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381:
+      return local_phase<Bls381Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit_shares, nullptr, nullptr, nullptr, r_share,
+                                    s_share, out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
 int cs_groth16_rep3_local(cs_ctx* ctx, cs_groth16_pk* pk, int party, const uint64_t* h_pub,
                           const uint64_t* h_wit_shares, const uint64_t* h_m1, const uint64_t* h_m2,
                           const uint64_t* r_share, const uint64_t* s_share, uint64_t* out_g_a, uint64_t* out_g1_b,
                           uint64_t* out_g2_b, uint64_t* out_l, uint64_t* out_h) {
+  return cs_groth16_rep3_local_parts(ctx, pk, party, CS_PART_ALL, h_pub, h_wit_shares, h_m1, h_m2, r_share, s_share,
+                                     out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+}
+
+int cs_groth16_rep3_local_parts(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsigned parts, const uint64_t* h_pub,
+                                const uint64_t* h_wit_shares, const uint64_t* h_m1, const uint64_t* h_m2,
+                                const uint64_t* r_share, const uint64_t* s_share, uint64_t* out_g_a,
+                                uint64_t* out_g1_b, uint64_t* out_g2_b, uint64_t* out_l, uint64_t* out_h) {
   if (!ctx || !pk || !h_pub || (pk->nw && !h_wit_shares) || !r_share || !s_share || !out_g_a || !out_g1_b ||
       !out_g2_b || !out_l || !out_h)
     return fail(CS_ERR_ARG, "cs_groth16_rep3_local: NULL argument");
@@ -383,11 +427,11 @@ int cs_groth16_rep3_local(cs_ctx* ctx, cs_groth16_pk* pk, int party, const uint6
   switch (pk->curve) {
     case CS_BN254:
       return local_phase<Bn254Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, nullptr, h_m1, h_m2, r_share, s_share,
-                                   out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+                                   out_g_a, out_g1_b, out_g2_b, out_l, out_h, parts);
 #if defined(CS_ENABLE_BLS12_381)
     case CS_BLS12_381:
       return local_phase<Bls381Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, nullptr, h_m1, h_m2, r_share, s_share,
-                                    out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+                                    out_g_a, out_g1_b, out_g2_b, out_l, out_h, parts);
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");
   }

@@ -14,6 +14,7 @@
 //    list (robust to skewed scalars) -> weighted bucket reduction sum_b b * S_b.
 //  * Arithmetic is exact 256/381-bit Montgomery on the integer pipe; no tensor cores.
 #pragma once
+#include <stdlib.h>
 #include "cs_common.cuh"
 #include "cs_curve.cuh"
 
@@ -150,8 +151,8 @@ CS_D uint32_t find_bucket(const uint32_t* __restrict__ arr, uint32_t nb1, uint32
 
 // --------------------------------------------------------------------------- accumulation level 0
 // One thread per slice of <= MSM_SLICE sorted entries of ONE bucket: mixed additions from the table.
-template <class F>
-CS_GLOBAL void __launch_bounds__(128) k_msm_accum0(const Affine<F>* __restrict__ table,
+template <class F, int MINB>
+CS_GLOBAL void __launch_bounds__(128, MINB) k_msm_accum0(const Affine<F>* __restrict__ table,
                                                    const uint32_t* __restrict__ sorted,
                                                    const uint32_t* __restrict__ count,
                                                    const uint32_t* __restrict__ start,
@@ -402,8 +403,23 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
             offset, start, cursor, ws.sorted.as<uint32_t>());
   CS_TRY(ws.mark(2, st));
-  CS_LAUNCH(k_msm_accum0<F>, ceil_div(max_s0, 128), 128, 0, st, table, ws.sorted.as<uint32_t>(), count,
-            start, sstart0, nb1, ws.part0.as<Xyzz<F>>());
+  {
+    // resident blocks per SM (register cap) -- tuned on B200, overridable for experiments
+    static int minb_env = -1;
+    if (minb_env < 0) { const char* e = getenv("CS_ACCUM0_MINB"); minb_env = e ? atoi(e) : 0; }
+    const int minb = minb_env ? minb_env : (sizeof(F) > 32 ? 2 : 4);
+#define CS_ACC0(M)                                                                                              \
+  CS_LAUNCH(k_msm_accum0<F COMMA M>, ceil_div(max_s0, 128), 128, 0, st, table, ws.sorted.as<uint32_t>(), count, \
+            start, sstart0, nb1, ws.part0.as<Xyzz<F>>())
+    switch (minb) {
+      case 2: CS_ACC0(2); break;
+      case 3: CS_ACC0(3); break;
+      case 5: CS_ACC0(5); break;
+      case 6: CS_ACC0(6); break;
+      default: CS_ACC0(4); break;
+    }
+#undef CS_ACC0
+  }
   CS_TRY(ws.mark(3, st));
   CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,
             nb1, ws.part1.as<Xyzz<F>>());

@@ -70,6 +70,25 @@ class Rep3Network:
         return conv(outs[self.prev]), conv(outs[self.next])
 
 
+class PairLink:
+    """Point-sized link between the two GPUs (ranks) of one party."""
+
+    def __init__(self, peer_global_rank, device="cpu"):
+        import torch.distributed as dist
+        self.dist, self.peer, self.device = dist, peer_global_rank, device
+
+    def send(self, arr):
+        import torch
+        t = torch.from_numpy(np.ascontiguousarray(arr).view(np.int64).copy()).to(self.device)
+        self.dist.send(t, self.peer)
+
+    def recv(self, nwords):
+        import torch
+        t = torch.empty(nwords, dtype=torch.int64, device=self.device)
+        self.dist.recv(t, self.peer)
+        return t.cpu().numpy().view(np.uint64)
+
+
 class Rep3State:
     """Correlated randomness of one party: rng1 = own stream, rng2 = previous party's stream
     (Rep3Rand, rngs.rs:86-156; seeds exchanged once over the network, rep3.rs:71-110)."""
@@ -144,24 +163,45 @@ class Rep3CoGroth16:
         q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
         self.gen_mont = B.ints_to_limbs(B.to_mont_ints(list(_G1_GEN_CANON), q, 4), 4).reshape(-1)
 
-    def prove(self, net, state, public_inputs, witness_shares, delta_g1, masks=None):
-        """witness_shares: [nw, 8] uint64 (a‖b per share, Montgomery); public_inputs incl. the leading 1.
-        delta_g1: affine Montgomery (pkey.delta_g1).  Returns (A, B, C) affine Montgomery; all parties
-        return the same proof (tests/test_dist_rep3.py)."""
-        lib, cv, pk = self.lib, self.curve, self.pk
-        n = pk.domain_size()
-        pid = net.id
-        # witness_map_from_matrices consumes two mask vectors (reduction.rs:160,182) ...
+    def draw(self, state, masks=None):
+        """All correlated randomness of one proof, in the order the reference consumes it: two mask
+        vectors (reduction.rs:160,182), r, s (groth16.rs:157), the rs mask (groth16.rs:297) and the EC
+        mask of scalar_mul (pointshare.rs:119-125)."""
+        lib, cv, n = self.lib, self.curve, self.pk.domain_size()
         if masks is None:
             m1 = state.masking_field_elements_vec(lib, cv, n)
             m2 = state.masking_field_elements_vec(lib, cv, n)
         else:
             m1, m2 = masks  # pre-drawn from the same two streams (bench.py draws them on the device)
-        # ... then r, s = T::rand (groth16.rs:157)
         r_sh, s_sh = state.rand(lib, cv), state.rand(lib, cv)
-        g_a, g1_b, g2_b, l_acc, h_acc = pk.rep3_local(pid, public_inputs, witness_shares, m1, m2, r_sh, s_sh)
+        rs_mask = B.from_mont_ints(B.limbs_to_ints(state.masking_field_elements_vec(lib, cv, 1)), BN254_R, 4)[0]
+        ec_mask = state.masking_ec_element(lib, cv, self.gen_mont)
+        return m1, m2, r_sh, s_sh, rs_mask, ec_mask
+
+    def helper_step(self, pid, state, public_inputs, witness_shares, pair_send, masks=None):
+        """Second GPU of a party: runs {witness map -> H, B2} and hands the two points to
+        the party's first GPU.  Draws the same randomness so both GPUs stay in lock-step."""
+        m1, m2, r_sh, s_sh, _, _ = self.draw(state, masks)
+        _, _, g2_b, _, h_acc = self.pk.rep3_local(pid, public_inputs, witness_shares, m1, m2, r_sh, s_sh,
+                                                  parts=B.CS_PART_B2 | B.CS_PART_H)
+        pair_send(np.concatenate([g2_b, h_acc]))
+
+    def prove(self, net, state, public_inputs, witness_shares, delta_g1, masks=None, pair_recv=None):
+        """witness_shares: [nw, 8] uint64 (a‖b per share, Montgomery); public_inputs incl. the leading 1.
+        delta_g1: affine Montgomery (pkey.delta_g1).  Returns (A, B, C) affine Montgomery; all parties
+        return the same proof (tests/test_dist_rep3.py).  pair_recv: when the party owns a second GPU,
+        a callable returning the helper's (g2_b ‖ h_acc)."""
+        lib, cv, pk = self.lib, self.curve, self.pk
+        pid = net.id
+        m1, m2, r_sh, s_sh, mask, ec_mask = self.draw(state, masks)
+        if pair_recv is None:
+            g_a, g1_b, g2_b, l_acc, h_acc = pk.rep3_local(pid, public_inputs, witness_shares, m1, m2, r_sh, s_sh)
+        else:
+            g_a, g1_b, _, l_acc, _ = pk.rep3_local(pid, public_inputs, witness_shares, None, None, r_sh, s_sh,
+                                                   parts=B.CS_PART_A | B.CS_PART_B1 | B.CS_PART_L)
+            both = pair_recv()
+            g2_b, h_acc = both[:g2_b_len(pk)], both[g2_b_len(pk):]
         # rs = local_mul_vec([r],[s]) (groth16.rs:297): r.a*s.a + r.a*s.b + r.b*s.a + mask
-        mask = B.from_mont_ints(B.limbs_to_ints(state.masking_field_elements_vec(lib, cv, 1)), BN254_R, 4)[0]
         rs = (_fr_mul_mont(lib, cv, r_sh[0], s_sh[0]) + _fr_mul_mont(lib, cv, r_sh[0], s_sh[1]) +
               _fr_mul_mont(lib, cv, r_sh[1], s_sh[0]) + mask) % BN254_R
         r_s_delta = B.point_scalar_mul(lib, cv, B.CS_G1, delta_g1, _fr_from_int(lib, cv, rs))
@@ -172,7 +212,7 @@ class Rep3CoGroth16:
         t = B.point_scalar_mul(lib, cv, B.CS_G1, g1_b, r_sh[0])                       # rhs.a * self.a
         t = B.point_add(lib, cv, B.CS_G1, t, B.point_scalar_mul(lib, cv, B.CS_G1, g1_b_prev, r_sh[0]))  # rhs.b * self.a
         t = B.point_add(lib, cv, B.CS_G1, t, B.point_scalar_mul(lib, cv, B.CS_G1, g1_b, r_sh[1]))       # rhs.a * self.b
-        r_g1_b = B.point_add(lib, cv, B.CS_G1, t, state.masking_ec_element(lib, cv, self.gen_mont))
+        r_g1_b = B.point_add(lib, cv, B.CS_G1, t, ec_mask)
         # groth16.rs:314-322
         g_c = B.point_scalar_mul(lib, cv, B.CS_G1, g_a_opened, s_sh[0])
         g_c = B.point_add(lib, cv, B.CS_G1, g_c, r_g1_b)
@@ -186,3 +226,7 @@ class Rep3CoGroth16:
         g2_b_opened = B.point_add(lib, cv, B.CS_G2, B.point_add(lib, cv, B.CS_G2, g2_b, pa), pn)
         self.last_randomness = (r_sh, s_sh)
         return g_a_opened, g2_b_opened, g_c_opened
+
+
+def g2_b_len(pk):
+    return 4 * pk.fq

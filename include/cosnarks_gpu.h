@@ -84,6 +84,12 @@ int cs_msm(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* h_
 int cs_msm_device(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* d_scalars, size_t n,
                   int scalars_montgomery, uint64_t* h_out_affine_mont, int* out_is_infinity);
 
+/* rep3::pointshare::msm_public_points (mpc-core/src/protocols/rep3/pointshare.rs:201-222; used by co-plonk
+ * mpc/rep3.rs:170-175 and co-noir-common mpc/rep3.rs:259-266): shares = n Rep3 shares a||b (Montgomery);
+ * returns the point share {a: sum a_i P_i, b: sum b_i P_i} as two affine points. */
+int cs_msm_rep3_shares(cs_ctx* ctx, const cs_bases* bases, size_t offset, const uint64_t* h_shares, size_t n,
+                       uint64_t* h_out_a_affine, uint64_t* h_out_b_affine);
+
 /* Measurement hooks (bench.py): when enabled, cs_msm / cs_msm_device record CUDA events at the five stage
  * boundaries of the MSM on its launching stream; cs_msm_stage_ms returns the last MSM's stage durations
  * {digits+histogram, scan+scatter, bucket accumulation (k_msm_accum0), partial folding, bucket reduction}. */
@@ -190,6 +196,29 @@ int cs_groth16_rep3_local(cs_ctx* ctx, cs_groth16_pk* pk, int party, const uint6
                           const uint64_t* h_r_share, const uint64_t* h_s_share,
                           uint64_t* out_g_a, uint64_t* out_g1_b, uint64_t* out_g2_b,
                           uint64_t* out_l_acc, uint64_t* out_h_acc);
+
+/* The same, restricted to a subset of the five MSMs, so that one party's local phase can be split over two
+ * GPUs (GPU0 takes {A, B1, L}, GPU1 takes {witness map -> H, B2}); outputs of parts that
+ * were not requested are the identity.  CS_PART_H includes the witness map. */
+#define CS_PART_A 1u
+#define CS_PART_B1 2u
+#define CS_PART_B2 4u
+#define CS_PART_L 8u
+#define CS_PART_H 16u
+#define CS_PART_ALL 31u
+int cs_groth16_rep3_local_parts(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsigned parts,
+                                const uint64_t* h_public_inputs, const uint64_t* h_witness_shares,
+                                const uint64_t* h_mask1, const uint64_t* h_mask2, const uint64_t* h_r_share,
+                                const uint64_t* h_s_share, uint64_t* out_g_a, uint64_t* out_g1_b,
+                                uint64_t* out_g2_b, uint64_t* out_l_acc, uint64_t* out_h_acc);
+
+/* ShamirGroth16Driver's local phase (co-groth16/src/mpc/shamir.rs:29-119): identical arithmetic to the plain
+ * driver on degree-t shares -- every party adds the public terms/points; outputs are degree-2t point shares
+ * that the host protocol opens (shamir/pointshare.rs:86-113). */
+int cs_groth16_shamir_local(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_public_inputs,
+                            const uint64_t* h_witness_shares, const uint64_t* h_r_share, const uint64_t* h_s_share,
+                            uint64_t* out_g_a, uint64_t* out_g1_b, uint64_t* out_g2_b,
+                            uint64_t* out_l_acc, uint64_t* out_h_acc);
 
 /* ---- single-point helpers used by the host-side protocol code (latency-only, run on the host) -----
  * scalar_mul_public_point_hs (mpc/rep3.rs:141-146), point addition / negation for

@@ -30,7 +30,7 @@ def build(force=False):
     if not force and not needs_build():
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-g0", "-DCS_EMU", "-fPIC", "-shared", "-pthread", "-w",
+    cmd = ["g++", "-std=c++17", "-O2", "-g0", "-DCS_EMU", "-DCS_ENABLE_BLS12_381", "-fPIC", "-shared", "-pthread", "-w",
            "-I", HERE, "-I", CSRC, "-o", OUT]
     for s in sources():
         cmd += ["-x", "c++", s]

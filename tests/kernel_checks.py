@@ -10,12 +10,12 @@ from helpers import Conv, golden_groth16, gp1, ih, load_golden, make_key
 from oracle import groth16 as OG
 from oracle import ntt as ON
 from oracle.ec import g1 as og1, g2 as og2
-from oracle.fields import BN254, groth16_roots_of_unity
+from oracle.fields import BN254, CURVES, groth16_roots_of_unity
 from oracle.pairing_bn254 import groth16_verify
 
 
-def check_field_ops(ctx, n=257, seed=1):
-    cv = Conv("bn254")
+def check_field_ops(ctx, n=257, seed=1, curve="bn254"):
+    cv = Conv(curve)
     r = cv.r
     rng = random.Random(seed)
     a = [rng.randrange(r) for _ in range(n)]
@@ -84,8 +84,8 @@ def check_roots(ctx):
         assert cv.fr_back(gen) == [eg] and cv.fr_back(shift) == [es], power
 
 
-def check_ntt(ctx, log_sizes, seed=3):
-    cv = Conv("bn254")
+def check_ntt(ctx, log_sizes, seed=3, curve="bn254"):
+    cv = Conv(curve)
     r = cv.r
     rng = random.Random(seed)
     for lg in log_sizes:
@@ -125,12 +125,13 @@ def _edge_case_inputs(G, gen, n, r, rng):
     return pts, sc
 
 
-def check_msm(ctx, group, n, window_bits=(0,), seed=4):
-    cv = Conv("bn254")
+def check_msm(ctx, group, n, window_bits=(0,), seed=4, curve="bn254"):
+    cv = Conv(curve)
     r = cv.r
     rng = random.Random(seed + group)
-    G = og1(BN254) if group == 0 else og2(BN254)
-    gen = BN254.g1 if group == 0 else BN254.g2
+    C = CURVES[curve]
+    G = og1(C) if group == 0 else og2(C)
+    gen = C.g1 if group == 0 else C.g2
     to_arr = cv.g1 if group == 0 else cv.g2
     to_pt = cv.pt1 if group == 0 else cv.pt2
     pts, sc = _edge_case_inputs(G, gen, n, r, rng)
@@ -286,3 +287,59 @@ def check_groth16_rep3_local(ctx, pk, cv, z, m, w, h_exp, vk, public, seed=5):
     s_tot = sum(x[0][0] for x in ssh) % r
     assert (A, Bp, C) == OG.prove_plain(z, m, w, r_tot, s_tot)
     assert groth16_verify(vk, public, (A, Bp, C))
+
+
+def check_msm_rep3_shares(ctx, n=200, seed=8):
+    """rep3::pointshare::msm_public_points: both share components from the interleaved array."""
+    cv = Conv("bn254")
+    rng = random.Random(seed)
+    G = og1(BN254)
+    pts = [G.mul(BN254.g1, rng.randrange(1, cv.r)) for _ in range(n)]
+    sh = [(rng.randrange(cv.r), rng.randrange(cv.r)) for _ in range(n)]
+    bases = ctx.bases_upload(cv.id, 0, cv.g1(pts))
+    oa, ob = ctx.msm_rep3_shares(bases, cv.fr([x for s in sh for x in s]).reshape(n, 8))
+    assert cv.pt1(oa) == G.msm(pts, [s[0] for s in sh]) and cv.pt1(ob) == G.msm(pts, [s[1] for s in sh])
+    bases.free()
+
+
+def check_groth16_shamir_local(ctx, name="multiplier2", seed=9):
+    """ShamirCoGroth16 (t = 1, n = 3, the only valid 3-party setting: shamir.rs:41-43): the three
+    parties' local phases on degree-1 shares, opened by Lagrange interpolation at 0 with weights
+    (3, -3, 1) as degree-2 sharings (shamir/pointshare.rs:102-111), give the plain proof for
+    r = r(0), s = s(0)."""
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    z, m, w, g = golden_groth16(name)
+    ni = m["num_instance_variables"]
+    pk = make_key(ctx, cv, z, m)
+    G1, G2 = og1(BN254), og2(BN254)
+
+    def shamir(v):  # degree-1 polynomial, party i evaluates at i + 1
+        a = rng.randrange(r)
+        return [(v + a * (i + 1)) % r for i in range(3)]
+
+    wsh = [shamir(x) for x in w[ni:]]
+    r0, s0 = rng.randrange(r), rng.randrange(r)
+    rsh, ssh = shamir(r0), shamir(s0)
+    lam = [3, r - 3, 1]
+    pub = cv.fr(w[:ni])
+    loc = [pk.shamir_local(pub, cv.fr([x[i] for x in wsh]), cv.fr([rsh[i]]), cv.fr([ssh[i]])) for i in range(3)]
+
+    def open_(pts, G):
+        acc = None
+        for P, l in zip(pts, lam):
+            acc = G.add(acc, G.mul(P, l))
+        return acc
+
+    A = open_([cv.pt1(loc[i][0]) for i in range(3)], G1)
+    Bp = open_([cv.pt2(loc[i][2]) for i in range(3)], G2)
+    gc = []
+    for i in range(3):
+        c = G1.add(G1.mul(A, ssh[i]), G1.mul(cv.pt1(loc[i][1]), rsh[i]))
+        c = G1.add(c, G1.neg(G1.mul(z["delta_g1"], rsh[i] * ssh[i] % r)))
+        c = G1.add(G1.add(c, cv.pt1(loc[i][3])), cv.pt1(loc[i][4]))
+        gc.append(c)
+    C = open_(gc, G1)
+    assert (A, Bp, C) == OG.prove_plain(z, m, w, r0, s0)
+    pk.free()

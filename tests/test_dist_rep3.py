@@ -84,3 +84,73 @@ def test_rep3_three_parties_gloo():
     assert proofs[0] == OG.prove_plain(z, m, w, r_tot, s_tot)
     # the reference exchanges only point-sized messages on this path
     assert all(x[6] < 4096 for x in res)
+
+
+def _party6(rank, port, emu_path, q):
+    """world 6 = 3 parties x 2 GPUs: even ranks run {A, B1, L} + the protocol, odd ranks {witness map -> H, B2}."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from co_snarks_b200 import binding as B
+    from co_snarks_b200.rep3 import PairLink, Rep3CoGroth16, Rep3Network, Rep3State
+    from helpers import Conv, golden_groth16, make_key
+    from oracle import groth16 as OG
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=6)
+    try:
+        mains = dist.new_group([0, 2, 4])
+        helpers = dist.new_group([1, 3, 5])
+        party, role = rank // 2, rank % 2
+        ctx = B.Context(0, lib_path=emu_path)
+        cv = Conv("bn254")
+        z, m, w, g = golden_groth16("poseidon")
+        ni = m["num_instance_variables"]
+        pk = make_key(ctx, cv, z, m)
+        wsh = OG.share_rep3(w[ni:], cv.r, random.Random(5))
+        mine = cv.fr([x for ab in wsh[party] for x in ab]).reshape(-1, 8)
+        net = Rep3Network(mains if role == 0 else helpers)
+        assert net.id == party
+        state = Rep3State(net, seed=1000 + party)  # both GPUs of a party derive identical streams
+        prover = Rep3CoGroth16(ctx, pk)
+        link = PairLink(rank + 1 if role == 0 else rank - 1)
+        pub = cv.fr(w[:ni])
+        if role == 0:
+            A, Bp, Cp = prover.prove(net, state, pub, mine, cv.g1([z["delta_g1"]])[0],
+                                     pair_recv=lambda: link.recv(4 * pk.fq + 2 * pk.fq))
+            r_sh, s_sh = prover.last_randomness
+            q.put((party, cv.pt1(A), cv.pt2(Bp), cv.pt1(Cp), cv.fr_back(r_sh), cv.fr_back(s_sh)))
+        else:
+            prover.helper_step(party, state, pub, mine, link.send)
+        pk.free()
+        ctx.close()
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_rep3_two_gpus_per_party_gloo():
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    emu = build_emu.build()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_party6, args=(r, port, emu, q)) for r in range(6)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(3))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import golden_groth16, ih
+    from oracle import groth16 as OG
+    from oracle.fields import BN254
+    from oracle.pairing_bn254 import groth16_verify
+    proofs = [(a, b, c) for _, a, b, c, _, _ in res]
+    assert proofs[0] == proofs[1] == proofs[2]
+    z, m, w, g = golden_groth16("poseidon")
+    assert groth16_verify(OG.vk_from_zkey(z), [ih(x) for x in g["public"]], proofs[0])
+    r_tot = sum(x[4][0] for x in res) % BN254.r
+    s_tot = sum(x[5][0] for x in res) % BN254.r
+    assert proofs[0] == OG.prove_plain(z, m, w, r_tot, s_tot)

@@ -38,3 +38,22 @@ def test_emu_plonk_round1_kat(emu_ctx):
 
 def test_emu_groth16_multiplier2(emu_ctx):
     K.check_groth16_fixture(emu_ctx, "multiplier2")
+
+
+# ---- BLS12-381 (12-limb Fq, 255-bit Fr)
+def test_emu_bls12_381_field_and_ntt(emu_ctx):
+    K.check_field_ops(emu_ctx, n=40, curve="bls12_381")
+    K.check_ntt(emu_ctx, [1, 6], curve="bls12_381")
+
+
+def test_emu_bls12_381_msm(emu_ctx):
+    K.check_msm(emu_ctx, 0, 40, curve="bls12_381")
+    K.check_msm(emu_ctx, 1, 14, curve="bls12_381")
+
+
+def test_emu_msm_rep3_shares(emu_ctx):
+    K.check_msm_rep3_shares(emu_ctx, n=60)
+
+
+def test_emu_groth16_shamir_local(emu_ctx):
+    K.check_groth16_shamir_local(emu_ctx)

@@ -57,3 +57,30 @@ def test_groth16_multiplier2(gpu_ctx):
 
 def test_groth16_poseidon(gpu_ctx):
     K.check_groth16_fixture(gpu_ctx, "poseidon")
+
+
+# ---- BLS12-381
+def test_bls12_381_field_and_ntt(gpu_ctx):
+    K.check_field_ops(gpu_ctx, n=1025, curve="bls12_381")
+    K.check_ntt(gpu_ctx, [1, 6, 12], curve="bls12_381")
+
+
+def test_bls12_381_msm_g1(gpu_ctx):
+    K.check_msm(gpu_ctx, 0, 700, window_bits=(0, 9), curve="bls12_381")
+
+
+def test_bls12_381_msm_g2(gpu_ctx):
+    K.check_msm(gpu_ctx, 1, 150, curve="bls12_381")
+
+
+def test_plonk_round1_kat_bls12_381(gpu_ctx):
+    """4096-point iNTT + ~4100-point MSM on BLS12-381 == the reference's known answers (round1.rs:397-417)."""
+    K.check_plonk_round1_kat(gpu_ctx, "bls12_381", "poseidon")
+
+
+def test_msm_rep3_shares(gpu_ctx):
+    K.check_msm_rep3_shares(gpu_ctx, n=900)
+
+
+def test_groth16_shamir_local(gpu_ctx):
+    K.check_groth16_shamir_local(gpu_ctx)
