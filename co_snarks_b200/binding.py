@@ -95,6 +95,9 @@ SIGNATURES = {
     "cs_fr_from_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_fq_to_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_fq_from_mont": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_fr_mul": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_fr_add": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_fr_sub": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_roots_of_unity": (C.c_int, [C.c_int, C.c_uint, C.c_void_p, C.c_void_p]),
 }
 

@@ -706,6 +706,42 @@ int cs_fq_from_mont(cs_curve curve, const uint64_t* in, uint64_t* out, size_t n)
   CS_DISPATCH_CURVE(curve, { return field_conv<typename Cfg::FqP>(in, out, n, false); });
   return 0;
 }
+int cs_fr_mul(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont) {
+  if (!a_mont || !b_mont || !out_mont) return fail(CS_ERR_ARG, "cs_fr_mul: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    typedef host::HFp<typename Cfg::FrP> HF;
+    HF a; HF b;
+    memcpy(a.l, a_mont, sizeof(a.l));
+    memcpy(b.l, b_mont, sizeof(b.l));
+    HF r = a * b;
+    memcpy(out_mont, r.l, sizeof(r.l));
+  });
+  return 0;
+}
+int cs_fr_add(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont) {
+  if (!a_mont || !b_mont || !out_mont) return fail(CS_ERR_ARG, "cs_fr_add: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    typedef host::HFp<typename Cfg::FrP> HF;
+    HF a; HF b;
+    memcpy(a.l, a_mont, sizeof(a.l));
+    memcpy(b.l, b_mont, sizeof(b.l));
+    HF r = a + b;
+    memcpy(out_mont, r.l, sizeof(r.l));
+  });
+  return 0;
+}
+int cs_fr_sub(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont) {
+  if (!a_mont || !b_mont || !out_mont) return fail(CS_ERR_ARG, "cs_fr_sub: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    typedef host::HFp<typename Cfg::FrP> HF;
+    HF a; HF b;
+    memcpy(a.l, a_mont, sizeof(a.l));
+    memcpy(b.l, b_mont, sizeof(b.l));
+    HF r = a - b;
+    memcpy(out_mont, r.l, sizeof(r.l));
+  });
+  return 0;
+}
 int cs_groth16_roots_of_unity(cs_curve curve, unsigned pow, uint64_t* out_gen, uint64_t* out_shift) {
   if (!out_gen || !out_shift) return fail(CS_ERR_ARG, "cs_groth16_roots_of_unity: NULL argument");
   CS_DISPATCH_CURVE(curve, { return roots_of_unity_t<Cfg>(pow, out_gen, out_shift); });

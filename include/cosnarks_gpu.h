@@ -235,6 +235,10 @@ int cs_fr_to_mont(cs_curve curve, const uint64_t* in_canonical, uint64_t* out_mo
 int cs_fr_from_mont(cs_curve curve, const uint64_t* in_mont, uint64_t* out_canonical, size_t n);
 int cs_fq_to_mont(cs_curve curve, const uint64_t* in_canonical, uint64_t* out_mont, size_t n);
 int cs_fq_from_mont(cs_curve curve, const uint64_t* in_mont, uint64_t* out_canonical, size_t n);
+/* single-element Fr arithmetic in Montgomery form (r*s of groth16.rs:297, share algebra of the host protocol) */
+int cs_fr_mul(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
+int cs_fr_add(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
+int cs_fr_sub(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
 int cs_groth16_roots_of_unity(cs_curve curve, unsigned pow, uint64_t* out_group_gen_mont,
                               uint64_t* out_coset_shift_mont);
 

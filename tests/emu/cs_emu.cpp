@@ -33,7 +33,10 @@ void syncthreads() {
 }
 void* dyn_smem() { return g_smem.data(); }
 
+static std::mutex g_launch_mutex;  // one emulated kernel at a time, whichever host thread launches it
+
 void launch(dim3 grid, dim3 block, size_t smem, bool uses_sync, const std::function<void()>& body) {
+  std::lock_guard<std::mutex> launch_lock(g_launch_mutex);
   g_smem.assign(smem + 16, 0);
   unsigned nthreads = block.x * block.y * block.z;
   for (unsigned bz = 0; bz < grid.z; bz++)
