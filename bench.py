@@ -313,17 +313,9 @@ def run_rep3(args):
     sh_pinned = torch.empty(shares.shape, dtype=torch.int64).pin_memory()
     sh_pinned.numpy().view(np.uint64)[:] = shares
     shares = sh_pinned.numpy().view(np.uint64)
-    # masks from the two correlated streams, differences taken on the device (mask PRF generation --
-    # ChaCha12 in the reference, rngs.rs:137-156 -- is outside the timed region; DESIGN.md "next")
-    a1, b1 = state.random_fes(n)
-    a2, b2 = state.random_fes(n)
-    def pinned(a):
-        t = torch.empty(a.shape, dtype=torch.int64).pin_memory()
-        t.numpy().view(np.uint64)[:] = a
-        return t
-
-    keep = [pinned(dev_sub(a1, b1)), pinned(dev_sub(a2, b2))]  # pinned: pageable H2D costs ~9 ms per proof
-    masks = tuple(t.numpy().view(np.uint64) for t in keep)
+    # the two n-element mask vectors are drawn on the device from the party's ChaCha12 streams inside the
+    # timed local phase (cs_groth16_rep3_local_prf), as the reference draws them inside prove()
+    masks = None
     prover = Rep3CoGroth16(ctx, pk)
     delta = syn.points["delta_g1"][0]
     pub = syn.public_inputs
@@ -370,7 +362,7 @@ def run_rep3(args):
     clk = clocks.stop()
     if rank == 0:
         nproofs = args.steps * (world // blk)
-        h2d = shares.nbytes + pub.nbytes + 2 * masks[0].nbytes
+        h2d = shares.nbytes + pub.nbytes
         print(json.dumps({
             "metric": METRIC, "value": nproofs / (ms * 1e-3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -378,10 +370,10 @@ def run_rep3(args):
             "data": "synthetic (seeded R1CS + known-toxic-waste key; proof pairing-verified: %s; parties agree: %s)" % (ok, same),
             "config": {"workload": "co-Groth16 Rep3, BN254, synthetic R1CS 2^%d constraints, 3 parties x %d GPU(s) on %dxB200, "
                                    "NCCL point exchange (BASELINE.json configs[2])" % (lg, gpp, blk),
-                       "groups": world // blk, "gpus_per_party": gpp, "mask_prf": "masks pre-drawn outside the timed region", "setup_s": round(setup_s, 1),
+                       "groups": world // blk, "gpus_per_party": gpp, "mask_prf": "ChaCha12 masks drawn on the device inside the timed region", "setup_s": round(setup_s, 1),
                        "l2": "working set exceeds L2"},
             "e2e": {"value": nproofs / (ms * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 1344,
-                    "note": "host share/mask buffers uploaded every step; timed by wall clock between synchronisations"},
+                    "note": "host (pinned) share buffers uploaded every step; timed by wall clock between synchronisations"},
             "gpu_launches": int(launches), "clocks": clk,
             "net_bytes_per_party_per_proof": net.bytes_sent // (args.steps + args.warmup + 1),
         }))

@@ -26,6 +26,11 @@ class CsError(RuntimeError):
     pass
 
 
+class Rep3Prf(C.Structure):
+    _fields_ = [("seed1", C.c_uint8 * 32), ("word_pos1", C.c_uint64), ("seed2", C.c_uint8 * 32),
+                ("word_pos2", C.c_uint64), ("rounds", C.c_uint)]
+
+
 class KeyDesc(C.Structure):
     _fields_ = [
         ("curve", C.c_int),
@@ -70,6 +75,9 @@ SIGNATURES = {
     "cs_domain_size": (C.c_size_t, [C.c_void_p]),
     "cs_ifft_in_to_out": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
     "cs_fft_out_to_in": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_fft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_ifft": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
+    "cs_eval_poly": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p]),
     "cs_bit_reverse": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_uint]),
     "cs_ifft_in_to_out_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
     "cs_fft_out_to_in_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]),
@@ -78,6 +86,8 @@ SIGNATURES = {
     "cs_vec_sub": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_vec_scale_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint]),
     "cs_rep3_local_mul_vec": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_rep3_masks_device": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint, C.c_size_t, C.c_void_p]),
+    "cs_chacha_keystream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_void_p]),
     "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
     "cs_groth16_pk_free": (None, [C.c_void_p]),
@@ -86,6 +96,7 @@ SIGNATURES = {
     "cs_groth16_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_rep3_local_parts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint] + [C.c_void_p] * 11),
+    "cs_groth16_rep3_local_prf": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint] + [C.c_void_p] * 12),
     "cs_groth16_shamir_local": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 9),
     "cs_groth16_rep3_local": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 11),
     "cs_point_scalar_mul": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -276,6 +287,21 @@ class Context:
         self._check(self.lib.cs_domain_create(self.h, curve, log_n, _ptr(g), C.byref(h)))
         return Domain(self, h, curve, log_n)
 
+    def rep3_masks_device(self, curve, seed1, pos1, seed2, pos2, n, d_out, rounds=12):
+        self._check(self.lib.cs_rep3_masks_device(self.h, curve, bytes(seed1), pos1, bytes(seed2), pos2, rounds, n,
+                                                  C.c_void_p(d_out)))
+
+    def chacha_keystream(self, key, first_block, rounds, nblocks):
+        out = np.zeros(nblocks * 16, dtype=np.uint32)
+        self._check(self.lib.cs_chacha_keystream(self.h, bytes(key), first_block, rounds, nblocks, _ptr(out)))
+        return out
+
+    def eval_poly(self, curve, d_coeffs, n, point_mont, batch=1):
+        out = np.zeros((batch, 4), dtype=np.uint64)
+        self._check(self.lib.cs_eval_poly(self.h, curve, C.c_void_p(d_coeffs), n, batch,
+                                          _ptr(np.ascontiguousarray(point_mont, dtype=np.uint64)), _ptr(out)))
+        return out
+
     def roots_of_unity(self, curve, power):
         gen = np.zeros(4, dtype=np.uint64)
         shift = np.zeros(4, dtype=np.uint64)
@@ -317,6 +343,13 @@ class Domain:
         else:
             self.ctx._check(self.ctx.lib.cs_fft_out_to_in(self.ctx.h, self.h, C.c_void_p(data), batch))
         return data
+
+    def fft(self, d_data, batch=1):
+        """natural in -> natural out on a device buffer (co-plonk's domain.fft)."""
+        self.ctx._check(self.ctx.lib.cs_fft(self.ctx.h, self.h, C.c_void_p(d_data), batch))
+
+    def ifft(self, d_data, batch=1):
+        self.ctx._check(self.ctx.lib.cs_ifft(self.ctx.h, self.h, C.c_void_p(d_data), batch))
 
     def free(self):
         if self.h:
@@ -400,13 +433,23 @@ class Groth16Key:
             _ptr(a), _ptr(b), _ptr(c)))
         return a, b, c
 
-    def rep3_local(self, party, public_inputs, witness_shares, mask1, mask2, r_share, s_share, parts=31):
-        """-> (g_a, g1_b, g2_b, l_acc, h_acc) affine Montgomery half shares.  parts: CS_PART_* bitmask."""
+    def rep3_local(self, party, public_inputs, witness_shares, mask1, mask2, r_share, s_share, parts=31, prf=None):
+        """-> (g_a, g1_b, g2_b, l_acc, h_acc) affine Montgomery half shares.  parts: CS_PART_* bitmask.
+        prf = (seed1, pos1, seed2, pos2[, rounds]) draws the two mask vectors on the device instead."""
         g1 = lambda: np.zeros(2 * self.fq, dtype=np.uint64)
         ga, gb1, gb2, l, h = g1(), g1(), np.zeros(4 * self.fq, dtype=np.uint64), g1(), g1()
-        self.ctx._check(self.ctx.lib.cs_groth16_rep3_local_parts(
+        p = None
+        if prf is not None:
+            p = Rep3Prf()
+            p.seed1[:] = list(bytes(prf[0]))
+            p.word_pos1 = prf[1]
+            p.seed2[:] = list(bytes(prf[2]))
+            p.word_pos2 = prf[3]
+            p.rounds = prf[4] if len(prf) > 4 else 12
+        self.ctx._check(self.ctx.lib.cs_groth16_rep3_local_prf(
             self.ctx.h, self.h, party, parts, _ptr(public_inputs), _ptr(witness_shares), _ptr(mask1), _ptr(mask2),
-            _ptr(r_share), _ptr(s_share), _ptr(ga), _ptr(gb1), _ptr(gb2), _ptr(l), _ptr(h)))
+            C.byref(p) if p is not None else None, _ptr(r_share), _ptr(s_share), _ptr(ga), _ptr(gb1), _ptr(gb2),
+            _ptr(l), _ptr(h)))
         return ga, gb1, gb2, l, h
 
     def shamir_local(self, public_inputs, witness_shares, r_share, s_share):

@@ -123,6 +123,7 @@ void cs_ctx_destroy(cs_ctx* ctx) {
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   ctx->io.release();
+  ctx->prf_keys.release();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -494,6 +495,20 @@ int cs_bit_reverse(cs_ctx* ctx, cs_curve curve, uint64_t* d_data, unsigned log_n
   return 0;
 }
 
+// natural-order transforms of co-plonk (`domain.fft / domain.ifft` on a Radix2EvaluationDomain with the
+// snarkjs generator, co-plonk/src/mpc/rep3.rs:140-152, types.rs:76-100): the bit reversal the Groth16 path
+// elides is applied explicitly.
+int cs_fft(cs_ctx* ctx, const cs_domain* d, uint64_t* d_data, unsigned batch) {
+  if (!ctx || !d || !d_data) return fail(CS_ERR_ARG, "cs_fft: NULL argument");
+  CS_TRY(cs_bit_reverse(ctx, (cs_curve)d->curve, d_data, d->log_n, batch));
+  return cs_fft_out_to_in(ctx, d, d_data, batch);
+}
+int cs_ifft(cs_ctx* ctx, const cs_domain* d, uint64_t* d_data, unsigned batch) {
+  if (!ctx || !d || !d_data) return fail(CS_ERR_ARG, "cs_ifft: NULL argument");
+  CS_TRY(cs_ifft_in_to_out(ctx, d, d_data, batch));
+  return cs_bit_reverse(ctx, (cs_curve)d->curve, d_data, d->log_n, batch);
+}
+
 static int ntt_host(cs_ctx* ctx, const cs_domain* d, uint64_t* h_data, unsigned batch, bool inv) {
   if (!ctx || !d || !h_data) return fail(CS_ERR_ARG, "ntt host wrapper: NULL argument");
   size_t bytes = ((size_t)1 << d->log_n) * batch * 32;
@@ -563,6 +578,42 @@ int cs_rep3_local_mul_vec(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const 
   return 0;
 }
 
+// Rep3Rand::masking_field_elements_vec on the device (rngs.rs:137-156)
+int cs_rep3_masks_device(cs_ctx* ctx, cs_curve curve, const uint8_t* h_seed1, uint64_t word_pos1, const uint8_t* h_seed2,
+                         uint64_t word_pos2, unsigned rounds, size_t n, uint64_t* d_out) {
+  if (!ctx || !h_seed1 || !h_seed2 || (n && !d_out)) return fail(CS_ERR_ARG, "cs_rep3_masks_device: NULL argument");
+  if (rounds == 0 || (rounds & 1) || rounds > 20) return fail(CS_ERR_ARG, "cs_rep3_masks_device: rounds must be even, <= 20");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_TRY(ctx->prf_keys.reserve(64));
+  uint8_t keys[64];
+  memcpy(keys, h_seed1, 32);
+  memcpy(keys + 32, h_seed2, 32);
+  CS_CUDA(cudaMemcpyAsync(ctx->prf_keys.p, keys, 64, cudaMemcpyHostToDevice, ctx->stream));
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_masks<typename Cfg::FrP>, ceil_div(n, 128), 128, 0, ctx->stream, ctx->prf_keys.as<uint32_t>(),
+              word_pos1, word_pos2, rounds, n, reinterpret_cast<uint32_t*>(d_out));
+  });
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));  // `keys` is a stack buffer
+  return 0;
+}
+
+int cs_chacha_keystream(cs_ctx* ctx, const uint8_t* h_key, uint64_t first_block, unsigned rounds, unsigned nblocks,
+                        uint32_t* h_out_words) {
+  if (!ctx || !h_key || !h_out_words) return fail(CS_ERR_ARG, "cs_chacha_keystream: NULL argument");
+  if (nblocks == 0) return 0;
+  CS_TRY(ctx->io.reserve(32 + (size_t)nblocks * 64));
+  CS_CUDA(cudaMemcpyAsync(ctx->io.p, h_key, 32, cudaMemcpyHostToDevice, ctx->stream));
+  uint32_t* d_out = ctx->io.as<uint32_t>() + 8;
+  CS_LAUNCH(k_chacha_keystream, ceil_div(nblocks, 64), 64, 0, ctx->stream, ctx->io.as<uint32_t>(), first_block, rounds,
+            nblocks, d_out);
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaMemcpyAsync(h_out_words, d_out, (size_t)nblocks * 64, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int cs_rep3_to_shamir(cs_ctx* ctx, cs_curve curve, const uint64_t* x, const uint64_t* h_ca, const uint64_t* h_cb,
                       uint64_t* out, size_t n) {
   if (!ctx || !x || !h_ca || !h_cb || !out) return fail(CS_ERR_ARG, "cs_rep3_to_shamir: NULL argument");
@@ -578,6 +629,54 @@ int cs_rep3_to_shamir(cs_ctx* ctx, cs_curve curve, const uint64_t* x, const uint
   });
   CS_CUDA(cudaGetLastError());
   CS_CUDA(cudaStreamSynchronize(ctx->stream));  // io staging is reused by later calls
+  return 0;
+}
+
+}  // extern "C"
+
+namespace cs {
+template <class Cfg>
+int eval_poly_t(cs_ctx* ctx, const uint64_t* d_coeffs, size_t n, unsigned batch, const uint64_t* h_point, uint64_t* h_out) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HF;
+  HF x;
+  memcpy(x.l, h_point, sizeof(x.l));
+  for (unsigned c = 0; c < batch; c++) memset(h_out + c * HF::N, 0, sizeof(x.l));
+  if (n == 0) return 0;
+  // table: point, then (point^POLY_CHUNK)^(2^j)
+  std::vector<HF> tab(1 + 48);
+  tab[0] = x;
+  HF pc = x;
+  for (unsigned k = 1; k < POLY_CHUNK; k <<= 1) pc = pc.sqr();  // POLY_CHUNK is a power of two
+  for (int j = 0; j < 48; j++) { tab[1 + j] = pc; pc = pc.sqr(); }
+  const unsigned threads = 128;
+  const size_t nchunks = (n + POLY_CHUNK - 1) / POLY_CHUNK;
+  const unsigned blocks = ceil_div(nchunks, threads);
+  CS_TRY(ctx->io.reserve(tab.size() * sizeof(HF) + (size_t)blocks * batch * sizeof(HF)));
+  uint32_t* d_tab = ctx->io.as<uint32_t>();
+  uint32_t* d_sums = d_tab + tab.size() * FrP::N;
+  CS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+  CS_LAUNCH_SYNC(k_poly_eval<FrP>, blocks, threads, (size_t)threads * batch * sizeof(HF), ctx->stream,
+                 reinterpret_cast<const uint32_t*>(d_coeffs), n, batch, d_tab, d_tab + FrP::N, d_sums);
+  CS_CUDA(cudaGetLastError());
+  std::vector<HF> sums((size_t)blocks * batch);
+  CS_CUDA(cudaMemcpyAsync(sums.data(), d_sums, sums.size() * sizeof(HF), cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (unsigned c = 0; c < batch; c++) {
+    HF acc = HF::zero();
+    for (unsigned b = 0; b < blocks; b++) acc = acc + sums[(size_t)b * batch + c];
+    memcpy(h_out + c * HF::N, acc.l, sizeof(acc.l));
+  }
+  return 0;
+}
+}  // namespace cs
+
+extern "C" {
+int cs_eval_poly(cs_ctx* ctx, cs_curve curve, const uint64_t* d_coeffs, size_t n, unsigned batch,
+                 const uint64_t* h_point_mont, uint64_t* h_out) {
+  if (!ctx || !h_point_mont || !h_out || (n && !d_coeffs)) return fail(CS_ERR_ARG, "cs_eval_poly: NULL argument");
+  if (batch != 1 && batch != 2) return fail(CS_ERR_ARG, "cs_eval_poly: batch must be 1 or 2");
+  CS_DISPATCH_CURVE(curve, { return eval_poly_t<Cfg>(ctx, d_coeffs, n, batch, h_point_mont, h_out); });
   return 0;
 }
 

@@ -152,7 +152,7 @@ template <class Cfg>
 int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint64_t* h_pub, const uint64_t* h_wit,
                 const uint64_t* d_wit_in, const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
                 uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h,
-                unsigned parts = CS_PART_ALL) {
+                unsigned parts = CS_PART_ALL, const cs_rep3_prf* prf = nullptr) {
   typedef HostGroup<Cfg, 0> H1;
   typedef HostGroup<Cfg, 1> H2;
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
@@ -174,7 +174,24 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
     if (do_l) CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
   }
   if (do_h) {
-    CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, h_m1 != nullptr, h_m2 != nullptr, ctx->stream)));
+    bool have_m1 = h_m1 != nullptr, have_m2 = h_m2 != nullptr;
+    if (prf && kind == CS_REP3) {
+      // masks drawn on the device from the party's two ChaCha streams (rngs.rs:137-156); the second
+      // vector continues 8 n words further, exactly as two consecutive fill_bytes calls would
+      typedef typename Cfg::FrP FrP;
+      const size_t n = pk->n;
+      CS_TRY(pk->d_m1.reserve(n * 32));
+      CS_TRY(pk->d_m2.reserve(n * 32));
+      CS_TRY(ctx->prf_keys.reserve(64));
+      CS_CUDA(cudaMemcpyAsync(ctx->prf_keys.p, prf->seed1, 32, cudaMemcpyHostToDevice, ctx->stream));
+      CS_CUDA(cudaMemcpyAsync((char*)ctx->prf_keys.p + 32, prf->seed2, 32, cudaMemcpyHostToDevice, ctx->stream));
+      CS_LAUNCH(k_rep3_masks<FrP>, ceil_div(n, 128), 128, 0, ctx->stream, ctx->prf_keys.as<uint32_t>(), prf->word_pos1,
+                prf->word_pos2, prf->rounds, n, pk->d_m1.as<uint32_t>());
+      CS_LAUNCH(k_rep3_masks<FrP>, ceil_div(n, 128), 128, 0, ctx->stream, ctx->prf_keys.as<uint32_t>(),
+                prf->word_pos1 + 8 * n, prf->word_pos2 + 8 * n, prf->rounds, n, pk->d_m2.as<uint32_t>());
+      have_m1 = have_m2 = true;
+    }
+    CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, have_m1, have_m2, ctx->stream)));
     CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
   }
   CS_TRY(ctx_join(ctx, 4));
@@ -419,6 +436,17 @@ int cs_groth16_rep3_local_parts(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsig
                                 const uint64_t* h_wit_shares, const uint64_t* h_m1, const uint64_t* h_m2,
                                 const uint64_t* r_share, const uint64_t* s_share, uint64_t* out_g_a,
                                 uint64_t* out_g1_b, uint64_t* out_g2_b, uint64_t* out_l, uint64_t* out_h) {
+  return cs_groth16_rep3_local_prf(ctx, pk, party, parts, h_pub, h_wit_shares, h_m1, h_m2, nullptr, r_share, s_share,
+                                   out_g_a, out_g1_b, out_g2_b, out_l, out_h);
+}
+
+int cs_groth16_rep3_local_prf(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsigned parts, const uint64_t* h_pub,
+                              const uint64_t* h_wit_shares, const uint64_t* h_m1, const uint64_t* h_m2,
+                              const cs_rep3_prf* prf, const uint64_t* r_share, const uint64_t* s_share,
+                              uint64_t* out_g_a, uint64_t* out_g1_b, uint64_t* out_g2_b, uint64_t* out_l,
+                              uint64_t* out_h) {
+  if (prf && (prf->rounds == 0 || (prf->rounds & 1) || prf->rounds > 20))
+    return fail(CS_ERR_ARG, "cs_groth16_rep3_local_prf: rounds must be even and <= 20");
   if (!ctx || !pk || !h_pub || (pk->nw && !h_wit_shares) || !r_share || !s_share || !out_g_a || !out_g1_b ||
       !out_g2_b || !out_l || !out_h)
     return fail(CS_ERR_ARG, "cs_groth16_rep3_local: NULL argument");
@@ -427,11 +455,11 @@ int cs_groth16_rep3_local_parts(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsig
   switch (pk->curve) {
     case CS_BN254:
       return local_phase<Bn254Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, nullptr, h_m1, h_m2, r_share, s_share,
-                                   out_g_a, out_g1_b, out_g2_b, out_l, out_h, parts);
+                                   out_g_a, out_g1_b, out_g2_b, out_l, out_h, parts, prf);
 #if defined(CS_ENABLE_BLS12_381)
     case CS_BLS12_381:
       return local_phase<Bls381Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit_shares, nullptr, h_m1, h_m2, r_share, s_share,
-                                    out_g_a, out_g1_b, out_g2_b, out_l, out_h, parts);
+                                    out_g_a, out_g1_b, out_g2_b, out_l, out_h, parts, prf);
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");
   }

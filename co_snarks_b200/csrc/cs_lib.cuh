@@ -9,6 +9,7 @@
 #include "cs_msm.cuh"
 #include "cs_ntt.cuh"
 #include "cs_vec.cuh"
+#include "cs_prf.cuh"
 #include "cs_host_field.h"
 #include "../../include/cosnarks_gpu.h"
 
@@ -53,6 +54,7 @@ struct cs_ctx {
   cudaEvent_t ev_side[cs::CS_NSIDE] = {};
   cs::MsmWorkspace msm_ws[cs::CS_NSIDE];
   cs::DevBuf io;  // staging for host-buffer convenience calls
+  cs::DevBuf prf_keys;
 };
 
 struct cs_bases {

@@ -1,0 +1,90 @@
+// On-device Rep3 mask generation: ChaCha keystream -> from_be_bytes_mod_order -> a - b.
+//
+// Replaces `Rep3Rand::masking_field_elements_vec` (mpc-core/src/protocols/rep3/rngs.rs:137-156) with
+// RngType = rand_chacha::ChaCha12Rng (mpc-core/src/lib.rs:13): for each of the two correlated streams the
+// seed is the ChaCha key, the block counter is 64-bit starting at 0, the stream id is 0 and 12 rounds
+// are run; element i takes keystream words [pos + 8i, pos + 8i + 8), reads them as 32 big-endian bytes
+// and reduces mod r.  The host keeps the ChaCha12Rng objects (seed + word position) and advances them
+// by 8n words per call, so masks never cross PCIe.
+#pragma once
+#include "cs_common.cuh"
+#include "cs_field.cuh"
+#include "cs_ntt.cuh"  // st_fr
+
+namespace cs {
+
+CS_D uint32_t rotl32(uint32_t x, int n) { return (x << n) | (x >> (32 - n)); }
+
+#define CS_QR(a, b, c, d)                     \
+  a += b; d = rotl32(d ^ a, 16);              \
+  c += d; b = rotl32(b ^ c, 12);              \
+  a += b; d = rotl32(d ^ a, 8);               \
+  c += d; b = rotl32(b ^ c, 7);
+
+CS_D void chacha_block(const uint32_t* key, uint64_t counter, uint32_t rounds, uint32_t* out) {
+  uint32_t s[16], x[16];
+  s[0] = 0x61707865u; s[1] = 0x3320646eu; s[2] = 0x79622d32u; s[3] = 0x6b206574u;
+  CS_UNROLL
+  for (int i = 0; i < 8; i++) s[4 + i] = key[i];
+  s[12] = (uint32_t)counter; s[13] = (uint32_t)(counter >> 32); s[14] = 0; s[15] = 0;
+  CS_UNROLL
+  for (int i = 0; i < 16; i++) x[i] = s[i];
+  for (uint32_t r = 0; r < rounds; r += 2) {
+    CS_QR(x[0], x[4], x[8], x[12]) CS_QR(x[1], x[5], x[9], x[13]) CS_QR(x[2], x[6], x[10], x[14]) CS_QR(x[3], x[7], x[11], x[15])
+    CS_QR(x[0], x[5], x[10], x[15]) CS_QR(x[1], x[6], x[11], x[12]) CS_QR(x[2], x[7], x[8], x[13]) CS_QR(x[3], x[4], x[9], x[14])
+  }
+  CS_UNROLL
+  for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
+}
+
+CS_D uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xff00u) | ((v << 8) & 0xff0000u) | (v << 24); }
+
+// 8 keystream words starting at word position `w` -> field element (Montgomery) of the big-endian value mod r
+template <class FrP>
+CS_D Fp<FrP> prf_field_element(const uint32_t* key, uint64_t w, uint32_t rounds) {
+  uint32_t blk[16], words[8];
+  uint64_t b0 = w >> 4;
+  uint32_t off = (uint32_t)(w & 15);
+  chacha_block(key, b0, rounds, blk);
+  uint32_t got = 0;
+  for (uint32_t k = off; k < 16 && got < 8; k++) words[got++] = blk[k];
+  if (got < 8) {
+    chacha_block(key, b0 + 1, rounds, blk);
+    for (uint32_t k = 0; got < 8; k++) words[got++] = blk[k];
+  }
+  // bytes of the keystream read big-endian: least significant limb = byte-swapped last word
+  Fp<FrP> v;
+  CS_UNROLL
+  for (int j = 0; j < 8; j++) v.l[j] = bswap32(words[7 - j]);
+  // v < 2^256 is not reduced.  R^2 * v with R^2 as the multiplicand keeps every row of the word-serial
+  // product inside its bounds (the unreduced operand is consumed one limb at a time) and the result
+  // (R^2 v + m r) / R < 2 r is brought to [0, r) by the final subtraction: v R mod r.
+  return Fp<FrP>::r2() * v;
+}
+
+// out[i] = F(stream1, pos1 + 8 i) - F(stream2, pos2 + 8 i)      (rngs.rs:103-106,137-156)
+template <class FrP>
+CS_GLOBAL void k_rep3_masks(const uint32_t* __restrict__ keys /* 16 words: key1 | key2 */, uint64_t pos1,
+                            uint64_t pos2, uint32_t rounds, size_t n, uint32_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k1[8], k2[8];
+  CS_UNROLL
+  for (int j = 0; j < 8; j++) { k1[j] = keys[j]; k2[j] = keys[8 + j]; }
+  Fp<FrP> a = prf_field_element<FrP>(k1, pos1 + 8 * i, rounds);
+  Fp<FrP> b = prf_field_element<FrP>(k2, pos2 + 8 * i, rounds);
+  st_fr<FrP>(out + i * FrP::N, a - b);
+}
+
+// raw keystream words (test hook: RFC 7539 block vector with rounds = 20)
+static CS_GLOBAL void k_chacha_keystream(const uint32_t* __restrict__ key, uint64_t first_block, uint32_t rounds,
+                                         uint32_t nblocks, uint32_t* __restrict__ out) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nblocks) return;
+  uint32_t k[8], blk[16];
+  for (int j = 0; j < 8; j++) k[j] = key[j];
+  chacha_block(k, first_block + b, rounds, blk);
+  for (int j = 0; j < 16; j++) out[(size_t)b * 16 + j] = blk[j];
+}
+
+}  // namespace cs

@@ -95,6 +95,53 @@ CS_GLOBAL void k_rep3_to_shamir(const uint32_t* __restrict__ x, const uint32_t* 
   }
 }
 
+// eval_poly (mpc-core/src/protocols/rep3/poly.rs:42-68; plain: DensePolynomial::evaluate): the reference
+// splits the coefficients into per-thread chunks, runs Horner on each, scales by point^(chunk start) and
+// sums.  Same here: one thread per chunk of POLY_CHUNK coefficients, shared-memory tree per block; the
+// per-block sums (`batch` components each) are added up by the caller.
+constexpr unsigned POLY_CHUNK = 64;
+template <class FrP>
+CS_GLOBAL void k_poly_eval(const uint32_t* __restrict__ coeffs, size_t n, uint32_t batch,
+                           const uint32_t* __restrict__ point, const uint32_t* __restrict__ point_chunk_pows,
+                           uint32_t* __restrict__ block_sums) {
+  constexpr int NW = FrP::N;
+  CS_DYN_SMEM(uint32_t, sm);  // blockDim.x * batch elements
+  typedef Fp<FrP> F;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t lo = t * POLY_CHUNK;
+  F x = ld_fr<FrP>(point);
+  F acc[2];
+  acc[0] = F::zero();
+  acc[1] = F::zero();
+  if (lo < n) {
+    size_t hi = lo + POLY_CHUNK < n ? lo + POLY_CHUNK : n;
+    for (size_t k = hi; k-- > lo;) {
+      acc[0] = acc[0] * x + ld_fr<FrP>(coeffs + (k * batch) * NW);
+      if (batch == 2) acc[1] = acc[1] * x + ld_fr<FrP>(coeffs + (k * batch + 1) * NW);
+    }
+    // scale by point^lo = (point^POLY_CHUNK)^t, square-and-multiply over the table of squarings
+    F pw = F::one();
+    for (uint32_t j = 0; (t >> j) != 0; j++)
+      if ((t >> j) & 1) pw = pw * ld_fr<FrP>(point_chunk_pows + (size_t)j * NW);
+    acc[0] = acc[0] * pw;
+    if (batch == 2) acc[1] = acc[1] * pw;
+  }
+  for (uint32_t c = 0; c < batch; c++) st_fr<FrP>(sm + ((size_t)threadIdx.x * batch + c) * NW, acc[c]);
+  __syncthreads();
+  for (uint32_t step = blockDim.x >> 1; step > 0; step >>= 1) {
+    if (threadIdx.x < step)
+      for (uint32_t c = 0; c < batch; c++) {
+        uint32_t* mine = sm + ((size_t)threadIdx.x * batch + c) * NW;
+        F v = ld_fr<FrP>(mine) + ld_fr<FrP>(sm + ((size_t)(threadIdx.x + step) * batch + c) * NW);
+        st_fr<FrP>(mine, v);
+      }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (uint32_t c = 0; c < batch; c++)
+      st_fr<FrP>(block_sums + ((size_t)blockIdx.x * batch + c) * NW, ld_fr<FrP>(sm + (size_t)c * NW));
+}
+
 // evaluate_constraint over CSR rows.  One thread per row.
 //   wit: n_wit entries of `batch` components (1: plain value / half share; 2: Rep3 share {a,b})
 //   pub: n_pub public inputs (pub[0] = 1).  Column index < n_pub selects a public input.

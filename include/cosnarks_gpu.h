@@ -116,6 +116,16 @@ size_t cs_domain_size(const cs_domain* dom);
 int cs_ifft_in_to_out(cs_ctx* ctx, const cs_domain* dom, uint64_t* d_data, unsigned batch);
 int cs_fft_out_to_in(cs_ctx* ctx, const cs_domain* dom, uint64_t* d_data, unsigned batch);
 int cs_bit_reverse(cs_ctx* ctx, cs_curve curve, uint64_t* d_data, unsigned log_n, unsigned batch);
+/* Natural-order transforms as co-plonk uses them (`T::fft / T::ifft` = domain.fft / domain.ifft on the
+ * snarkjs-rooted Radix2EvaluationDomain, co-plonk/src/mpc/rep3.rs:140-152, types.rs:76-100): natural in,
+ * natural out; data must hold domain-size elements (zero-pad shorter inputs as arkworks does). */
+int cs_fft(cs_ctx* ctx, const cs_domain* dom, uint64_t* d_data, unsigned batch);
+int cs_ifft(cs_ctx* ctx, const cs_domain* dom, uint64_t* d_data, unsigned batch);
+/* evaluate_poly_public / rep3::poly::eval_poly (mpc-core/src/protocols/rep3/poly.rs:42-68): evaluate the
+ * (shared) polynomial with n coefficients (`batch` components each, device memory) at a public point;
+ * h_out receives `batch` field elements (the share of the evaluation). */
+int cs_eval_poly(cs_ctx* ctx, cs_curve curve, const uint64_t* d_coeffs, size_t n, unsigned batch,
+                 const uint64_t* h_point_mont, uint64_t* h_out);
 /* host-buffer convenience wrappers (copy in, transform, copy out) -- what a drop-in for the
  * `&mut [T]` signatures of the reference binds to */
 int cs_ifft_in_to_out_host(cs_ctx* ctx, const cs_domain* dom, uint64_t* h_data, unsigned batch);
@@ -136,6 +146,15 @@ int cs_vec_sub(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t*
 int cs_vec_scale_table(cs_ctx* ctx, cs_curve curve, uint64_t* d_x, const uint64_t* d_table, size_t n, unsigned batch);
 int cs_rep3_local_mul_vec(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b,
                           const uint64_t* d_mask, uint64_t* d_out, size_t n);
+/* Rep3Rand::masking_field_elements_vec on the device (mpc-core/src/protocols/rep3/rngs.rs:137-156,
+ * RngType = rand_chacha::ChaCha12Rng): seeds = the two ChaCha keys (own stream / previous party's stream),
+ * word_pos = each rng's current position in 32-bit words (ChaCha12Rng::get_word_pos), rounds = 12.
+ * Writes n masks a_i - b_i (Montgomery) to device memory; the caller advances both rngs by 8 n words.
+ * cs_chacha_keystream is the test hook for the block function (RFC 7539 vector with rounds = 20). */
+int cs_rep3_masks_device(cs_ctx* ctx, cs_curve curve, const uint8_t* h_seed1, uint64_t word_pos1,
+                         const uint8_t* h_seed2, uint64_t word_pos2, unsigned rounds, size_t n, uint64_t* d_out);
+int cs_chacha_keystream(cs_ctx* ctx, const uint8_t* h_key, uint64_t first_block, unsigned rounds, unsigned nblocks,
+                        uint32_t* h_out_words);
 int cs_rep3_to_shamir(cs_ctx* ctx, cs_curve curve, const uint64_t* d_x, const uint64_t* h_ca_mont,
                       const uint64_t* h_cb_mont, uint64_t* d_out, size_t n);
 
@@ -211,6 +230,21 @@ int cs_groth16_rep3_local_parts(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsig
                                 const uint64_t* h_mask1, const uint64_t* h_mask2, const uint64_t* h_r_share,
                                 const uint64_t* h_s_share, uint64_t* out_g_a, uint64_t* out_g1_b,
                                 uint64_t* out_g2_b, uint64_t* out_l_acc, uint64_t* out_h_acc);
+
+/* The same with the two witness-map mask vectors drawn ON THE DEVICE from the party's correlated ChaCha
+ * streams (Rep3Rand, rngs.rs:86-156): mask1 uses words [pos, pos + 8n) of each stream, mask2 the next 8n
+ * words (two consecutive masking_field_elements_vec calls, reduction.rs:160,182); the caller advances
+ * both rngs by 16 n words.  prf == NULL falls back to the host-supplied h_mask1 / h_mask2. */
+typedef struct {
+  uint8_t seed1[32]; uint64_t word_pos1;   /* this party's stream  (rng1) */
+  uint8_t seed2[32]; uint64_t word_pos2;   /* previous party's stream (rng2) */
+  unsigned rounds;                         /* 12 = ChaCha12Rng */
+} cs_rep3_prf;
+int cs_groth16_rep3_local_prf(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsigned parts,
+                              const uint64_t* h_public_inputs, const uint64_t* h_witness_shares,
+                              const uint64_t* h_mask1, const uint64_t* h_mask2, const cs_rep3_prf* prf,
+                              const uint64_t* h_r_share, const uint64_t* h_s_share, uint64_t* out_g_a,
+                              uint64_t* out_g1_b, uint64_t* out_g2_b, uint64_t* out_l_acc, uint64_t* out_h_acc);
 
 /* ShamirGroth16Driver's local phase (co-groth16/src/mpc/shamir.rs:29-119): identical arithmetic to the plain
  * driver on degree-t shares -- every party adds the public terms/points; outputs are degree-2t point shares

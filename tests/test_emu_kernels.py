@@ -57,3 +57,11 @@ def test_emu_msm_rep3_shares(emu_ctx):
 
 def test_emu_groth16_shamir_local(emu_ctx):
     K.check_groth16_shamir_local(emu_ctx)
+
+
+def test_emu_plonk_primitives(emu_ctx):
+    K.check_plonk_primitives(emu_ctx, lg=5)
+
+
+def test_emu_rep3_mask_prf(emu_ctx):
+    K.check_rep3_mask_prf(emu_ctx, n=40)

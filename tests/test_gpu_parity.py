@@ -84,3 +84,11 @@ def test_msm_rep3_shares(gpu_ctx):
 
 def test_groth16_shamir_local(gpu_ctx):
     K.check_groth16_shamir_local(gpu_ctx)
+
+
+def test_plonk_primitives(gpu_ctx):
+    K.check_plonk_primitives(gpu_ctx, lg=11)
+
+
+def test_rep3_mask_prf(gpu_ctx):
+    K.check_rep3_mask_prf(gpu_ctx, n=5000)
