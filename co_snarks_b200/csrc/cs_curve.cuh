@@ -27,10 +27,12 @@ struct Fp2 {
   // mul / sqr are out-of-line (one copy per kernel) to keep the G2 point formulas in the I-cache.
   friend CS_D Fp2 operator*(const Fp2& a, const Fp2& b) { return mul_ool(a, b); }
   static CS_DN Fp2 mul_ool(Fp2 a, Fp2 b) {
-    // Karatsuba: 3 base multiplications
-    F v0 = a.c0 * b.c0, v1 = a.c1 * b.c1;
+    // Karatsuba: 3 base multiplications, inlined HERE (not three calls) so that ptxas can interleave the
+    // three independent carry chains: the G2 kernels run at 2-3 resident blocks and need the ILP
+    F v0 = F::mul_inline(a.c0, b.c0), v1 = F::mul_inline(a.c1, b.c1);
+    F v2 = F::mul_inline(a.c0 + a.c1, b.c0 + b.c1);
     Fp2 r;
-    r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - v0 - v1;
+    r.c1 = v2 - v0 - v1;
     r.c0 = v0 - v1;
     return r;
   }
@@ -38,8 +40,8 @@ struct Fp2 {
   static CS_DN Fp2 sqr_ool(Fp2 a) {
     // (c0 + c1 u)^2 = (c0 + c1)(c0 - c1) + 2 c0 c1 u
     Fp2 r;
-    F t = a.c0 * a.c1;
-    r.c0 = (a.c0 + a.c1) * (a.c0 - a.c1);
+    F t = F::mul_inline(a.c0, a.c1);
+    r.c0 = F::mul_inline(a.c0 + a.c1, a.c0 - a.c1);
     r.c1 = t + t;
     return r;
   }

@@ -73,6 +73,15 @@ class Rep3Network:
         return conv(outs[self.prev]), conv(outs[self.next])
 
 
+def random_field_limbs(rng, n):
+    """n uniform field elements as canonical limbs [n, 4] from a numpy Generator (253-bit draws, < r);
+    used to build secret sharings of a witness (rep3.rs:281-293)."""
+    a = rng.integers(0, 2 ** 63, size=(n, 4), dtype=np.uint64) << np.uint64(1)
+    a |= rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    return a
+
+
 class PairLink:
     """Point-sized link between the two GPUs (ranks) of one party."""
 

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from co_snarks_b200 import binding as B
-from co_snarks_b200.rep3 import Rep3State
+from co_snarks_b200.rep3 import random_field_limbs
 from workloads.synth_groth16 import SynthGroth16
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
@@ -13,7 +13,7 @@ syn = SynthGroth16(ctx, lg, valid=False)
 pk = syn.make_key()
 n = 1 << lg
 rng = np.random.Generator(np.random.PCG64(1))
-fes = lambda k: Rep3State._fes(rng, k)
+fes = lambda k: random_field_limbs(rng, k)
 nw = syn.m - syn.ni
 shares = np.concatenate([fes(nw), fes(nw)], axis=1)
 m1, m2 = fes(n), fes(n)
