@@ -20,7 +20,8 @@
 
 namespace cs {
 
-constexpr unsigned MSM_SLICE = 32;      // entries per slice (levels 0 and 1 of the segmented reduction)
+constexpr unsigned MSM_SLICE_MAX = 64;  // entries per slice (levels 0 and 1 of the segmented reduction): 32 or 64
+constexpr unsigned MSM_ORDER_BLOCK = 256;
 constexpr unsigned MSM_RED_SEG = 16;    // buckets per thread in the weighted bucket reduction
 constexpr unsigned MSM_SIGN = 0x80000000u;
 
@@ -88,7 +89,7 @@ CS_GLOBAL void k_msm_infmask(const Affine<F>* __restrict__ table, uint32_t n, ui
 // --------------------------------------------------------------------------- scans (one block)
 // From count[0..B]: start = exclusive scan of count; ns0[b] = ceil(count[b]/S), ns1 = ceil(ns0/S);
 // sstart0 / sstart1 = exclusive scans.  Arrays have B + 2 entries (last = total).
-static CS_GLOBAL void k_msm_scan(const uint32_t* __restrict__ count, uint32_t nb1 /* B + 1 */,
+static CS_GLOBAL void k_msm_scan(const uint32_t* __restrict__ count, uint32_t nb1 /* B + 1 */, uint32_t MSM_SLICE,
                           uint32_t* __restrict__ start, uint32_t* __restrict__ sstart0,
                           uint32_t* __restrict__ sstart1) {
   __shared__ uint32_t sm[3][1024];
@@ -149,22 +150,96 @@ CS_D uint32_t find_bucket(const uint32_t* __restrict__ arr, uint32_t nb1, uint32
   return lo;
 }
 
+// --------------------------------------------------------------------------- slice order (by length)
+// Slices of one warp should have the same length, otherwise every lane waits for the longest one
+// (bucket loads are Poisson: with 2^19 buckets and ~26 entries each the warp maximum is ~1.4x the
+// mean).  A counting sort of the slices by length, longest first: per-block shared-memory histograms
+// (k_msm_slice_hist), one thread per length scanning the block columns (k_msm_slice_offsets), then a
+// scatter with block-local ranks (k_msm_slice_order).  order[] = slice id, order_b[] = its bucket.
+static CS_GLOBAL void k_msm_slice_hist(const uint32_t* __restrict__ count, const uint32_t* __restrict__ sstart0,
+                                       uint32_t nb1, uint32_t S, uint32_t* __restrict__ slice_len,
+                                       uint32_t* __restrict__ slice_bkt, uint32_t* __restrict__ block_hist) {
+  __shared__ uint32_t h[MSM_SLICE_MAX + 1];
+  for (uint32_t k = threadIdx.x; k <= MSM_SLICE_MAX; k += blockDim.x) h[k] = 0;
+  __syncthreads();
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < sstart0[nb1]) {
+    uint32_t lo = 0, hi = nb1;  // largest b with sstart0[b] <= s
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (sstart0[mid] <= s) lo = mid; else hi = mid;
+    }
+    uint32_t j = s - sstart0[lo];
+    uint32_t len = count[lo] - j * S;
+    if (len > S) len = S;
+    slice_len[s] = len;
+    slice_bkt[s] = lo;
+    atomicAdd(&h[len], 1u);
+  }
+  __syncthreads();
+  for (uint32_t k = threadIdx.x; k <= MSM_SLICE_MAX; k += blockDim.x)
+    block_hist[(size_t)blockIdx.x * (MSM_SLICE_MAX + 1) + k] = h[k];
+}
+
+// thread L (one per length): block_hist[.][L] -> exclusive offsets over blocks; len_base[L] = start of the
+// region of length-L slices in `order` (descending length), computed by thread 0 after a barrier.
+static CS_GLOBAL void k_msm_slice_offsets(uint32_t* __restrict__ block_hist, uint32_t nblocks,
+                                          uint32_t* __restrict__ len_base) {
+  __shared__ uint32_t tot[MSM_SLICE_MAX + 1];
+  uint32_t L = threadIdx.x;
+  if (L <= MSM_SLICE_MAX) {
+    uint32_t run = 0;
+    for (uint32_t b = 0; b < nblocks; b++) {
+      uint32_t v = block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L];
+      block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L] = run;
+      run += v;
+    }
+    tot[L] = run;
+  }
+  __syncthreads();
+  if (L == 0) {
+    uint32_t run = 0;
+    for (int k = MSM_SLICE_MAX; k >= 0; k--) { len_base[k] = run; run += tot[k]; }
+  }
+}
+
+static CS_GLOBAL void k_msm_slice_order(const uint32_t* __restrict__ slice_len, const uint32_t* __restrict__ slice_bkt,
+                                        uint32_t nslices_max, const uint32_t* __restrict__ sstart0, uint32_t nb1,
+                                        const uint32_t* __restrict__ block_off, const uint32_t* __restrict__ len_base,
+                                        uint32_t* __restrict__ order, uint32_t* __restrict__ order_b) {
+  __shared__ uint32_t h[MSM_SLICE_MAX + 1];
+  for (uint32_t k = threadIdx.x; k <= MSM_SLICE_MAX; k += blockDim.x) h[k] = 0;
+  __syncthreads();
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < sstart0[nb1]) {
+    uint32_t len = slice_len[s];
+    uint32_t rank = atomicAdd(&h[len], 1u);
+    uint32_t pos = len_base[len] + block_off[(size_t)blockIdx.x * (MSM_SLICE_MAX + 1) + len] + rank;
+    order[pos] = s;
+    order_b[pos] = slice_bkt[s];
+  }
+}
+
 // --------------------------------------------------------------------------- accumulation level 0
-// One thread per slice of <= MSM_SLICE sorted entries of ONE bucket: mixed additions from the table.
+// One thread per slice of <= S sorted entries of ONE bucket: mixed additions from the table.  Threads take
+// slices in length order (order[]), so the lanes of a warp run the same number of additions.
 template <class F, int MINB>
 CS_GLOBAL void __launch_bounds__(128, MINB) k_msm_accum0(const Affine<F>* __restrict__ table,
-                                                   const uint32_t* __restrict__ sorted,
-                                                   const uint32_t* __restrict__ count,
-                                                   const uint32_t* __restrict__ start,
-                                                   const uint32_t* __restrict__ sstart0, uint32_t nb1,
-                                                   Xyzz<F>* __restrict__ part0) {
-  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= sstart0[nb1]) return;
-  uint32_t b = find_bucket(sstart0, nb1, s);
+                                                         const uint32_t* __restrict__ sorted,
+                                                         const uint32_t* __restrict__ count,
+                                                         const uint32_t* __restrict__ start,
+                                                         const uint32_t* __restrict__ sstart0, uint32_t nb1, uint32_t S,
+                                                         const uint32_t* __restrict__ order,
+                                                         const uint32_t* __restrict__ order_b,
+                                                         Xyzz<F>* __restrict__ part0) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= sstart0[nb1]) return;
+  uint32_t s = order[t];
+  uint32_t b = order_b[t];
   uint32_t j = s - sstart0[b];
-  uint32_t beg = start[b] + j * MSM_SLICE;
+  uint32_t beg = start[b] + j * S;
   uint32_t end = start[b] + count[b];
-  if (end > beg + MSM_SLICE) end = beg + MSM_SLICE;
+  if (end > beg + S) end = beg + S;
   Xyzz<F> acc = Xyzz<F>::inf();
   uint32_t e = sorted[beg];
   Affine<F> p = table[e & ~MSM_SIGN];
@@ -184,15 +259,15 @@ CS_GLOBAL void __launch_bounds__(128, MINB) k_msm_accum0(const Affine<F>* __rest
 template <class F>
 CS_GLOBAL void __launch_bounds__(128) k_msm_accum1(const Xyzz<F>* __restrict__ part0,
                                                    const uint32_t* __restrict__ sstart0,
-                                                   const uint32_t* __restrict__ sstart1, uint32_t nb1,
+                                                   const uint32_t* __restrict__ sstart1, uint32_t nb1, uint32_t S,
                                                    Xyzz<F>* __restrict__ part1) {
   uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= sstart1[nb1]) return;
   uint32_t b = find_bucket(sstart1, nb1, s);
   uint32_t j = s - sstart1[b];
-  uint32_t beg = sstart0[b] + j * MSM_SLICE;
+  uint32_t beg = sstart0[b] + j * S;
   uint32_t end = sstart0[b + 1];
-  if (end > beg + MSM_SLICE) end = beg + MSM_SLICE;
+  if (end > beg + S) end = beg + S;
   Xyzz<F> acc = part0[beg];
   for (uint32_t k = beg + 1; k < end; k++) padd(acc, part0[k]);
   part1[s] = acc;
@@ -243,14 +318,15 @@ CS_GLOBAL void __launch_bounds__(128) k_msm_reduce_seg(const Xyzz<F>* __restrict
   red[t] = tot;
 }
 
-// Single block: sum `cnt` points into out[0].
+// Block b sums red[k] for k = b*T + t, stride gridDim.x*T, into out[b] (shared-memory tree); launched
+// twice: many blocks, then one block over the block results.
 template <class F>
 CS_GLOBAL void k_msm_final_sum(const Xyzz<F>* __restrict__ red, uint32_t cnt,
                                                       Xyzz<F>* __restrict__ out) {
   CS_DYN_SMEM(Xyzz<F>, sm);
   const uint32_t T = blockDim.x, t = threadIdx.x;
   Xyzz<F> acc = Xyzz<F>::inf();
-  for (uint32_t k = t; k < cnt; k += T) padd(acc, red[k]);
+  for (uint32_t k = blockIdx.x * T + t; k < cnt; k += gridDim.x * T) padd(acc, red[k]);
   sm[t] = acc;
   __syncthreads();
   for (uint32_t step = T >> 1; step > 0; step >>= 1) {
@@ -261,7 +337,7 @@ CS_GLOBAL void k_msm_final_sum(const Xyzz<F>* __restrict__ red, uint32_t cnt,
     }
     __syncthreads();
   }
-  if (t == 0) out[0] = sm[0];
+  if (t == 0) out[blockIdx.x] = sm[0];
 }
 
 // --------------------------------------------------------------------------- table precomputation
@@ -324,6 +400,10 @@ static inline MsmShape msm_shape(uint32_t scalar_bits, uint32_t c) {
   return s;
 }
 
+// Window size.  The work is W n mixed additions + ~4 * 2^(c-1) full additions in the bucket reduction
+// (running sums + the per-segment scalar multiple).  Measured on B200 at n = 2^20 (G1, dense):
+// c = 16: accumulate 2.90 ms, sort 0.42, fold+reduce 0.75;  c = 20: accumulate 2.34 ms but sort 1.32 and
+// fold+reduce 1.0 -- the 2^19-bucket phases eat the gain, so 16 stays the cap (window_bits overrides).
 static inline uint32_t msm_auto_window(size_t n) {
   int lg = 0;
   while ((1ull << (lg + 1)) <= n) lg++;
@@ -332,10 +412,16 @@ static inline uint32_t msm_auto_window(size_t n) {
   if (c > 16) c = 16;
   return (uint32_t)c;
 }
+static inline uint32_t msm_slice(const MsmShape& sh) {
+  const char* e = getenv("CS_MSM_SLICE");  // test hook: exercise the 64-entry path with few buckets
+  if (e && atoi(e) == 64) return 64u;
+  if (e && atoi(e) == 32) return 32u;
+  return sh.c >= 18 ? 64u : 32u;
+}
 
 constexpr int MSM_NSTAGE = 5;  // digits | scan+scatter | accum0 | accum1+2 | reduce+final
 struct MsmWorkspace {
-  DevBuf dig, sorted, meta, part0, part1, bucket, red, scal, result;
+  DevBuf dig, sorted, meta, part0, part1, bucket, red, scal, result, order;
   void* h_result = nullptr;  // pinned, holds one Xyzz
   size_t h_result_cap = 0;
   bool profile = false;      // record CUDA events at the stage boundaries (bench.py roofline)
@@ -352,7 +438,7 @@ struct MsmWorkspace {
       ev[i] = nullptr;
     }
     dig.release(); sorted.release(); meta.release(); part0.release(); part1.release();
-    bucket.release(); red.release(); scal.release(); result.release();
+    bucket.release(); red.release(); scal.release(); result.release(); order.release();
     if (h_result) cudaFreeHost(h_result);
     h_result = nullptr;
     h_result_cap = 0;
@@ -369,8 +455,9 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   const size_t nent = (size_t)sh.W * n;
   if (nent >= (1ull << 31) || (size_t)sh.W * nbases >= (1ull << 31))
     return fail(-3, "msm: W*n = %zu exceeds 2^31 entries", nent);
-  const size_t max_s0 = nent / MSM_SLICE + nb1;
-  const size_t max_s1 = max_s0 / MSM_SLICE + nb1;
+  const uint32_t S = msm_slice(sh);
+  const size_t max_s0 = nent / S + nb1;
+  const size_t max_s1 = max_s0 / S + nb1;
   CS_TRY(ws.dig.reserve(nent * 4));
   CS_TRY(ws.sorted.reserve(nent * 4));
   // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1]
@@ -381,14 +468,25 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_TRY(ws.bucket.reserve((size_t)nb1 * sizeof(Xyzz<F>)));
   const uint32_t L = sh.B < MSM_RED_SEG ? sh.B : MSM_RED_SEG;
   const uint32_t nseg = (sh.B + L - 1) / L;
-  CS_TRY(ws.red.reserve((size_t)nseg * sizeof(Xyzz<F>)));
-  CS_TRY(ws.result.reserve(sizeof(Xyzz<F>)));
   const uint32_t fs_threads = sizeof(Xyzz<F>) > 128 ? 128 : 256;  // <= 32 KB of dynamic shared memory
+  const uint32_t fs_blocks = nseg > 4 * fs_threads ? (nseg + fs_threads - 1) / fs_threads : 1;
+  CS_TRY(ws.red.reserve(((size_t)nseg + fs_blocks) * sizeof(Xyzz<F>)));
+  CS_TRY(ws.result.reserve(sizeof(Xyzz<F>)));
+  // slice order: slice_len | slice_bkt | order | order_b (max_s0 each) | block_hist | len_base
+  const uint32_t ob = ceil_div(max_s0, MSM_ORDER_BLOCK);
+  const size_t order_words = 4 * max_s0 + (size_t)ob * (MSM_SLICE_MAX + 1) + (MSM_SLICE_MAX + 1);
+  CS_TRY(ws.order.reserve(order_words * 4));
   if (ws.h_result_cap < sizeof(Xyzz<F>)) {
     if (ws.h_result) cudaFreeHost(ws.h_result);
     CS_CUDA(cudaMallocHost(&ws.h_result, sizeof(Xyzz<F>)));
     ws.h_result_cap = sizeof(Xyzz<F>);
   }
+  uint32_t* slice_len = ws.order.as<uint32_t>();
+  uint32_t* slice_bkt = slice_len + max_s0;
+  uint32_t* order = slice_bkt + max_s0;
+  uint32_t* order_b = order + max_s0;
+  uint32_t* block_hist = order_b + max_s0;
+  uint32_t* len_base = block_hist + (size_t)ob * (MSM_SLICE_MAX + 1);
   uint32_t* count = ws.meta.as<uint32_t>();
   uint32_t* cursor = count + nb1;
   uint32_t* start = cursor + nb1;
@@ -399,18 +497,22 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W, infmask, offset,
             ws.dig.as<uint32_t>(), count);
   CS_TRY(ws.mark(1, st));
-  CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, start, sstart0, sstart1);
+  CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, S, start, sstart0, sstart1);
   CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
             offset, start, cursor, ws.sorted.as<uint32_t>());
+  CS_LAUNCH_SYNC(k_msm_slice_hist, ob, MSM_ORDER_BLOCK, 0, st, count, sstart0, nb1, S, slice_len, slice_bkt, block_hist);
+  CS_LAUNCH_SYNC(k_msm_slice_offsets, 1, 128, 0, st, block_hist, ob, len_base);
+  CS_LAUNCH_SYNC(k_msm_slice_order, ob, MSM_ORDER_BLOCK, 0, st, slice_len, slice_bkt, (uint32_t)max_s0, sstart0, nb1,
+                 block_hist, len_base, order, order_b);
   CS_TRY(ws.mark(2, st));
   {
     // resident blocks per SM (register cap) -- tuned on B200, overridable for experiments
     static int minb_env = -1;
     if (minb_env < 0) { const char* e = getenv("CS_ACCUM0_MINB"); minb_env = e ? atoi(e) : 0; }
-    const int minb = minb_env ? minb_env : (sizeof(F) > 32 ? 2 : 4);
+    const int minb = minb_env ? minb_env : (sizeof(F) > 32 ? 3 : 4);
 #define CS_ACC0(M)                                                                                              \
   CS_LAUNCH(k_msm_accum0<F COMMA M>, ceil_div(max_s0, 128), 128, 0, st, table, ws.sorted.as<uint32_t>(), count, \
-            start, sstart0, nb1, ws.part0.as<Xyzz<F>>())
+            start, sstart0, nb1, S, order, order_b, ws.part0.as<Xyzz<F>>())
     switch (minb) {
       case 2: CS_ACC0(2); break;
       case 3: CS_ACC0(3); break;
@@ -422,14 +524,22 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   }
   CS_TRY(ws.mark(3, st));
   CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,
-            nb1, ws.part1.as<Xyzz<F>>());
+            nb1, S, ws.part1.as<Xyzz<F>>());
   CS_LAUNCH(k_msm_accum2<F>, ceil_div(nb1, 128), 128, 0, st, ws.part1.as<Xyzz<F>>(), sstart1, nb1,
             ws.bucket.as<Xyzz<F>>());
   CS_TRY(ws.mark(4, st));
   CS_LAUNCH(k_msm_reduce_seg<F>, ceil_div(nseg, 128), 128, 0, st, ws.bucket.as<Xyzz<F>>(), sh.B, L,
             ws.red.as<Xyzz<F>>());
-  CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
-                 ws.result.as<Xyzz<F>>());
+  if (fs_blocks > 1) {
+    Xyzz<F>* stage = ws.red.as<Xyzz<F>>() + nseg;
+    CS_LAUNCH_SYNC(k_msm_final_sum<F>, fs_blocks, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
+                   stage);
+    CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, stage, fs_blocks,
+                   ws.result.as<Xyzz<F>>());
+  } else {
+    CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
+                   ws.result.as<Xyzz<F>>());
+  }
   CS_TRY(ws.mark(5, st));
   CS_CUDA(cudaMemcpyAsync(ws.h_result, ws.result.p, sizeof(Xyzz<F>), cudaMemcpyDeviceToHost, st));
   CS_CUDA(cudaGetLastError());

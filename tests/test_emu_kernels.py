@@ -24,6 +24,12 @@ def test_emu_msm_g1(emu_ctx):
     K.check_msm(emu_ctx, 0, 120, window_bits=(0, 7))
 
 
+def test_emu_msm_g1_slice64(emu_ctx, monkeypatch):
+    """the 64-entries-per-slice path used for windows >= 18 bits, forced on a small bucket count"""
+    monkeypatch.setenv("CS_MSM_SLICE", "64")
+    K.check_msm(emu_ctx, 0, 300, window_bits=(5,))
+
+
 def test_emu_msm_g2(emu_ctx):
     K.check_msm(emu_ctx, 1, 40, window_bits=(0,))
 

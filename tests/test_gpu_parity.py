@@ -28,7 +28,7 @@ def test_ntt_multi_pass(gpu_ctx):
 
 
 def test_msm_g1(gpu_ctx):
-    K.check_msm(gpu_ctx, 0, 1500, window_bits=(0, 5, 11))
+    K.check_msm(gpu_ctx, 0, 1500, window_bits=(0, 5, 11, 19))
 
 
 def test_msm_g1_tiny(gpu_ctx):
@@ -36,7 +36,7 @@ def test_msm_g1_tiny(gpu_ctx):
 
 
 def test_msm_g2(gpu_ctx):
-    K.check_msm(gpu_ctx, 1, 300, window_bits=(0, 8))
+    K.check_msm(gpu_ctx, 1, 300, window_bits=(0, 8, 18))
 
 
 def test_msm_crs_points(gpu_ctx):
