@@ -86,10 +86,13 @@ SIGNATURES = {
     "cs_vec_sub": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_vec_scale_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint]),
     "cs_rep3_local_mul_vec": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_vec_lincomb": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_uint, C.c_size_t, C.c_void_p]),
     "cs_rep3_masks_device": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint, C.c_size_t, C.c_void_p]),
     "cs_chacha_keystream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_void_p]),
     "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
+    "cs_groth16_pk_from_zkey": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "cs_wtns_read": (C.c_int, [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "cs_groth16_pk_free": (None, [C.c_void_p]),
     "cs_groth16_domain_size": (C.c_size_t, [C.c_void_p]),
     "cs_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -287,6 +290,12 @@ class Context:
         self._check(self.lib.cs_domain_create(self.h, curve, log_n, _ptr(g), C.byref(h)))
         return Domain(self, h, curve, log_n)
 
+    def vec_lincomb(self, curve, d_inputs, weights_mont, n, d_out):
+        k = len(d_inputs)
+        arr = (C.c_void_p * k)(*[C.c_void_p(p) for p in d_inputs])
+        w = np.ascontiguousarray(weights_mont, dtype=np.uint64)
+        self._check(self.lib.cs_vec_lincomb(self.h, curve, arr, _ptr(w), k, n, C.c_void_p(d_out)))
+
     def rep3_masks_device(self, curve, seed1, pos1, seed2, pos2, n, d_out, rounds=12):
         self._check(self.lib.cs_rep3_masks_device(self.h, curve, bytes(seed1), pos1, bytes(seed2), pos2, rounds, n,
                                                   C.c_void_p(d_out)))
@@ -403,6 +412,20 @@ class Groth16Key:
         self.fq = limbs_of(curve, "fq")
         del keep
 
+    @classmethod
+    def from_zkey(cls, ctx, path, curve=CS_BN254, window_bits=0):
+        """Groth16ZKey::from_reader + upload in one step (cs_groth16_pk_from_zkey)."""
+        self = cls.__new__(cls)
+        self.ctx, self.curve = ctx, curve
+        h = C.c_void_p()
+        npub = C.c_size_t(0)
+        ctx._check(ctx.lib.cs_groth16_pk_from_zkey(ctx.h, os.fsencode(path), window_bits, C.byref(h), C.byref(npub)))
+        self.h = h
+        self.ni = npub.value + 1
+        self.nw = None
+        self.fq = limbs_of(curve, "fq")
+        return self
+
     def domain_size(self):
         return int(self.ctx.lib.cs_groth16_domain_size(self.h))
 
@@ -464,6 +487,17 @@ class Groth16Key:
         if self.h:
             self.ctx.lib.cs_groth16_pk_free(self.h)
             self.h = None
+
+
+def read_wtns(lib, path, curve=CS_BN254):
+    """witness.wtns -> np.uint64 [nVars, 4] Montgomery (Witness::from_reader)."""
+    n = C.c_size_t(0)
+    if lib.cs_wtns_read(os.fsencode(path), curve, None, 0, C.byref(n)):
+        raise CsError(lib.cs_last_error().decode())
+    out = np.zeros((n.value, 4), dtype=np.uint64)
+    if lib.cs_wtns_read(os.fsencode(path), curve, _ptr(out), n.value, C.byref(n)):
+        raise CsError(lib.cs_last_error().decode())
+    return out
 
 
 # host-side single-point helpers (run on the host inside the library; no context needed)

@@ -578,6 +578,27 @@ int cs_rep3_local_mul_vec(cs_ctx* ctx, cs_curve curve, const uint64_t* a, const 
   return 0;
 }
 
+int cs_vec_lincomb(cs_ctx* ctx, cs_curve curve, const uint64_t* const* d_inputs, const uint64_t* h_weights_mont, unsigned k,
+                   size_t n, uint64_t* d_out) {
+  if (!ctx || !d_inputs || !h_weights_mont || !d_out) return fail(CS_ERR_ARG, "cs_vec_lincomb: NULL argument");
+  if (k == 0 || k > LINCOMB_MAX) return fail(CS_ERR_ARG, "cs_vec_lincomb: k must be in [1, %u]", LINCOMB_MAX);
+  if (n == 0) return 0;
+  LincombArgs a;
+  memset(&a, 0, sizeof(a));
+  for (unsigned j = 0; j < k; j++) {
+    if (!d_inputs[j]) return fail(CS_ERR_ARG, "cs_vec_lincomb: input %u is NULL", j);
+    a.in[j] = reinterpret_cast<const uint32_t*>(d_inputs[j]);
+    memcpy(a.w[j], h_weights_mont + 4 * j, 32);
+  }
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_vec_lincomb<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, a, k, reinterpret_cast<uint32_t*>(d_out), n);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // Rep3Rand::masking_field_elements_vec on the device (rngs.rs:137-156)
 int cs_rep3_masks_device(cs_ctx* ctx, cs_curve curve, const uint8_t* h_seed1, uint64_t word_pos1, const uint8_t* h_seed2,
                          uint64_t word_pos2, unsigned rounds, size_t n, uint64_t* d_out) {

@@ -1,0 +1,197 @@
+// snarkjs .zkey / .wtns ingest straight into the device layout.
+//
+// The reference parses these with taceo-circom-types (`Groth16ZKey::from_reader`, `Witness::from_reader`;
+// co-circom/co-circom/src/bin/co-circom.rs:1005-1016) into arkworks structs and converts again per proof.
+// The binary formats already store what the kernels want: points as affine little-endian MONTGOMERY limbs
+// (all-zero = infinity) and one (matrix, row, signal, value) record per non-zero coefficient, so sections
+// 5-9 are handed to cs_groth16_pk_create without touching them and section 4 becomes the CSR arrays.
+// Layout facts (probed on test_vectors/): header section 2 = n8q, q, n8r, r, nVars, nPublic,
+// domainSize, alpha1, beta1, beta2, gamma2, delta1, delta2; section 4 values are in R^2-Montgomery form;
+// the A rows nConstraints .. nConstraints+nPublic are the public-input rows that
+// groth16/reduction.rs:111-113 re-inserts, so they are dropped from the matrices here.
+#include <stdio.h>
+#include <fstream>
+#include <map>
+#include "cs_lib.cuh"
+
+using namespace cs;
+
+namespace {
+
+struct Sections {
+  std::vector<uint8_t> data;
+  std::map<uint32_t, std::pair<size_t, size_t>> sec;  // type -> (offset, length)
+};
+
+int read_file(const char* path, const char* magic, Sections& s) {
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return fail(CS_ERR_ARG, "cannot open %s", path);
+  std::streamsize sz = f.tellg();
+  f.seekg(0);
+  s.data.resize((size_t)sz);
+  if (sz && !f.read((char*)s.data.data(), sz)) return fail(CS_ERR_ARG, "cannot read %s", path);
+  if (sz < 12 || memcmp(s.data.data(), magic, 4) != 0) return fail(CS_ERR_ARG, "%s: bad magic (expected '%s')", path, magic);
+  uint32_t nsec;
+  memcpy(&nsec, s.data.data() + 8, 4);
+  size_t off = 12;
+  for (uint32_t i = 0; i < nsec; i++) {
+    if (off + 12 > s.data.size()) return fail(CS_ERR_ARG, "%s: truncated section table", path);
+    uint32_t typ;
+    uint64_t len;
+    memcpy(&typ, s.data.data() + off, 4);
+    memcpy(&len, s.data.data() + off + 4, 8);
+    off += 12;
+    if (off + len > s.data.size()) return fail(CS_ERR_ARG, "%s: section %u exceeds the file", path, typ);
+    if (!s.sec.count(typ)) s.sec[typ] = {off, (size_t)len};
+    off += len;
+  }
+  return 0;
+}
+
+uint32_t rd32(const uint8_t* p) { uint32_t v; memcpy(&v, p, 4); return v; }
+
+// BN254 / BLS12-381 from the base-field modulus bytes
+int detect_curve(const uint8_t* q, uint32_t n8q) {
+  auto matches = [&](auto P, uint32_t nlimbs32) {
+    if (n8q != nlimbs32 * 4) return false;
+    for (uint32_t i = 0; i < nlimbs32; i++) if (rd32(q + 4 * i) != decltype(P)::mod((int)i)) return false;
+    return true;
+  };
+  if (matches(Bn254Fq{}, 8)) return CS_BN254;
+  if (matches(Bls381Fq{}, 12)) return CS_BLS12_381;
+  return -1;
+}
+
+template <class FrP>
+void coeff_from_r2(const uint8_t* src, uint64_t* dst) {
+  // stored x R^2 -> x R: one Montgomery reduction (multiply by 1)
+  host::HFp<FrP> v;
+  memcpy(v.l, src, sizeof(v.l));
+  host::HFp<FrP> r = v.from_mont();
+  memcpy(dst, r.l, sizeof(r.l));
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_groth16_pk_from_zkey(cs_ctx* ctx, const char* path, int window_bits, cs_groth16_pk** out, size_t* out_n_public) {
+  if (!ctx || !path || !out) return fail(CS_ERR_ARG, "cs_groth16_pk_from_zkey: NULL argument");
+  Sections z;
+  CS_TRY(read_file(path, "zkey", z));
+  for (uint32_t t = 1; t <= 9; t++)
+    if (!z.sec.count(t)) return fail(CS_ERR_ARG, "%s: section %u missing", path, t);
+  const uint8_t* d = z.data.data();
+  if (rd32(d + z.sec[1].first) != 1) return fail(CS_ERR_ARG, "%s: not a Groth16 zkey (protocol %u)", path, rd32(d + z.sec[1].first));
+  const uint8_t* h = d + z.sec[2].first;
+  uint32_t n8q = rd32(h);
+  const uint8_t* q = h + 4;
+  uint32_t n8r = rd32(q + n8q);
+  const uint8_t* p = q + n8q + 4 + n8r;
+  int curve = detect_curve(q, n8q);
+  if (curve < 0) return fail(CS_ERR_ARG, "%s: unsupported curve (base field of %u bytes)", path, n8q);
+#if !defined(CS_ENABLE_BLS12_381)
+  if (curve != CS_BN254) return fail(CS_ERR_ARG, "%s: BLS12-381 support is not compiled in", path);
+#endif
+  if (n8r != 32) return fail(CS_ERR_ARG, "%s: unexpected scalar field size %u", path, n8r);
+  uint32_t n_vars = rd32(p), n_public = rd32(p + 4), domain = rd32(p + 8);
+  p += 12;
+  const size_t g1 = 2 * n8q, g2 = 4 * n8q;
+  const uint8_t *alpha1 = p, *beta1 = p + g1, *beta2 = p + 2 * g1, *delta1 = p + 2 * g1 + 2 * g2, *delta2 = delta1 + g1;
+  if ((size_t)(delta2 + g2 - h) > z.sec[2].second) return fail(CS_ERR_ARG, "%s: header section too short", path);
+  // ---- section 4 -> CSR (A, B) without the trailing public-input rows
+  const uint8_t* c = d + z.sec[4].first;
+  uint32_t ncoef = rd32(c);
+  const size_t rec = 12 + n8r;
+  if (4 + (size_t)ncoef * rec > z.sec[4].second) return fail(CS_ERR_ARG, "%s: coefficient section too short", path);
+  uint32_t max_row = 0;
+  for (uint32_t i = 0; i < ncoef; i++) {
+    const uint8_t* r = c + 4 + (size_t)i * rec;
+    if (rd32(r) > 1) return fail(CS_ERR_ARG, "%s: coefficient %u names matrix %u", path, i, rd32(r));
+    if (rd32(r + 8) >= n_vars) return fail(CS_ERR_ARG, "%s: coefficient %u names signal %u >= nVars", path, i, rd32(r + 8));
+    if (rd32(r + 4) > max_row) max_row = rd32(r + 4);
+  }
+  if (ncoef && max_row + 1 < n_public + 1) return fail(CS_ERR_ARG, "%s: fewer rows than public inputs", path);
+  const size_t ni = (size_t)n_public + 1;
+  const size_t nc = ncoef ? (size_t)max_row + 1 - ni : 0;
+  std::vector<uint32_t> rp[2], col[2];
+  std::vector<uint64_t> cf[2];
+  for (int m = 0; m < 2; m++) rp[m].assign(nc + 1, 0);
+  for (uint32_t i = 0; i < ncoef; i++) {
+    const uint8_t* r = c + 4 + (size_t)i * rec;
+    uint32_t m = rd32(r), row = rd32(r + 4);
+    if (row < nc) rp[m][row + 1]++;
+  }
+  for (int m = 0; m < 2; m++) {
+    for (size_t k = 0; k < nc; k++) rp[m][k + 1] += rp[m][k];
+    col[m].resize(rp[m][nc]);
+    cf[m].resize((size_t)rp[m][nc] * 4);
+  }
+  std::vector<uint32_t> fill[2] = {std::vector<uint32_t>(rp[0].begin(), rp[0].end() - (nc ? 1 : 0)),
+                                   std::vector<uint32_t>(rp[1].begin(), rp[1].end() - (nc ? 1 : 0))};
+  for (uint32_t i = 0; i < ncoef; i++) {
+    const uint8_t* r = c + 4 + (size_t)i * rec;
+    uint32_t m = rd32(r), row = rd32(r + 4);
+    if (row >= nc) continue;
+    uint32_t pos = fill[m][row]++;
+    col[m][pos] = rd32(r + 8);
+    if (curve == CS_BN254) coeff_from_r2<Bn254Fr>(r + 12, &cf[m][(size_t)pos * 4]);
+    else coeff_from_r2<Bls381Fr>(r + 12, &cf[m][(size_t)pos * 4]);
+  }
+  // ---- descriptor pointing INTO the file image for every point array (copied only if the section
+  // happens to start at an address that is not 8-byte aligned: offsets in the format are multiples of 4)
+  std::vector<std::vector<uint64_t>> realigned;
+  auto aligned = [&](const uint8_t* src, size_t bytes) -> const uint64_t* {
+    if (((uintptr_t)src & 7) == 0) return (const uint64_t*)src;
+    realigned.emplace_back((bytes + 7) / 8);
+    memcpy(realigned.back().data(), src, bytes);
+    return realigned.back().data();
+  };
+  cs_groth16_key_desc k;
+  memset(&k, 0, sizeof(k));
+  k.curve = (cs_curve)curve;
+  k.num_constraints = nc;
+  k.num_instance_variables = ni;
+  k.num_witness_variables = n_vars - ni;
+  static const uint32_t zero_rp[1] = {0};
+  k.a_row_ptr = nc ? rp[0].data() : zero_rp; k.a_col = col[0].data(); k.a_coeff = cf[0].data(); k.a_nnz = col[0].size();
+  k.b_row_ptr = nc ? rp[1].data() : zero_rp; k.b_col = col[1].data(); k.b_coeff = cf[1].data(); k.b_nnz = col[1].size();
+  k.alpha_g1 = aligned(alpha1, g1); k.beta_g1 = aligned(beta1, g1); k.beta_g2 = aligned(beta2, g2);
+  k.delta_g1 = aligned(delta1, g1); k.delta_g2 = aligned(delta2, g2);
+  auto pts = [&](uint32_t t, size_t sz, const uint64_t*& ptr, size_t& len) {
+    ptr = aligned(d + z.sec[t].first, z.sec[t].second);
+    len = z.sec[t].second / sz;
+  };
+  pts(5, g1, k.a_query, k.a_query_len);
+  pts(6, g1, k.b_g1_query, k.b_g1_query_len);
+  pts(7, g2, k.b_g2_query, k.b_g2_query_len);
+  pts(8, g1, k.l_query, k.l_query_len);
+  pts(9, g1, k.h_query, k.h_query_len);
+  if (k.a_query_len != n_vars || k.h_query_len != domain)
+    return fail(CS_ERR_ARG, "%s: section sizes disagree with the header (A %zu vs nVars %u, H %zu vs domain %u)", path,
+                k.a_query_len, n_vars, k.h_query_len, domain);
+  k.window_bits = window_bits;
+  if (out_n_public) *out_n_public = n_public;
+  return cs_groth16_pk_create(ctx, &k, out);
+}
+
+int cs_wtns_read(const char* path, cs_curve curve, uint64_t* out_mont, size_t capacity, size_t* out_n) {
+  if (!path || !out_n) return fail(CS_ERR_ARG, "cs_wtns_read: NULL argument");
+  Sections w;
+  CS_TRY(read_file(path, "wtns", w));
+  if (!w.sec.count(1) || !w.sec.count(2)) return fail(CS_ERR_ARG, "%s: missing section", path);
+  const uint8_t* h = w.data.data() + w.sec[1].first;
+  uint32_t n8 = rd32(h);
+  uint32_t nvars = rd32(h + 4 + n8);
+  if (n8 != 32) return fail(CS_ERR_ARG, "%s: unexpected field size %u", path, n8);
+  if ((size_t)nvars * n8 > w.sec[2].second) return fail(CS_ERR_ARG, "%s: values section too short", path);
+  *out_n = nvars;
+  if (!out_mont) return 0;  // size query
+  if (capacity < nvars) return fail(CS_ERR_ARG, "cs_wtns_read: buffer holds %zu elements, file has %u", capacity, nvars);
+  // canonical little-endian -> Montgomery (ark Fr representation)
+  std::vector<uint64_t> tmp((size_t)nvars * 4);
+  memcpy(tmp.data(), w.data.data() + w.sec[2].first, (size_t)nvars * 32);
+  return cs_fr_to_mont(curve, tmp.data(), out_mont, nvars);
+}
+
+}  // extern "C"

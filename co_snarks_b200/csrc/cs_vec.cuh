@@ -95,6 +95,32 @@ CS_GLOBAL void k_rep3_to_shamir(const uint32_t* __restrict__ x, const uint32_t* 
   }
 }
 
+// out_i = sum_j w_j * in_j[i], j < k <= LINCOMB_MAX.  Shamir's king-based degree reduction
+// (mpc-core/src/protocols/shamir/network.rs:150-243): the "pair consumption" `inp += r_2t` / `share -= r_t`
+// are k = 2 calls with weights (1, +-1); the king's Lagrange-weighted accumulation over the 2t+1 received
+// vectors (:170-187) is one call with k = 2t+1; each party's fresh share `acc * c_id` (:196-214) is k = 1.
+constexpr unsigned LINCOMB_MAX = 8;
+struct LincombArgs {
+  const uint32_t* in[LINCOMB_MAX];
+  uint32_t w[LINCOMB_MAX][8];
+};
+template <class FrP>
+CS_GLOBAL void k_vec_lincomb(LincombArgs args, uint32_t k, uint32_t* __restrict__ out, size_t n) {
+  constexpr int NW = FrP::N;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    Fp<FrP> acc = Fp<FrP>::zero();
+    for (uint32_t j = 0; j < k; j++) {
+      Fp<FrP> w;
+      CS_UNROLL
+      for (int l = 0; l < NW; l++) w.l[l] = args.w[j][l];
+      acc = acc + ld_fr<FrP>(args.in[j] + i * NW) * w;
+    }
+    st_fr<FrP>(out + i * NW, acc);
+  }
+}
+
 // eval_poly (mpc-core/src/protocols/rep3/poly.rs:42-68; plain: DensePolynomial::evaluate): the reference
 // splits the coefficients into per-thread chunks, runs Horner on each, scales by point^(chunk start) and
 // sums.  Same here: one thread per chunk of POLY_CHUNK coefficients, shared-memory tree per block; the

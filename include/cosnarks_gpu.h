@@ -146,6 +146,12 @@ int cs_vec_sub(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t*
 int cs_vec_scale_table(cs_ctx* ctx, cs_curve curve, uint64_t* d_x, const uint64_t* d_table, size_t n, unsigned batch);
 int cs_rep3_local_mul_vec(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b,
                           const uint64_t* d_mask, uint64_t* d_out, size_t n);
+/* out_i = sum_{j<k} w_j * in_j[i]  (k <= 8, weights Montgomery on the host, vectors on the device).
+ * Shamir degree reduction (mpc-core/src/protocols/shamir/network.rs:150-243) in three uses: consuming a
+ * double-sharing pair (`inp += r_2t`, `share -= r_t`: weights 1, +-1), the king's Lagrange-weighted sum of the
+ * 2t+1 received vectors (:170-187), and the fresh share `acc * c_id` sent back to each party (:196-214). */
+int cs_vec_lincomb(cs_ctx* ctx, cs_curve curve, const uint64_t* const* d_inputs, const uint64_t* h_weights_mont,
+                   unsigned k, size_t n, uint64_t* d_out);
 /* Rep3Rand::masking_field_elements_vec on the device (mpc-core/src/protocols/rep3/rngs.rs:137-156,
  * RngType = rand_chacha::ChaCha12Rng): seeds = the two ChaCha keys (own stream / previous party's stream),
  * word_pos = each rng's current position in 32-bit words (ChaCha12Rng::get_word_pos), rounds = 12.
@@ -186,6 +192,14 @@ typedef struct {
 int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* desc, cs_groth16_pk** out);
 void cs_groth16_pk_free(cs_groth16_pk* pk);
 size_t cs_groth16_domain_size(const cs_groth16_pk* pk);
+
+/* snarkjs file ingest (what co-circom does with taceo-circom-types before calling prove,
+ * co-circom/co-circom/src/bin/co-circom.rs:1005-1016): a Groth16 .zkey goes straight to the device-resident
+ * key (its point sections already are Montgomery limb arrays), a .wtns to Montgomery field elements.
+ * cs_wtns_read with out_mont == NULL only reports the element count. */
+int cs_groth16_pk_from_zkey(cs_ctx* ctx, const char* zkey_path, int window_bits, cs_groth16_pk** out,
+                            size_t* out_n_public);
+int cs_wtns_read(const char* wtns_path, cs_curve curve, uint64_t* out_mont, size_t capacity, size_t* out_n);
 
 int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party,
                            const uint64_t* h_public_inputs, const uint64_t* h_witness,

@@ -418,3 +418,131 @@ def check_rep3_mask_prf(ctx, n=100):
         assert got == OC.masking_field_elements_vec(seeds[p], pos[p], seeds[prev], pos[prev], n, cv.r)
         tot = [(x + y) % cv.r for x, y in zip(tot, got)]
     assert tot == [0] * n
+
+
+def check_shamir_degree_reduce(ctx, n=64, seed=12):
+    """Shamir king-based degree reduction (shamir/network.rs:150-243) assembled from cs_vec_lincomb, for
+    n = 3 parties, t = 1: every party masks its degree-2t product share with r_2t, the king interpolates
+    with the Lagrange weights, re-shares, and r_t is subtracted -- the result must be a degree-t sharing
+    of the products."""
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    nparties, t = 3, 1
+
+    def share(v, deg):
+        co = [v] + [rng.randrange(r) for _ in range(deg)]
+        return [sum(c * pow(i + 1, e, r) for e, c in enumerate(co)) % r for i in range(nparties)]
+
+    a = [rng.randrange(r) for _ in range(n)]
+    b = [rng.randrange(r) for _ in range(n)]
+    sa, sb = [share(x, t) for x in a], [share(x, t) for x in b]
+    pairs = []
+    for _ in range(n):
+        rr = rng.randrange(r)
+        pairs.append((share(rr, t), share(rr, 2 * t)))
+    # lagrange weights for interpolation at 0 from points 1..3
+    lam = []
+    for i in range(nparties):
+        num, den = 1, 1
+        for j in range(nparties):
+            if j != i:
+                num = num * (-(j + 1)) % r
+                den = den * ((i + 1) - (j + 1)) % r
+        lam.append(num * pow(den, r - 2, r) % r)
+    one, minus_one = 1, r - 1
+    masked = []
+    for p in range(nparties):
+        da = ctx.to_device(cv.fr([sa[i][p] for i in range(n)]))
+        db = ctx.to_device(cv.fr([sb[i][p] for i in range(n)]))
+        dprod = ctx.alloc(n * 32)
+        ctx._check(ctx.lib.cs_vec_mul(ctx.h, cv.id, da, db, dprod, n))   # shamir local_mul_vec (arithmetic.rs:73-80)
+        d2t = ctx.to_device(cv.fr([pairs[i][1][p] for i in range(n)]))
+        dm = ctx.alloc(n * 32)
+        ctx.vec_lincomb(cv.id, [dprod, d2t], cv.fr([one, one]), n, dm)   # inp += r_2t
+        masked.append(dm)
+        for d in (da, db, dprod, d2t):
+            ctx.free(d)
+    dacc = ctx.alloc(n * 32)
+    ctx.vec_lincomb(cv.id, masked, cv.fr(lam), n, dacc)                  # king: sum_j lambda_j * inp_j
+    acc = cv.fr_back(ctx.d2h(dacc, (n, 4)))
+    # the king sees a*b + r (the double-sharing pair's secret masks the product)
+    assert acc == [(x * y + sum(l * pairs[i][1][p] for p, l in enumerate(lam))) % r for i, (x, y) in enumerate(zip(a, b))]
+    # fresh degree-t shares of the public value acc: here the trivial re-sharing acc + 0 * x, then share -= r_t
+    final = []
+    for p in range(nparties):
+        drt = ctx.to_device(cv.fr([pairs[i][0][p] for i in range(n)]))
+        dout = ctx.alloc(n * 32)
+        ctx.vec_lincomb(cv.id, [dacc, drt], cv.fr([one, minus_one]), n, dout)  # share -= r_t
+        final.append(cv.fr_back(ctx.d2h(dout, (n, 4))))
+        ctx.free(drt)
+        ctx.free(dout)
+    # opening the degree-t result from parties 1, 2 (weights 2, -1) gives a * b
+    for i in range(n):
+        assert (2 * final[0][i] - final[1][i]) % r == a[i] * b[i] % r
+    for d in masked + [dacc]:
+        ctx.free(d)
+
+
+def check_zkey_ingest(ctx, tmp_path, name="multiplier2"):
+    """cs_groth16_pk_from_zkey + cs_wtns_read (co-circom.rs:1005-1016): a snarkjs-format key/witness pair goes
+    file -> device and proves to the golden proof bytes; the writer's output is also parsed by the oracle's
+    reader, and -- when the reference tree is mounted -- the reference's own files are ingested too."""
+    import os
+    import zkey_writer
+    from oracle import formats as OF
+    from oracle.formats import proof_to_json
+    cv = Conv("bn254")
+    z, m, w, g = golden_groth16(name)
+    zp, wp = os.path.join(str(tmp_path), name + ".zkey"), os.path.join(str(tmp_path), name + ".wtns")
+    zkey_writer.write_zkey(zp, z, m)
+    zkey_writer.write_wtns(wp, cv.r, w)
+    z2 = OF.read_groth16_zkey(zp)  # the test writer agrees with the oracle's reader
+    assert z2["a_query"] == z["a_query"] and OF.zkey_matrices(z2)["a"] == m["a"]
+    files = [(zp, wp)]
+    ref = "/root/reference/test_vectors/Groth16/bn254/%s/" % name
+    if os.path.isdir(ref):
+        files.append((ref + "circuit.zkey", ref + "witness.wtns"))
+    for zf, wf in files:
+        pk = B.Groth16Key.from_zkey(ctx, zf)
+        assert pk.domain_size() == g["domain_size"] and pk.ni == m["num_instance_variables"]
+        wit = B.read_wtns(ctx.lib, wf)
+        assert cv.fr_back(wit) == w
+        for pr in g["oracle_proofs"]:
+            A, Bp, Cp = pk.prove_plain(np.ascontiguousarray(wit[:pk.ni]), np.ascontiguousarray(wit[pk.ni:]),
+                                       cv.fr([ih(pr["r"])]), cv.fr([ih(pr["s"])]))
+            assert proof_to_json(cv.pt1(A), cv.pt2(Bp), cv.pt1(Cp)) == pr["json"]
+        pk.free()
+    # error behaviour
+    bad = os.path.join(str(tmp_path), "bad.zkey")
+    open(bad, "wb").write(b"nope" + bytes(20))
+    try:
+        B.Groth16Key.from_zkey(ctx, bad)
+        raise AssertionError("bad magic must fail")
+    except B.CsError as e:
+        assert "bad magic" in str(e)
+
+
+def check_prove_cli(ctx_lib_path, tmp_path, name="multiplier2"):
+    """python -m co_snarks_b200.prove: zkey + wtns in, snarkjs-layout proof.json out, accepted by the pairing
+    check under the fixture's verification key (the acceptance test of co-groth16/src/lib.rs:40-91)."""
+    import json
+    import os
+    import zkey_writer
+    from co_snarks_b200 import prove as P
+    from oracle.formats import read_proof_json
+    cv = Conv("bn254")
+    z, m, w, g = golden_groth16(name)
+    zp, wp = os.path.join(str(tmp_path), "c.zkey"), os.path.join(str(tmp_path), "w.wtns")
+    zkey_writer.write_zkey(zp, z, m)
+    zkey_writer.write_wtns(wp, cv.r, w)
+    out, pub = os.path.join(str(tmp_path), "proof.json"), os.path.join(str(tmp_path), "public.json")
+    argv = ["--zkey", zp, "--wtns", wp, "--out", out, "--public-out", pub]
+    if ctx_lib_path:
+        argv += ["--lib", ctx_lib_path]
+    P.main(argv)
+    proof = read_proof_json(out)
+    public = [int(x) for x in json.load(open(pub))]
+    assert public == [ih(x) for x in g["public"]]
+    assert groth16_verify(OG.vk_from_zkey(z), public, proof)
+    assert json.load(open(out))["protocol"] == "groth16"

@@ -71,3 +71,18 @@ def test_emu_plonk_primitives(emu_ctx):
 
 def test_emu_rep3_mask_prf(emu_ctx):
     K.check_rep3_mask_prf(emu_ctx, n=40)
+
+
+def test_emu_shamir_degree_reduce(emu_ctx):
+    K.check_shamir_degree_reduce(emu_ctx, n=20)
+
+
+def test_emu_zkey_ingest(emu_ctx, tmp_path):
+    K.check_zkey_ingest(emu_ctx, tmp_path, "multiplier2")
+
+
+def test_emu_prove_cli(emu_ctx, tmp_path):
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "emu"))
+    import build_emu
+    K.check_prove_cli(build_emu.OUT, tmp_path)

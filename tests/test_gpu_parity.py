@@ -92,3 +92,15 @@ def test_plonk_primitives(gpu_ctx):
 
 def test_rep3_mask_prf(gpu_ctx):
     K.check_rep3_mask_prf(gpu_ctx, n=5000)
+
+
+def test_shamir_degree_reduce(gpu_ctx):
+    K.check_shamir_degree_reduce(gpu_ctx, n=3000)
+
+
+def test_zkey_ingest(gpu_ctx, tmp_path):
+    K.check_zkey_ingest(gpu_ctx, tmp_path, "poseidon")
+
+
+def test_prove_cli(gpu_ctx, tmp_path):
+    K.check_prove_cli(None, tmp_path, "poseidon")
