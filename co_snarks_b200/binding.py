@@ -44,6 +44,7 @@ class KeyDesc(C.Structure):
         ("l_query", u64p), ("l_query_len", C.c_size_t),
         ("h_query", u64p), ("h_query_len", C.c_size_t),
         ("window_bits", C.c_int),
+        ("c_row_ptr", u32p), ("c_col", u32p), ("c_coeff", u64p), ("c_nnz", C.c_size_t),
     ]
 
 
@@ -96,6 +97,7 @@ SIGNATURES = {
     "cs_groth16_pk_free": (None, [C.c_void_p]),
     "cs_groth16_domain_size": (C.c_size_t, [C.c_void_p]),
     "cs_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_groth16_witness_map_libsnark": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_rep3_local_parts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint] + [C.c_void_p] * 11),
@@ -384,7 +386,9 @@ class Groth16Key:
         d.num_instance_variables = matrices_csr["num_instance_variables"]
         d.num_witness_variables = matrices_csr["num_witness_variables"]
         keep = []
-        for name in ("a", "b"):
+        for name in ("a", "b", "c"):
+            if name not in matrices_csr:
+                continue
             rp, col, coeff = matrices_csr[name]
             rp = np.ascontiguousarray(rp, dtype=np.uint32)
             col = np.ascontiguousarray(col, dtype=np.uint32)
@@ -435,6 +439,14 @@ class Groth16Key:
         self.ctx._check(self.ctx.lib.cs_groth16_witness_map(
             self.ctx.h, self.h, kind, party, _ptr(np.ascontiguousarray(public_inputs, dtype=np.uint64)),
             _ptr(np.ascontiguousarray(witness, dtype=np.uint64)), _ptr(mask1), _ptr(mask2), _ptr(out)))
+        return out
+
+    def witness_map_libsnark(self, public_inputs, witness, kind=CS_PLAIN, party=0, mask=None):
+        n = self.domain_size()
+        out = np.zeros((n, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_groth16_witness_map_libsnark(
+            self.ctx.h, self.h, kind, party, _ptr(np.ascontiguousarray(public_inputs, dtype=np.uint64)),
+            _ptr(np.ascontiguousarray(witness, dtype=np.uint64)), _ptr(mask), _ptr(out)))
         return out
 
     def prove_plain(self, public_inputs, witness, r_mont, s_mont):

@@ -22,6 +22,11 @@ struct cs_groth16_pk {
   cs_domain* dom = nullptr;
   DevBuf coset_tab;  // shift^bitrev(p) / n
   DevBuf d_pub, d_wit, d_a, d_b, d_c, d_m1, d_m2, d_pubscal;
+  // LibSnarkReduction (reduction.rs:241-342): C matrix, arkworks domain, coset = GENERATOR
+  DevBuf c_rowptr, c_col, c_coeff;
+  bool have_c = false;
+  cs_domain* dom_ark = nullptr;
+  DevBuf coset_tab_ark, ginv_pows, vinv_over_n;
 };
 
 namespace {
@@ -99,10 +104,10 @@ int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, cons
   CS_TRY(pk->d_c.reserve((size_t)n * 32));
   // a = A w (+ promoted public rows, reduction.rs:104-113), b = B w   (evaluate_constraint)
   CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->a_rowptr.as<uint32_t>(), pk->a_col.as<uint32_t>(),
-            pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch,
+            pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch, batch,
             pub_comp, (uint32_t)pk->nc, (uint32_t)pk->ni, n, pk->d_a.as<uint32_t>());
   CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->b_rowptr.as<uint32_t>(), pk->b_col.as<uint32_t>(),
-            pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch,
+            pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch, batch,
             pub_comp, (uint32_t)pk->nc, 0u, n, pk->d_b.as<uint32_t>());
   unsigned blocks = ceil_div(n, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -131,6 +136,98 @@ int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, cons
   else
     CS_LAUNCH(k_plain_mul_sub<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
               pk->d_c.as<uint32_t>(), pk->d_c.as<uint32_t>(), (size_t)n);
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Lazily builds what LibSnarkReduction needs: Domain::new (arkworks generator), the bit-reversed coset
+// table GENERATOR^rev(p) / n, the natural-order powers GENERATOR^-i and the constant (g^n - 1)^-1 / n.
+template <class Cfg>
+int ensure_libsnark(cs_ctx* ctx, cs_groth16_pk* pk) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HF;
+  if (pk->dom_ark) return 0;
+  if (!pk->have_c) return fail(CS_ERR_STATE, "LibSnarkReduction needs the C matrix (cs_groth16_key_desc.c_*)");
+  CS_TRY(cs_domain_create(ctx, (cs_curve)pk->curve, pk->log_n, nullptr, &pk->dom_ark));
+  const size_t n = pk->n;
+  HF g = HF::from_u64(std::is_same<Cfg, Bn254Cfg>::value ? 5 : 7);  // F::GENERATOR
+  HF ginv = g.inverse();
+  HF ninv = HF::from_u64(n).inverse();
+  uint64_t e[HF::N] = {0};
+  e[0] = n;
+  HF vinv = (g.pow(e, HF::N) - HF::one()).inverse();  // vanishing polynomial over the coset, inverted
+  HF c = vinv * ninv;
+  std::vector<HF> pw(32 + 1 + 32);
+  HF a = g, b = ginv;
+  for (int j = 0; j < 32; j++) { pw[j] = a; pw[33 + j] = b; a = a.sqr(); b = b.sqr(); }
+  pw[32] = ninv;
+  DevBuf dpw;
+  CS_TRY(dpw.reserve(pw.size() * sizeof(HF)));
+  CS_CUDA(cudaMemcpyAsync(dpw.p, pw.data(), pw.size() * sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+  CS_TRY(pk->coset_tab_ark.reserve(n * sizeof(HF)));
+  CS_TRY(pk->ginv_pows.reserve(n * sizeof(HF)));
+  CS_TRY(pk->vinv_over_n.reserve(sizeof(HF)));
+  CS_CUDA(cudaMemcpyAsync(pk->vinv_over_n.p, c.l, sizeof(HF), cudaMemcpyHostToDevice, ctx->stream));
+  if (pk->log_n)
+    CS_LAUNCH(k_ntt_coset_table<FrP>, ceil_div(n, 256), 256, 0, ctx->stream, dpw.as<uint32_t>(), dpw.as<uint32_t>() + 32 * FrP::N,
+              pk->log_n, pk->coset_tab_ark.as<uint32_t>());
+  CS_LAUNCH(k_ntt_twiddles<FrP>, ceil_div(n, 256), 256, 0, ctx->stream, dpw.as<uint32_t>() + 33 * FrP::N, (uint32_t)n,
+            pk->ginv_pows.as<uint32_t>());
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  dpw.release();
+  return 0;
+}
+
+// LibSnarkReduction::witness_map_from_matrices on the device; h (coefficients of H, natural order) in pk->d_c.
+template <class Cfg>
+int witness_map_libsnark_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint32_t* d_wit, bool have_mask,
+                                cudaStream_t st) {
+  typedef typename Cfg::FrP FrP;
+  CS_TRY(ensure_libsnark<Cfg>(ctx, pk));
+  const unsigned batch = kind == CS_REP3 ? 2 : 1;
+  const int pub_comp = kind == CS_REP3 ? (party == 0 ? 0 : (party == 1 ? 1 : -1)) : 0;
+  const int pub_comp_hs = kind == CS_REP3 ? (party == 0 ? 0 : -1) : 0;
+  const uint32_t n = (uint32_t)pk->n;
+  CS_TRY(pk->d_a.reserve((size_t)n * batch * 32));
+  CS_TRY(pk->d_b.reserve((size_t)n * batch * 32));
+  CS_TRY(pk->d_c.reserve((size_t)n * 32));
+  CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->a_rowptr.as<uint32_t>(), pk->a_col.as<uint32_t>(),
+            pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch, batch, pub_comp,
+            (uint32_t)pk->nc, (uint32_t)pk->ni, n, pk->d_a.as<uint32_t>());
+  CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->b_rowptr.as<uint32_t>(), pk->b_col.as<uint32_t>(),
+            pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch, batch, pub_comp,
+            (uint32_t)pk->nc, 0u, n, pk->d_b.as<uint32_t>());
+  // c from the C matrix as HALF shares (reduction.rs:292-298)
+  CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->c_rowptr.as<uint32_t>(), pk->c_col.as<uint32_t>(),
+            pk->c_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, 1u, batch, pub_comp_hs,
+            (uint32_t)pk->nc, 0u, n, pk->d_c.as<uint32_t>());
+  const uint32_t* post = pk->log_n ? pk->coset_tab_ark.as<uint32_t>() : nullptr;
+  CS_TRY(ntt_run(ctx, pk->dom_ark, pk->d_a.as<uint32_t>(), batch, true, post, st));
+  CS_TRY(ntt_run(ctx, pk->dom_ark, pk->d_a.as<uint32_t>(), batch, false, nullptr, st));
+  CS_TRY(ntt_run(ctx, pk->dom_ark, pk->d_b.as<uint32_t>(), batch, true, post, st));
+  CS_TRY(ntt_run(ctx, pk->dom_ark, pk->d_b.as<uint32_t>(), batch, false, nullptr, st));
+  CS_TRY(ntt_run(ctx, pk->dom_ark, pk->d_c.as<uint32_t>(), 1, true, post, st));
+  CS_TRY(ntt_run(ctx, pk->dom_ark, pk->d_c.as<uint32_t>(), 1, false, nullptr, st));
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  // ab = local_mul_vec(a, b) - c   (reduction.rs:289, :316-322; the constant factor is folded into the iNTT below)
+  if (kind == CS_REP3)
+    CS_LAUNCH(k_rep3_local_mul<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
+              have_mask ? pk->d_m1.as<uint32_t>() : (const uint32_t*)nullptr, pk->d_c.as<uint32_t>(), pk->d_c.as<uint32_t>(),
+              (size_t)n);
+  else
+    CS_LAUNCH(k_plain_mul_sub<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
+              pk->d_c.as<uint32_t>(), pk->d_c.as<uint32_t>(), (size_t)n);
+  // interpolate over the coset: iNTT scaled by (g^n - 1)^-1 / n, bit_reverse, times g^-i  (reduction.rs:324-339)
+  if (pk->log_n) {
+    CS_TRY((ntt_enqueue<FrP>(pk->d_c.as<uint32_t>(), pk->dom_ark->tw_inv.as<uint32_t>(), pk->log_n, 1, false, nullptr,
+                             pk->vinv_over_n.as<uint32_t>(), st)));
+    CS_LAUNCH(k_bit_reverse<FrP>, ceil_div(n, 256), 256, 0, st, pk->d_c.as<uint32_t>(), pk->log_n, 1u);
+  } else {
+    CS_LAUNCH(k_vec_scale_table<FrP>, 1, 32, 0, st, pk->d_c.as<uint32_t>(), pk->vinv_over_n.as<uint32_t>(), (size_t)1, 1u);
+  }
+  CS_LAUNCH(k_vec_scale_table<FrP>, blocks, 256, 0, st, pk->d_c.as<uint32_t>(), pk->ginv_pows.as<uint32_t>(), (size_t)n, 1u);
   CS_CUDA(cudaGetLastError());
   return 0;
 }
@@ -307,6 +404,12 @@ int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* d, cs_groth16_p
   CS_TRY(upload(ctx, pk->b_rowptr, d->b_row_ptr, (nc + 1) * 4));
   CS_TRY(upload(ctx, pk->b_col, d->b_col, d->b_nnz * 4));
   CS_TRY(upload(ctx, pk->b_coeff, d->b_coeff, d->b_nnz * 32));
+  if (d->c_row_ptr) {
+    CS_TRY(upload(ctx, pk->c_rowptr, d->c_row_ptr, (nc + 1) * 4));
+    CS_TRY(upload(ctx, pk->c_col, d->c_col, d->c_nnz * 4));
+    CS_TRY(upload(ctx, pk->c_coeff, d->c_coeff, d->c_nnz * 32));
+    pk->have_c = true;
+  }
   CS_CUDA(cudaStreamSynchronize(ctx->stream));
   pk->alpha_g1.assign(d->alpha_g1, d->alpha_g1 + 2 * fq);
   pk->beta_g1.assign(d->beta_g1, d->beta_g1 + 2 * fq);
@@ -337,7 +440,8 @@ int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* d, cs_groth16_p
 void cs_groth16_pk_free(cs_groth16_pk* pk) {
   if (!pk) return;
   DevBuf* bufs[] = {&pk->a_rowptr, &pk->a_col, &pk->a_coeff, &pk->b_rowptr, &pk->b_col, &pk->b_coeff, &pk->coset_tab,
-                    &pk->d_pub, &pk->d_wit, &pk->d_a, &pk->d_b, &pk->d_c, &pk->d_m1, &pk->d_m2, &pk->d_pubscal};
+                    &pk->d_pub, &pk->d_wit, &pk->d_a, &pk->d_b, &pk->d_c, &pk->d_m1, &pk->d_m2, &pk->d_pubscal,
+                    &pk->c_rowptr, &pk->c_col, &pk->c_coeff, &pk->coset_tab_ark, &pk->ginv_pows, &pk->vinv_over_n};
   for (DevBuf* b : bufs) b->release();
   cs_bases_free(pk->a_query);
   cs_bases_free(pk->b_g1);
@@ -345,6 +449,7 @@ void cs_groth16_pk_free(cs_groth16_pk* pk) {
   cs_bases_free(pk->l_query);
   cs_bases_free(pk->h_query);
   cs_domain_free(pk->dom);
+  cs_domain_free(pk->dom_ark);
   delete pk;
 }
 
@@ -366,6 +471,29 @@ int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, i
     case CS_BLS12_381:
       CS_TRY((witness_map_device<Bls381Cfg>(ctx, pk, kind, party, pk->d_wit.as<uint32_t>(), h_m1 != nullptr,
                                             h_m2 != nullptr, ctx->stream)));
+      break;
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+  if (h_out) CS_CUDA(cudaMemcpyAsync(h_out, pk->d_c.p, pk->n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int cs_groth16_witness_map_libsnark(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party, const uint64_t* h_pub,
+                                    const uint64_t* h_wit, const uint64_t* h_mask, uint64_t* h_out) {
+  if (!ctx || !pk || !h_pub || (pk->nw && !h_wit)) return fail(CS_ERR_ARG, "cs_groth16_witness_map_libsnark: NULL argument");
+  if (kind != CS_PLAIN && kind != CS_REP3) return fail(CS_ERR_ARG, "cs_groth16_witness_map_libsnark: bad share kind");
+  if (kind == CS_REP3 && (party < 0 || party > 2)) return fail(CS_ERR_ARG, "cs_groth16_witness_map_libsnark: party must be 0..2");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, h_mask, nullptr));
+  switch (pk->curve) {
+    case CS_BN254:
+      CS_TRY((witness_map_libsnark_device<Bn254Cfg>(ctx, pk, kind, party, pk->d_wit.as<uint32_t>(), h_mask != nullptr, ctx->stream)));
+      break;
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381:
+      CS_TRY((witness_map_libsnark_device<Bls381Cfg>(ctx, pk, kind, party, pk->d_wit.as<uint32_t>(), h_mask != nullptr, ctx->stream)));
       break;
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");

@@ -178,7 +178,7 @@ CS_GLOBAL void k_poly_eval(const uint32_t* __restrict__ coeffs, size_t n, uint32
 template <class FrP>
 CS_GLOBAL void k_spmv(const uint32_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
                       const uint32_t* __restrict__ coeff, const uint32_t* __restrict__ pub, uint32_t n_pub,
-                      const uint32_t* __restrict__ wit, uint32_t batch, int pub_comp, uint32_t nrows,
+                      const uint32_t* __restrict__ wit, uint32_t batch, uint32_t wstride, int pub_comp, uint32_t nrows,
                       uint32_t n_pubrows, uint32_t domain, uint32_t* __restrict__ out) {
   constexpr int NW = FrP::N;
   uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -197,7 +197,9 @@ CS_GLOBAL void k_spmv(const uint32_t* __restrict__ row_ptr, const uint32_t* __re
           if (pub_comp == 0) acc[0] = acc[0] + t; else acc[1] = acc[1] + t;
         }
       } else {
-        size_t wi = (size_t)(cidx - n_pub) * batch;
+        // wstride = elements per witness entry (2 for Rep3 shares); batch < wstride evaluates the `a`
+        // component only: evaluate_constraint_half_share (mpc/rep3.rs:51-74)
+        size_t wi = (size_t)(cidx - n_pub) * wstride;
         acc[0] = acc[0] + cf * ld_fr<FrP>(wit + wi * NW);
         if (batch == 2) acc[1] = acc[1] + cf * ld_fr<FrP>(wit + (wi + 1) * NW);
       }

@@ -187,6 +187,8 @@ typedef struct {
   const uint64_t* l_query; size_t l_query_len;
   const uint64_t* h_query; size_t h_query_len;
   int window_bits; /* 0 = default */
+  /* optional: the C matrix, needed only by LibSnarkReduction (groth16/reduction.rs:241-342); NULL otherwise */
+  const uint32_t* c_row_ptr; const uint32_t* c_col; const uint64_t* c_coeff; size_t c_nnz;
 } cs_groth16_key_desc;
 
 int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* desc, cs_groth16_pk** out);
@@ -204,6 +206,14 @@ int cs_wtns_read(const char* wtns_path, cs_curve curve, uint64_t* out_mont, size
 int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party,
                            const uint64_t* h_public_inputs, const uint64_t* h_witness,
                            const uint64_t* h_mask1, const uint64_t* h_mask2, uint64_t* h_out);
+
+/* LibSnarkReduction::witness_map_from_matrices (groth16/reduction.rs:241-342; the arkworks/libsnark-style
+ * witness map, not used by the CLI: co-circom.rs:1020): Domain::new + coset GENERATOR, a and b from A/B,
+ * c from the C matrix as half shares, ONE local_mul_vec (one mask vector), h = coefficients of
+ * (a*b - c) / Z over the coset, natural order.  Requires c_* in the key descriptor. */
+int cs_groth16_witness_map_libsnark(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party,
+                                    const uint64_t* h_public_inputs, const uint64_t* h_witness,
+                                    const uint64_t* h_mask, uint64_t* h_out);
 
 /* Groth16::plain_prove (co-groth16/src/groth16.rs:484-490) with the randomness (r, s) supplied by
  * the caller (the reference draws it from thread_rng, mpc/plain.rs:23-26).  public_inputs includes

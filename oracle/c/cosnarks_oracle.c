@@ -270,6 +270,7 @@ typedef struct {
   const u64* l_query; size_t l_query_len;
   const u64* h_query; size_t h_query_len;
   int window_bits;
+  const uint32_t* c_row_ptr; const uint32_t* c_col; const u64* c_coeff; size_t c_nnz;
 } key_desc;
 
 /* evaluate_constraint (reduction.rs:196-210; mpc/plain.rs:29-43, mpc/rep3.rs:31-49) */

@@ -66,6 +66,71 @@ def witness_map_plain(matrices, public_inputs, witness, r, two_adicity):
     return [(x * y - z) % r for x, y, z in zip(a2, b2, c)]
 
 
+# ---------------------------------------------------------------- LibSnarkReduction (reduction.rs:241-342)
+ARK_GENERATOR = {21888242871839275222246405745257275088548364400416034343698204186575808495617: 5,
+                 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001: 7}
+
+
+def ark_domain(n_min, r):
+    """Domain::new(n): size = next power of two, generator = GENERATOR^((r-1)/size) (arkworks'
+    get_root_of_unity; checked against ark-bn254 / ark-bls12-381's TWO_ADIC_ROOT_OF_UNITY)."""
+    size = 1 << max(0, (n_min - 1).bit_length())
+    g = ARK_GENERATOR[r]
+    return size, pow(g, (r - 1) // size, r), g
+
+
+def witness_map_libsnark(matrices, public_inputs, witness, r, kind="plain", pid=0, mask=None):
+    """LibSnarkReduction::witness_map_from_matrices -> coefficients of H in natural order.
+    kind = "plain" (witness = values) or "rep3" (witness = (a, b) shares, one mask vector)."""
+    nc, ni = matrices["num_constraints"], matrices["num_instance_variables"]
+    n, gen, g = ark_domain(nc + ni, r)
+    table = bit_reversed_coset_table(g, n, r)
+
+    def coset1(v):
+        v = ifft_in_to_out(v, gen, r)
+        v = [x * t % r for x, t in zip(v, table)]
+        return fft_out_to_in(v, gen, r)
+
+    if kind == "plain":
+        a = evaluate_constraint_plain(matrices["a"], public_inputs, witness, n, r)
+        a[nc:nc + ni] = list(public_inputs[:ni])
+        b = evaluate_constraint_plain(matrices["b"], public_inputs, witness, n, r)
+        c = evaluate_constraint_plain(matrices["c"], public_inputs, witness, n, r)
+        a, b = coset1(a), coset1(b)
+        ab = [x * y % r for x, y in zip(a, b)]
+    else:
+        a = evaluate_constraint_rep3(pid, matrices["a"], public_inputs, witness, n, r)
+        for k in range(ni):
+            a[nc + k] = promote_to_trivial_share(pid, public_inputs[k])
+        b = evaluate_constraint_rep3(pid, matrices["b"], public_inputs, witness, n, r)
+        # evaluate_constraint_half_share (mpc/rep3.rs:51-74): public terms on party 0 only, witness.a
+        npub = len(public_inputs)
+        c = []
+        for row in matrices["c"]:
+            acc = 0
+            for coeff, idx in row:
+                if idx < npub:
+                    if pid == 0:
+                        acc += public_inputs[idx] * coeff
+                else:
+                    acc += witness[idx - npub][0] * coeff
+            c.append(acc % r)
+        c += [0] * (n - len(c))
+        a = list(zip(coset1([x[0] for x in a]), coset1([x[1] for x in a])))
+        b = list(zip(coset1([x[0] for x in b]), coset1([x[1] for x in b])))
+        ab = local_mul_vec_rep3(a, b, mask if mask is not None else [0] * n, r)
+    c = coset1(c)
+    vinv = inv((pow(g, n, r) - 1) % r, r)
+    ab = [(x - y) * vinv % r for x, y in zip(ab, c)]
+    ab = bit_reverse_perm(ifft_in_to_out(ab, gen, r))
+    ginv = inv(g, r)
+    out, cur = [], 1
+    for x in ab:
+        out.append(x * cur % r)
+        cur = cur * ginv % r
+    return out
+
+
 def _calc_coeff(G, initial, query, vk_param, inputs, aux, add_public=True):
     """groth16.rs:179-203.  `add_public` = whether this party adds public points (party 0 / plain)."""
     npub = len(inputs)

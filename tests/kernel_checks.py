@@ -546,3 +546,55 @@ def check_prove_cli(ctx_lib_path, tmp_path, name="multiplier2"):
     assert public == [ih(x) for x in g["public"]]
     assert groth16_verify(OG.vk_from_zkey(z), public, proof)
     assert json.load(open(out))["protocol"] == "groth16"
+
+
+def check_libsnark_reduction(ctx, m_vars=50, seed=14):
+    """LibSnarkReduction::witness_map_from_matrices (reduction.rs:241-342), plain and Rep3, against the oracle
+    restatement; the oracle itself is checked by the QAP identity A(x)B(x) - C(x) = H(x) Z(x) at a random point
+    (the reference's only fixtures for this reduction are BLS12-377 keys, a curve outside the GPU build)."""
+    from oracle.ntt import ifft
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    w = [1, rng.randrange(r)]
+    A, Bm, Cm = [], [], []
+    for k in range(2, m_vars):
+        j1, j2, j3 = rng.randrange(k), rng.randrange(k), rng.randrange(k)
+        A.append([(1, j1), (1, j2)] if j1 != j2 else [(2, j1)])
+        Bm.append([(rng.randrange(1, 9), j3)])
+        Cm.append([(Bm[-1][0][0], k)])
+        w.append((w[j1] + w[j2]) * w[j3] % r)
+    mat = dict(a=A, b=Bm, c=Cm, num_constraints=m_vars - 2, num_instance_variables=2, num_witness_variables=m_vars - 2)
+    h = OG.witness_map_libsnark(mat, w[:2], w[2:], r)
+    n, gen, g = OG.ark_domain(m_vars, r)
+    a = OG.evaluate_constraint_plain(A, w[:2], w[2:], n, r)
+    a[m_vars - 2:m_vars] = w[:2]
+    b = OG.evaluate_constraint_plain(Bm, w[:2], w[2:], n, r)
+    c = OG.evaluate_constraint_plain(Cm, w[:2], w[2:], n, r)
+    x = rng.randrange(r)
+    ev = lambda p: sum(co * pow(x, i, r) for i, co in enumerate(p)) % r
+    assert (ev(ifft(a, gen, r)) * ev(ifft(b, gen, r)) - ev(ifft(c, gen, r))) % r == ev(h) * (pow(x, n, r) - 1) % r
+    # device: key with dummy points (only the matrices matter for the witness map)
+    G = og1(BN254)
+    P1 = cv.g1([BN254.g1])
+    P2 = cv.g2([BN254.g2])
+    mc = dict(num_constraints=m_vars - 2, num_instance_variables=2, num_witness_variables=m_vars - 2,
+              a=cv.csr(A), b=cv.csr(Bm), c=cv.csr(Cm))
+    pts = dict(alpha_g1=P1, beta_g1=P1, beta_g2=P2, delta_g1=P1, delta_g2=P2, a_query=np.repeat(P1, m_vars, 0),
+               b_g1_query=np.repeat(P1, m_vars, 0), b_g2_query=np.repeat(P2, m_vars, 0),
+               l_query=np.repeat(P1, m_vars - 2, 0), h_query=np.repeat(P1, n, 0))
+    pk = B.Groth16Key(ctx, cv.id, mc, pts)
+    assert pk.domain_size() == n
+    pub = cv.fr(w[:2])
+    assert cv.fr_back(pk.witness_map_libsnark(pub, cv.fr(w[2:]))) == h
+    wsh = OG.share_rep3(w[2:], r, rng)
+    prf = [[rng.randrange(r) for _ in range(n)] for _ in range(3)]
+    masks = [[(prf[i][j] - prf[(i + 2) % 3][j]) % r for j in range(n)] for i in range(3)]
+    tot = [0] * n
+    for i in range(3):
+        sh = cv.fr([v for ab in wsh[i] for v in ab])
+        got = cv.fr_back(pk.witness_map_libsnark(pub, sh, B.CS_REP3, i, cv.fr(masks[i])))
+        assert got == OG.witness_map_libsnark(mat, w[:2], wsh[i], r, "rep3", i, masks[i])
+        tot = [(p + q) % r for p, q in zip(tot, got)]
+    assert tot == h
+    pk.free()

@@ -86,3 +86,7 @@ def test_emu_prove_cli(emu_ctx, tmp_path):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "emu"))
     import build_emu
     K.check_prove_cli(build_emu.OUT, tmp_path)
+
+
+def test_emu_libsnark_reduction(emu_ctx):
+    K.check_libsnark_reduction(emu_ctx, m_vars=20)

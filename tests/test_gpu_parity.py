@@ -104,3 +104,7 @@ def test_zkey_ingest(gpu_ctx, tmp_path):
 
 def test_prove_cli(gpu_ctx, tmp_path):
     K.check_prove_cli(None, tmp_path, "poseidon")
+
+
+def test_libsnark_reduction(gpu_ctx):
+    K.check_libsnark_reduction(gpu_ctx, m_vars=3000)
