@@ -18,8 +18,8 @@ int fail(int code, const char* fmt, ...) {
   last_error() = buf;
   return code;
 }
-uint64_t& launch_counter() {
-  static uint64_t c = 0;
+std::atomic<uint64_t>& launch_counter() {
+  static std::atomic<uint64_t> c{0};
   return c;
 }
 
@@ -134,7 +134,7 @@ int cs_ctx_synchronize(cs_ctx* ctx) {
   return 0;
 }
 
-uint64_t cs_ctx_launch_count(const cs_ctx*) { return launch_counter(); }
+uint64_t cs_ctx_launch_count(const cs_ctx*) { return launch_counter().load(); }
 
 int cs_dev_alloc(cs_ctx* ctx, size_t bytes, void** d_out) {
   if (!ctx || !d_out) return fail(CS_ERR_ARG, "cs_dev_alloc: bad argument");

@@ -3,6 +3,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -24,7 +25,7 @@
 
 namespace cs {
 
-uint64_t& launch_counter();
+std::atomic<uint64_t>& launch_counter();
 
 // thread-local last error (returned by cs_last_error())
 std::string& last_error();

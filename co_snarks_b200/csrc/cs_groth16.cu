@@ -21,7 +21,7 @@ struct cs_groth16_pk {
   std::vector<uint64_t> a_head, b1_head, b2_head;  // query[0..ni] host copies
   cs_domain* dom = nullptr;
   DevBuf coset_tab;  // shift^bitrev(p) / n
-  DevBuf d_pub, d_wit, d_a, d_b, d_c, d_m1, d_m2, d_pubscal;
+  DevBuf d_pub, d_wit, d_a, d_b, d_c, d_m1, d_m2;
   // LibSnarkReduction (reduction.rs:241-342): C matrix, arkworks domain, coset = GENERATOR
   DevBuf c_rowptr, c_col, c_coeff;
   bool have_c = false;
@@ -440,7 +440,7 @@ int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* d, cs_groth16_p
 void cs_groth16_pk_free(cs_groth16_pk* pk) {
   if (!pk) return;
   DevBuf* bufs[] = {&pk->a_rowptr, &pk->a_col, &pk->a_coeff, &pk->b_rowptr, &pk->b_col, &pk->b_coeff, &pk->coset_tab,
-                    &pk->d_pub, &pk->d_wit, &pk->d_a, &pk->d_b, &pk->d_c, &pk->d_m1, &pk->d_m2, &pk->d_pubscal,
+                    &pk->d_pub, &pk->d_wit, &pk->d_a, &pk->d_b, &pk->d_c, &pk->d_m1, &pk->d_m2,
                     &pk->c_rowptr, &pk->c_col, &pk->c_coeff, &pk->coset_tab_ark, &pk->ginv_pows, &pk->vinv_over_n};
   for (DevBuf* b : bufs) b->release();
   cs_bases_free(pk->a_query);

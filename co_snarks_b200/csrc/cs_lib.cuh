@@ -74,7 +74,7 @@ struct cs_domain {
 };
 
 namespace cs {
-uint64_t& launch_counter();
+std::atomic<uint64_t>& launch_counter();
 int ctx_fork(cs_ctx* ctx, int nside);
 int ctx_join(cs_ctx* ctx, int nside);
 int msm_enqueue_dyn(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,

@@ -69,14 +69,23 @@ def make_r1cs(m, seed=1):
 class SynthGroth16:
     """Builds matrices + key; `key_arrays` are what cs_groth16_pk_create consumes."""
 
-    def __init__(self, ctx, log_m, seed=1, setup_seed=2, valid=True):
+    def __init__(self, ctx, log_m, seed=1, setup_seed=2, valid=True, r1cs=None):
+        """r1cs = (a_rows, b_rows, c_rows, full_witness, num_instance_variables) builds a key for an explicit
+        system instead of the seeded chain (rows = lists of (coeff, variable))."""
         r = BN254_R
         self.ctx = ctx
-        self.m = m = 1 << log_m
-        self.ni = 2
-        self.nc = m - 2
-        self.n = n = m  # domain size
-        a_rows, b_rows, c_cols, self.witness = make_r1cs(m, seed)
+        if r1cs is None:
+            self.m = m = 1 << log_m
+            self.ni = 2
+            self.nc = m - 2
+            a_rows, b_rows, c_cols, self.witness = make_r1cs(m, seed)
+            c_rows = [[(1, v)] for v in c_cols]
+        else:
+            a_rows, b_rows, c_rows, self.witness, self.ni = r1cs
+            self.m = m = len(self.witness)
+            self.nc = len(a_rows)
+            log_m = max(0, (self.nc + self.ni - 1).bit_length())
+        self.n = n = 1 << log_m  # domain size = next_power_of_two(nc + ni)
         self.a_rows, self.b_rows = a_rows, b_rows
         rng = random.Random(setup_seed)
         tau, alpha, beta, gamma, delta = (rng.randrange(1, r) for _ in range(5))
@@ -102,8 +111,9 @@ class SynthGroth16:
             for j, row in enumerate(b_rows):
                 for cf, v in row:
                     Bt[v] = (Bt[v] + cf * L[j]) % r
-            for j, v in enumerate(c_cols):
-                Ct[v] = (Ct[v] + L[j]) % r
+            for j, row in enumerate(c_rows):
+                for cf, v in row:
+                    Ct[v] = (Ct[v] + cf * L[j]) % r
             dinv, ginv = pow(delta, r - 2, r), pow(gamma, r - 2, r)
             comb = [(beta * a + alpha * b + c) % r for a, b, c in zip(At, Bt, Ct)]
             l_sc = [x * dinv % r for x in comb[self.ni:]]
@@ -120,6 +130,7 @@ class SynthGroth16:
             At = [rng.randrange(r) for _ in range(m)]
             Bt = [rng.randrange(r) for _ in range(m)]
             l_sc = [rng.randrange(r) for _ in range(m - self.ni)]
+            self.c_rows = c_rows
             h_sc = [rng.randrange(r) for _ in range(n)]
             ic_sc = [rng.randrange(r) for _ in range(self.ni)]
         g1 = _fq_pts(list(G1_GEN), 2)[0]
@@ -133,7 +144,8 @@ class SynthGroth16:
             alpha_g1=small[0:1], beta_g1=small[1:2], delta_g1=small[2:3],
             beta_g2=small2[0:1], delta_g2=small2[2:3],
             a_query=fb(c, B.CS_G1, g1, a_fr), b_g1_query=fb(c, B.CS_G1, g1, b_fr),
-            b_g2_query=fb(c, B.CS_G2, g2, b_fr), l_query=fb(c, B.CS_G1, g1, _fr(l_sc)),
+            b_g2_query=fb(c, B.CS_G2, g2, b_fr),
+            l_query=fb(c, B.CS_G1, g1, _fr(l_sc)) if l_sc else np.zeros((0, 8), dtype=np.uint64),
             h_query=fb(c, B.CS_G1, g1, _fr(h_sc)))
         self.gamma_g2 = small2[1:2]
         self.ic = small[3:3 + self.ni]
@@ -146,10 +158,10 @@ class SynthGroth16:
                     cols.append(v)
                     cfs.append(cf)
                 rp[i + 1] = len(cols)
-            return rp, np.array(cols, dtype=np.uint32), _fr(cfs)
+            return rp, np.array(cols, dtype=np.uint32), (_fr(cfs) if cfs else np.zeros((0, 4), dtype=np.uint64))
 
         self.matrices = dict(num_constraints=self.nc, num_instance_variables=self.ni,
-                             num_witness_variables=m - self.ni, a=csr(a_rows), b=csr(b_rows))
+                             num_witness_variables=m - self.ni, a=csr(a_rows), b=csr(b_rows), c=csr(c_rows))
         self.public_inputs = _fr(self.witness[:self.ni])
         self.private_witness = _fr(self.witness[self.ni:])
 
