@@ -249,7 +249,8 @@ template <class Cfg>
 int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint64_t* h_pub, const uint64_t* h_wit,
                 const uint64_t* d_wit_in, const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
                 uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h,
-                unsigned parts = CS_PART_ALL, const cs_rep3_prf* prf = nullptr) {
+                unsigned parts = CS_PART_ALL, const cs_rep3_prf* prf = nullptr, const uint64_t* rs_mont = nullptr,
+                uint64_t* out_rs_delta = nullptr) {
   typedef HostGroup<Cfg, 0> H1;
   typedef HostGroup<Cfg, 1> H2;
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
@@ -325,6 +326,8 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
         b2_acc = host::hadd(b2_acc, H2::mul(H2::load(pk->b2_head.data() + k * g2l), h_pub + k * 4));
     }
   }
+  if (rs_mont && out_rs_delta)  // (r s) * delta_1 (groth16.rs:297-298), also while the GPU is busy
+    H1::store(out_rs_delta, H1::mul(H1::load(pk->delta_g1.data()), rs_mont));
   CS_CUDA(cudaStreamSynchronize(ctx->stream));
   uint64_t tmp[24];
   int inf = 0;
@@ -349,17 +352,18 @@ int prove_plain_t(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const u
                   uint64_t* out_c) {
   typedef HostGroup<Cfg, 0> H1;
   typedef host::HFp<typename Cfg::FrP> HR;
-  uint64_t a[12], b1[12], l[12], h[12];
-  CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, d_wit, nullptr, nullptr, r, s, a, b1, out_b, l, h)));
-  // groth16.rs:296-322 with the plain driver: C = s*A + r*B1 - (r s)*delta1 + L + H
+  uint64_t a[12], b1[12], l[12], h[12], rsd[12];
   HR rr, ss;
   memcpy(rr.l, r, sizeof(rr.l));
   memcpy(ss.l, s, sizeof(ss.l));
   HR rs = rr * ss;
+  CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, d_wit, nullptr, nullptr, r, s, a, b1, out_b, l, h,
+                           CS_PART_ALL, nullptr, rs.l, rsd)));
+  // groth16.rs:296-322 with the plain driver: C = s*A + r*B1 - (r s)*delta1 + L + H
   typename H1::X A = H1::load(a);
   typename H1::X c = H1::mul(A, s);
   c = host::hadd(c, H1::mul(H1::load(b1), r));
-  c = host::hadd(c, host::hneg(H1::mul(H1::load(pk->delta_g1.data()), rs.l)));
+  c = host::hadd(c, host::hneg(H1::load(rsd)));
   c = host::hadd(c, H1::load(l));
   c = host::hadd(c, H1::load(h));
   memcpy(out_a, a, 2 * H1::HF::N * 8);

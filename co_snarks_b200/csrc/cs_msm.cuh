@@ -22,7 +22,7 @@ namespace cs {
 
 constexpr unsigned MSM_SLICE_MAX = 64;  // entries per slice (levels 0 and 1 of the segmented reduction): 32 or 64
 constexpr unsigned MSM_ORDER_BLOCK = 256;
-constexpr unsigned MSM_RED_SEG = 16;    // buckets per thread in the weighted bucket reduction
+constexpr unsigned MSM_RED_SEG = 4;     // buckets per thread in the weighted bucket reduction
 constexpr unsigned MSM_SIGN = 0x80000000u;
 
 // --------------------------------------------------------------------------- digits + histogram
