@@ -248,7 +248,7 @@ def run_ours(args):
                     "stage_ms": {"digits": float(stage[0]), "sort": float(stage[1]), "accumulate": float(stage[2]),
                                  "fold": float(stage[3]), "reduce": float(stage[4])}},
             "ntt": {"2p%d_ms" % lg: ntt_avg, "gbs_algorithmic": 64.0 * n / (ntt_avg * 1e-3) / 1e9},
-            "cpu_baseline": cpu_baseline(args),
+            "cpu_baseline": cpu_baseline(args) if world == 1 else None,  # rank 0 at N = 1 only
         }
     pk.free()
     ctx.close()

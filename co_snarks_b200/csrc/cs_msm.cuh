@@ -181,25 +181,48 @@ static CS_GLOBAL void k_msm_slice_hist(const uint32_t* __restrict__ count, const
     block_hist[(size_t)blockIdx.x * (MSM_SLICE_MAX + 1) + k] = h[k];
 }
 
-// thread L (one per length): block_hist[.][L] -> exclusive offsets over blocks; len_base[L] = start of the
-// region of length-L slices in `order` (descending length), computed by thread 0 after a barrier.
-static CS_GLOBAL void k_msm_slice_offsets(uint32_t* __restrict__ block_hist, uint32_t nblocks,
-                                          uint32_t* __restrict__ len_base) {
-  __shared__ uint32_t tot[MSM_SLICE_MAX + 1];
-  uint32_t L = threadIdx.x;
-  if (L <= MSM_SLICE_MAX) {
-    uint32_t run = 0;
-    for (uint32_t b = 0; b < nblocks; b++) {
-      uint32_t v = block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L];
-      block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L] = run;
-      run += v;
-    }
-    tot[L] = run;
+// Column L of block_hist (one column per slice length) -> exclusive offsets over the histogram blocks, in
+// three barrier-free steps: chunk sums (thread = (L, chunk)), a short serial scan per length, chunk write-back.
+constexpr unsigned MSM_OFF_CHUNKS = 64;
+static CS_GLOBAL void k_msm_slice_off1(const uint32_t* __restrict__ block_hist, uint32_t nblocks,
+                                       uint32_t* __restrict__ chunk_sum) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS) return;
+  uint32_t L = id / MSM_OFF_CHUNKS, ch = id % MSM_OFF_CHUNKS;
+  uint32_t per = (nblocks + MSM_OFF_CHUNKS - 1) / MSM_OFF_CHUNKS;
+  uint32_t lo = ch * per, hi = lo + per < nblocks ? lo + per : nblocks;
+  uint32_t sum = 0;
+  for (uint32_t b = lo; b < hi; b++) sum += block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L];
+  chunk_sum[id] = sum;
+}
+// one thread: per-length chunk prefixes and len_base[L] = start of the length-L region of `order` (longest first)
+static CS_GLOBAL void k_msm_slice_off2(uint32_t* __restrict__ chunk_sum, uint32_t* __restrict__ len_base) {
+  uint32_t L = blockIdx.x * blockDim.x + threadIdx.x;
+  if (L > MSM_SLICE_MAX) return;
+  uint32_t run = 0;
+  for (uint32_t c = 0; c < MSM_OFF_CHUNKS; c++) {
+    uint32_t v = chunk_sum[L * MSM_OFF_CHUNKS + c];
+    chunk_sum[L * MSM_OFF_CHUNKS + c] = run;
+    run += v;
   }
-  __syncthreads();
-  if (L == 0) {
+  len_base[MSM_SLICE_MAX + 1 + L] = run;  // column totals, consumed by k_msm_slice_off3's thread 0
+}
+static CS_GLOBAL void k_msm_slice_off3(uint32_t* __restrict__ block_hist, uint32_t nblocks,
+                                       const uint32_t* __restrict__ chunk_sum, uint32_t* __restrict__ len_base) {
+  uint32_t id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id == 0) {
     uint32_t run = 0;
-    for (int k = MSM_SLICE_MAX; k >= 0; k--) { len_base[k] = run; run += tot[k]; }
+    for (int k = MSM_SLICE_MAX; k >= 0; k--) { len_base[k] = run; run += len_base[MSM_SLICE_MAX + 1 + k]; }
+  }
+  if (id >= (MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS) return;
+  uint32_t L = id / MSM_OFF_CHUNKS, ch = id % MSM_OFF_CHUNKS;
+  uint32_t per = (nblocks + MSM_OFF_CHUNKS - 1) / MSM_OFF_CHUNKS;
+  uint32_t lo = ch * per, hi = lo + per < nblocks ? lo + per : nblocks;
+  uint32_t run = chunk_sum[id];
+  for (uint32_t b = lo; b < hi; b++) {
+    uint32_t v = block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L];
+    block_hist[(size_t)b * (MSM_SLICE_MAX + 1) + L] = run;
+    run += v;
   }
 }
 
@@ -474,7 +497,8 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_TRY(ws.result.reserve(sizeof(Xyzz<F>)));
   // slice order: slice_len | slice_bkt | order | order_b (max_s0 each) | block_hist | len_base
   const uint32_t ob = ceil_div(max_s0, MSM_ORDER_BLOCK);
-  const size_t order_words = 4 * max_s0 + (size_t)ob * (MSM_SLICE_MAX + 1) + (MSM_SLICE_MAX + 1);
+  const size_t order_words = 4 * max_s0 + (size_t)ob * (MSM_SLICE_MAX + 1) + 2 * (MSM_SLICE_MAX + 1) +
+                             (size_t)(MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS;
   CS_TRY(ws.order.reserve(order_words * 4));
   if (ws.h_result_cap < sizeof(Xyzz<F>)) {
     if (ws.h_result) cudaFreeHost(ws.h_result);
@@ -487,6 +511,7 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   uint32_t* order_b = order + max_s0;
   uint32_t* block_hist = order_b + max_s0;
   uint32_t* len_base = block_hist + (size_t)ob * (MSM_SLICE_MAX + 1);
+  uint32_t* chunk_sum = len_base + 2 * (MSM_SLICE_MAX + 1);
   uint32_t* count = ws.meta.as<uint32_t>();
   uint32_t* cursor = count + nb1;
   uint32_t* start = cursor + nb1;
@@ -501,7 +526,12 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
             offset, start, cursor, ws.sorted.as<uint32_t>());
   CS_LAUNCH_SYNC(k_msm_slice_hist, ob, MSM_ORDER_BLOCK, 0, st, count, sstart0, nb1, S, slice_len, slice_bkt, block_hist);
-  CS_LAUNCH_SYNC(k_msm_slice_offsets, 1, 128, 0, st, block_hist, ob, len_base);
+  {
+    const uint32_t nt = (MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS;
+    CS_LAUNCH(k_msm_slice_off1, ceil_div(nt, 128), 128, 0, st, block_hist, ob, chunk_sum);
+    CS_LAUNCH(k_msm_slice_off2, 1, 128, 0, st, chunk_sum, len_base);
+    CS_LAUNCH(k_msm_slice_off3, ceil_div(nt, 128), 128, 0, st, block_hist, ob, chunk_sum, len_base);
+  }
   CS_LAUNCH_SYNC(k_msm_slice_order, ob, MSM_ORDER_BLOCK, 0, st, slice_len, slice_bkt, (uint32_t)max_s0, sstart0, nb1,
                  block_hist, len_base, order, order_b);
   CS_TRY(ws.mark(2, st));
