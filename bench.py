@@ -247,7 +247,10 @@ def run_ours(args):
             "msm": {"g1_2p%d_ms" % lg: msm_avg, "mscalar_per_s": nw / (msm_avg * 1e-3) / 1e6,
                     "stage_ms": {"digits": float(stage[0]), "sort": float(stage[1]), "accumulate": float(stage[2]),
                                  "fold": float(stage[3]), "reduce": float(stage[4])}},
-            "ntt": {"2p%d_ms" % lg: ntt_avg, "gbs_algorithmic": 64.0 * n / (ntt_avg * 1e-3) / 1e9},
+            "ntt": {"2p%d_ms" % lg: ntt_avg, "gbs_algorithmic": 64.0 * n / (ntt_avg * 1e-3) / 1e9,
+                    "gmodmul_s": n * lg / 2 / (ntt_avg * 1e-3) / 1e9,
+                    "int_pipe_frac": n * lg / 2 / (ntt_avg * 1e-3) / 1e9 / gmul_peak,
+                    "note": "n/2 log n butterflies of one Montgomery product each: integer-pipe bound like the MSM"},
             "cpu_baseline": cpu_baseline(args) if world == 1 else None,  # rank 0 at N = 1 only
         }
     pk.free()

@@ -39,8 +39,10 @@ int ctx_join(cs_ctx* ctx, int nside) {
 template <class FrP>
 static int ntt_smem_optin() {
 #if !defined(CS_EMU)
-  CS_CUDA(cudaFuncSetAttribute(k_ntt_pass<FrP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  CS_CUDA(cudaFuncSetAttribute(k_ntt_pass<FrP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+#define CS_NTT_ATTR(D, S, KB) \
+  CS_CUDA(cudaFuncSetAttribute(k_ntt_pass<FrP, D, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, KB * 1024))
+  CS_NTT_ATTR(true, false, 64); CS_NTT_ATTR(false, false, 64); CS_NTT_ATTR(true, true, 96); CS_NTT_ATTR(false, true, 96);
+#undef CS_NTT_ATTR
 #endif
   return 0;
 }

@@ -69,8 +69,10 @@ CS_GLOBAL void k_ntt_coset_table(const uint32_t* __restrict__ pw, const uint32_t
 // DIT=false: decimation in frequency (half-size shrinks);  DIT=true: decimation in time.
 // post (optional): out[g] *= post[g]   (per-element table, e.g. the scaled coset table)
 // scale (optional): out[g] *= *scale   (e.g. 1/n)
-template <class FrP, bool DIT>
-CS_GLOBAL void k_ntt_pass(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, uint32_t logn,
+// TWS: the pass's 2^k - 1 twiddles are staged in shared memory next to the tile (heap order: the stage with
+// local half-size mm uses entries [mm - 1, 2 mm - 1)), so the stage loop never waits on L2.
+template <class FrP, bool DIT, bool TWS>
+CS_GLOBAL void __launch_bounds__(512) k_ntt_pass(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, uint32_t logn,
                           uint32_t log_stride, uint32_t k, uint32_t batch,
                           const uint32_t* __restrict__ post, const uint32_t* __restrict__ scale) {
   typedef Fp<FrP> F;
@@ -86,6 +88,18 @@ CS_GLOBAL void k_ntt_pass(uint32_t* __restrict__ data, const uint32_t* __restric
   const uint32_t hi = tile >> log_stride;
   const size_t gbase = ((size_t)hi << (k + log_stride)) + lo;
   const uint32_t T = blockDim.x;
+  uint4* tp0 = pl1 + (size_t)rows * cols;
+  uint4* tp1 = tp0 + rows;
+  if (TWS) {
+    for (uint32_t idx = threadIdx.x; idx + 1 < rows; idx += T) {
+      uint32_t e = idx + 1;
+      uint32_t lmm = 31 - __clz(e);
+      uint32_t jj = (e - (1u << lmm)) * stride + lo;
+      const uint4* src = reinterpret_cast<const uint4*>(tw + ((size_t)jj << (logn - 1 - (lmm + log_stride))) * NW);
+      tp0[idx] = src[0];
+      tp1[idx] = src[1];
+    }
+  }
   // load
   for (uint32_t idx = threadIdx.x; idx < rows * cols; idx += T) {
     uint32_t r = idx / cols, cix = idx - r * cols;
@@ -114,7 +128,13 @@ CS_GLOBAL void k_ntt_pass(uint32_t* __restrict__ data, const uint32_t* __restric
         a = pl0[i1]; c = pl1[i1];
         y.l[0] = a.x; y.l[1] = a.y; y.l[2] = a.z; y.l[3] = a.w; y.l[4] = c.x; y.l[5] = c.y; y.l[6] = c.z; y.l[7] = c.w;
       }
-      w = ld_fr<FrP>(tw + ((size_t)jj << tshift) * NW);
+      if (TWS) {
+        uint32_t ti = (mm - 1) + (r0 & (mm - 1));
+        uint4 a = tp0[ti], c = tp1[ti];
+        w.l[0] = a.x; w.l[1] = a.y; w.l[2] = a.z; w.l[3] = a.w; w.l[4] = c.x; w.l[5] = c.y; w.l[6] = c.z; w.l[7] = c.w;
+      } else {
+        w = ld_fr<FrP>(tw + ((size_t)jj << tshift) * NW);
+      }
       F o0, o1;
       if (DIT) {
         F t = y * w;
@@ -186,19 +206,22 @@ int ntt_enqueue(uint32_t* d_data, const uint32_t* d_tw, uint32_t logn, uint32_t 
     uint32_t log_stride = dit ? done : (logn - done - k);
     bool last = (p + 1 == npass);
     uint32_t rows = 1u << k;
+    static int tws_env = -1, thr_env = -1;  // tuning hooks (profiles/r1_ntt_variant_sweep.jsonl)
+    if (tws_env < 0) { const char* e = getenv("CS_NTT_TWS"); tws_env = e ? atoi(e) : 1; }
+    if (thr_env < 0) { const char* e = getenv("CS_NTT_THREADS"); thr_env = e ? atoi(e) : 512; }
+    const bool tws = tws_env != 0;
     uint32_t threads = (rows / 2) * batch;
-    if (threads > 512) threads = 512;
+    if (threads > (uint32_t)thr_env) threads = thr_env;
     if (threads < 32) threads = 32;
-    size_t smem = (size_t)rows * batch * 32;
+    size_t smem = (size_t)rows * batch * 32 + (tws ? (size_t)rows * 32 : 0);
     uint32_t blocks = 1u << (logn - k);
     const uint32_t* post = last ? d_post : nullptr;
     const uint32_t* scale = last ? d_scale : nullptr;
-    if (dit)
-      CS_LAUNCH_SYNC(k_ntt_pass<FrP COMMA true>, blocks, threads, smem, st, d_data, d_tw, logn, log_stride, k,
-                     batch, post, scale);
-    else
-      CS_LAUNCH_SYNC(k_ntt_pass<FrP COMMA false>, blocks, threads, smem, st, d_data, d_tw, logn, log_stride, k,
-                     batch, post, scale);
+#define CS_NTT_GO(D, S) \
+  CS_LAUNCH_SYNC(k_ntt_pass<FrP COMMA D COMMA S>, blocks, threads, smem, st, d_data, d_tw, logn, log_stride, k, batch, post, scale)
+    if (dit) { if (tws) CS_NTT_GO(true, true); else CS_NTT_GO(true, false); }
+    else     { if (tws) CS_NTT_GO(false, true); else CS_NTT_GO(false, false); }
+#undef CS_NTT_GO
     done += k;
   }
   CS_CUDA(cudaGetLastError());
