@@ -106,6 +106,10 @@ int cs_ctx_create(int device, void* stream, cs_ctx** out) {
     CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
   }
   CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+#if !defined(CS_EMU)
+  if (const char* e = getenv("CS_L2_FETCH"))  // experiment hook: L2 fetch granularity (32/64/128 B) for the random table reads
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+#endif
   CS_TRY(ntt_smem_optin<Bn254Fr>());
 #if defined(CS_ENABLE_BLS12_381)
   CS_TRY(ntt_smem_optin<Bls381Fr>());
