@@ -89,6 +89,11 @@ SIGNATURES = {
     "cs_rep3_local_mul_vec": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_vec_lincomb": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.c_void_p, C.c_uint, C.c_size_t, C.c_void_p]),
     "cs_rep3_masks_device": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.c_uint, C.c_size_t, C.c_void_p]),
+    "cs_rep3_mul_vec_reshare": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(Rep3Prf), C.c_void_p, C.c_void_p]),
+    "cs_rep3_set_b": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cs_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cs_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_chacha_keystream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_void_p]),
     "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
@@ -301,6 +306,33 @@ class Context:
     def rep3_masks_device(self, curve, seed1, pos1, seed2, pos2, n, d_out, rounds=12):
         self._check(self.lib.cs_rep3_masks_device(self.h, curve, bytes(seed1), pos1, bytes(seed2), pos2, rounds, n,
                                                   C.c_void_p(d_out)))
+
+    def rep3_mul_vec_reshare(self, curve, d_a, d_b, n, prf_args, d_out, d_next_out=None):
+        """mul_vec = local_mul_vec + reshare_vec as one kernel (arithmetic.rs:132-160); asynchronous."""
+        prf = None
+        if prf_args is not None:
+            s1, p1, s2, p2, rounds = prf_args
+            prf = Rep3Prf((C.c_uint8 * 32)(*bytes(s1)), p1, (C.c_uint8 * 32)(*bytes(s2)), p2, rounds)
+        self._check(self.lib.cs_rep3_mul_vec_reshare(self.h, curve, C.c_void_p(d_a), C.c_void_p(d_b), n,
+                                                     C.byref(prf) if prf is not None else None, C.c_void_p(d_out),
+                                                     C.c_void_p(d_next_out) if d_next_out else None))
+
+    def rep3_set_b(self, curve, d_recv, n, d_out):
+        self._check(self.lib.cs_rep3_set_b(self.h, curve, C.c_void_p(d_recv), n, C.c_void_p(d_out)))
+
+    def ipc_export(self, d_ptr):
+        h = np.zeros(64, dtype=np.uint8)
+        self._check(self.lib.cs_ipc_export(self.h, C.c_void_p(d_ptr), _ptr(h)))
+        return h
+
+    def ipc_open(self, handle64):
+        out = C.c_void_p()
+        h = np.ascontiguousarray(handle64, dtype=np.uint8)
+        self._check(self.lib.cs_ipc_open(self.h, _ptr(h), C.byref(out)))
+        return out.value
+
+    def ipc_close(self, peer_ptr):
+        self._check(self.lib.cs_ipc_close(self.h, C.c_void_p(peer_ptr)))
 
     def chacha_keystream(self, key, first_block, rounds, nblocks):
         out = np.zeros(nblocks * 16, dtype=np.uint32)

@@ -106,10 +106,6 @@ int cs_ctx_create(int device, void* stream, cs_ctx** out) {
     CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
   }
   CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
-#if !defined(CS_EMU)
-  if (const char* e = getenv("CS_L2_FETCH"))  // experiment hook: L2 fetch granularity (32/64/128 B) for the random table reads
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
-#endif
   CS_TRY(ntt_smem_optin<Bn254Fr>());
 #if defined(CS_ENABLE_BLS12_381)
   CS_TRY(ntt_smem_optin<Bls381Fr>());
@@ -623,6 +619,67 @@ int cs_rep3_masks_device(cs_ctx* ctx, cs_curve curve, const uint8_t* h_seed1, ui
   });
   CS_CUDA(cudaGetLastError());
   CS_CUDA(cudaStreamSynchronize(ctx->stream));  // `keys` is a stack buffer
+  return 0;
+}
+
+// mul_vec = local_mul_vec + reshare_vec in one kernel over peer memory (arithmetic.rs:132-160)
+int cs_rep3_mul_vec_reshare(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b, size_t n,
+                            const cs_rep3_prf* prf, uint64_t* d_out, uint64_t* d_next_out) {
+  if (!ctx || (n && (!d_a || !d_b || !d_out))) return fail(CS_ERR_ARG, "cs_rep3_mul_vec_reshare: NULL argument");
+  if (prf && (prf->rounds == 0 || (prf->rounds & 1) || prf->rounds > 20))
+    return fail(CS_ERR_ARG, "cs_rep3_mul_vec_reshare: rounds must be even, <= 20");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  PrfKeys keys;
+  memset(&keys, 0, sizeof(keys));
+  if (prf) {
+    memcpy(keys.k, prf->seed1, 32);
+    memcpy(keys.k + 8, prf->seed2, 32);
+  }
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_mul_vec_reshare<typename Cfg::FrP>, ceil_div(n, 128), 128, 0, ctx->stream,
+              reinterpret_cast<const uint32_t*>(d_a), reinterpret_cast<const uint32_t*>(d_b), keys,
+              prf ? prf->word_pos1 : 0, prf ? prf->word_pos2 : 0, prf ? prf->rounds : 0u, n,
+              reinterpret_cast<uint32_t*>(d_out), reinterpret_cast<uint32_t*>(d_next_out));
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_rep3_set_b(cs_ctx* ctx, cs_curve curve, const uint64_t* d_recv, size_t n, uint64_t* d_out) {
+  if (!ctx || (n && (!d_recv || !d_out))) return fail(CS_ERR_ARG, "cs_rep3_set_b: NULL argument");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_set_b<typename Cfg::FrP>, ceil_div(n, 256), 256, 0, ctx->stream,
+              reinterpret_cast<const uint32_t*>(d_recv), n, reinterpret_cast<uint32_t*>(d_out));
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// peer mapping of another process's device buffer (one process per GPU): cudaIpc handles are 64 opaque bytes
+int cs_ipc_export(cs_ctx* ctx, const void* d_ptr, uint8_t* out_handle64) {
+  if (!ctx || !d_ptr || !out_handle64) return fail(CS_ERR_ARG, "cs_ipc_export: NULL argument");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CS_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+  memcpy(out_handle64, &h, 64);
+  return 0;
+}
+int cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** out_peer_ptr) {
+  if (!ctx || !handle64 || !out_peer_ptr) return fail(CS_ERR_ARG, "cs_ipc_open: NULL argument");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  CS_CUDA(cudaIpcOpenMemHandle(out_peer_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return 0;
+}
+int cs_ipc_close(cs_ctx* ctx, void* peer_ptr) {
+  if (!ctx || !peer_ptr) return fail(CS_ERR_ARG, "cs_ipc_close: NULL argument");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_CUDA(cudaIpcCloseMemHandle(peer_ptr));
   return 0;
 }
 

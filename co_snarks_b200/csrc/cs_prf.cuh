@@ -76,6 +76,42 @@ CS_GLOBAL void k_rep3_masks(const uint32_t* __restrict__ keys /* 16 words: key1 
   st_fr<FrP>(out + i * FrP::N, a - b);
 }
 
+struct PrfKeys { uint32_t k[16]; };  // key1 | key2, passed by value
+
+// mul_vec on large vectors as ONE kernel (mpc-core/src/protocols/rep3/arithmetic.rs:132-160):
+//   z_i = a_i * b_i + mask_i          local_mul_vec, masks drawn in registers (rngs.rs:103-106)
+//   out[i].a = z_i                    this party's half of the new share
+//   next_out[i].b = z_i               reshare_vec: the store goes straight into the NEXT party's share vector
+//                                     (peer memory over NVLink; `next_out` is an IPC-mapped pointer)
+// After all three parties' kernels have completed, every `out` holds complete (a, b) shares -- no staging
+// buffer, no pack/unpack pass, and the transfer overlaps the arithmetic element by element.
+template <class FrP>
+CS_GLOBAL void k_rep3_mul_vec_reshare(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, PrfKeys keys,
+                                      uint64_t pos1, uint64_t pos2, uint32_t rounds, size_t n,
+                                      uint32_t* __restrict__ out, uint32_t* __restrict__ next_out) {
+  constexpr int NW = FrP::N;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fp<FrP> aa = ld_fr<FrP>(a + (2 * i) * NW), ab = ld_fr<FrP>(a + (2 * i + 1) * NW);
+  Fp<FrP> ba = ld_fr<FrP>(b + (2 * i) * NW), bb = ld_fr<FrP>(b + (2 * i + 1) * NW);
+  Fp<FrP> z = aa * (ba + bb) + ab * ba;
+  if (rounds) {
+    Fp<FrP> m1 = prf_field_element<FrP>(keys.k, pos1 + 8 * i, rounds);
+    Fp<FrP> m2 = prf_field_element<FrP>(keys.k + 8, pos2 + 8 * i, rounds);
+    z = z + (m1 - m2);
+  }
+  st_fr<FrP>(out + (2 * i) * NW, z);
+  if (next_out) st_fr<FrP>(next_out + (2 * i + 1) * NW, z);
+}
+
+// b-halves arriving through a staging buffer (the NCCL send/recv baseline of the same step): out[i].b = recv[i]
+template <class FrP>
+CS_GLOBAL void k_rep3_set_b(const uint32_t* __restrict__ recv, size_t n, uint32_t* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_fr<FrP>(out + (2 * i + 1) * FrP::N, ld_fr<FrP>(recv + i * FrP::N));
+}
+
 // raw keystream words (test hook: RFC 7539 block vector with rounds = 20)
 static CS_GLOBAL void k_chacha_keystream(const uint32_t* __restrict__ key, uint64_t first_block, uint32_t rounds,
                                          uint32_t nblocks, uint32_t* __restrict__ out) {

@@ -73,6 +73,55 @@ class Rep3Network:
         return conv(outs[self.prev]), conv(outs[self.next])
 
 
+class Rep3MulVec:
+    """rep3::arithmetic::mul_vec on device-resident share vectors (arithmetic.rs:132-176; the large-vector
+    pattern local_mul_vec + reshare_vec of co-plonk/src/mpc/rep3.rs:185-196).
+
+    fused:  ONE kernel per party computes z = a*b + mask (masks from the on-device ChaCha12 PRF) and stores it
+            into its own share vector (.a) and, over NVLink peer memory, into the next party's (.b); the
+            parties then meet at a barrier.  Needs the three ranks on GPUs of one box (CUDA IPC mapping).
+    staged: the same kernel without the peer store; the a-halves travel through Rep3Network.reshare
+            (any transport -- gloo/TCP like the reference's mpc-net, or NCCL) and are packed in by cs_rep3_set_b."""
+
+    def __init__(self, ctx, net, curve=B.CS_BN254):
+        self.ctx, self.net, self.curve = ctx, net, curve
+        self._peers = {}
+
+    def connect(self, d_out):
+        """Maps the next party's output buffer (each party passes its own d_out); returns the peer pointer."""
+        import torch
+        h = self.ctx.ipc_export(d_out)
+        t = torch.from_numpy(h.copy()).to(self.net.device)
+        outs = [torch.empty_like(t) for _ in range(3)]
+        self.net.dist.all_gather(outs, t, group=self.net.group)
+        peer = self.ctx.ipc_open(outs[self.net.next].cpu().numpy())
+        self._peers[d_out] = peer
+        return peer
+
+    def disconnect(self, d_out):
+        self.ctx.synchronize()
+        self.net.dist.barrier(group=self.net.group)
+        self.ctx.ipc_close(self._peers.pop(d_out))
+
+    def mul_vec_fused(self, state, d_a, d_b, n, d_out, wait=True):
+        self.ctx.rep3_mul_vec_reshare(self.curve, d_a, d_b, n, state.prf_args(), d_out, self._peers[d_out])
+        state.advance(8 * n)
+        if wait:  # the b-halves are complete once every party's kernel has finished
+            self.ctx.synchronize()
+            self.net.dist.barrier(group=self.net.group)
+
+    def mul_vec_staged(self, state, d_a, d_b, n, d_out):
+        self.ctx.rep3_mul_vec_reshare(self.curve, d_a, d_b, n, state.prf_args(), d_out, None)
+        state.advance(8 * n)
+        self.ctx.synchronize()
+        za = self.ctx.d2h(d_out, (n, 2, 4))[:, 0, :].copy()
+        zb = self.net.reshare(za)
+        d_recv = self.ctx.to_device(np.ascontiguousarray(zb))
+        self.ctx.rep3_set_b(self.curve, d_recv, n, d_out)
+        self.ctx.synchronize()
+        self.ctx.free(d_recv)
+
+
 def random_field_limbs(rng, n):
     """n uniform field elements as canonical limbs [n, 4] from a numpy Generator (253-bit draws, < r);
     used to build secret sharings of a witness (rep3.rs:281-293)."""

@@ -270,6 +270,24 @@ int cs_groth16_rep3_local_prf(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsigne
                               const uint64_t* h_r_share, const uint64_t* h_s_share, uint64_t* out_g_a,
                               uint64_t* out_g1_b, uint64_t* out_g2_b, uint64_t* out_l_acc, uint64_t* out_h_acc);
 
+/* mul_vec on large share vectors as ONE kernel over NVLink peer memory
+ * (rep3::arithmetic::local_mul_vec + reshare_vec, mpc-core/src/protocols/rep3/arithmetic.rs:132-160; the
+ * call pattern of co-plonk/src/mpc/rep3.rs:185-196 and round3.rs): z_i = a_i*b_i + mask_i with the masks
+ * drawn in registers from `prf` (NULL = no masks), d_out[i].a = z_i, and -- when d_next_out is not NULL --
+ * d_next_out[i].b = z_i, where d_next_out is the NEXT party's d_out mapped with cs_ipc_open (or any device
+ * pointer this GPU can store to).  Asynchronous on the context stream: once all three parties' kernels have
+ * completed (stream sync + barrier), every d_out holds full Rep3PrimeFieldShare{a,b} elements.  The caller
+ * advances both rngs by 8 n words.  cs_rep3_set_b is the staging-buffer variant of the second half
+ * (d_out[i].b = d_recv[i]) for transports that deliver the b-halves as a contiguous vector. */
+int cs_rep3_mul_vec_reshare(cs_ctx* ctx, cs_curve curve, const uint64_t* d_a, const uint64_t* d_b, size_t n,
+                            const cs_rep3_prf* prf, uint64_t* d_out, uint64_t* d_next_out);
+int cs_rep3_set_b(cs_ctx* ctx, cs_curve curve, const uint64_t* d_recv, size_t n, uint64_t* d_out);
+/* One process per GPU: export a cs_malloc'ed buffer as a 64-byte CUDA IPC handle / map a peer's handle
+ * (peer access over NVLink is enabled on first use) / unmap it. */
+int cs_ipc_export(cs_ctx* ctx, const void* d_ptr, uint8_t* out_handle64);
+int cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** out_peer_ptr);
+int cs_ipc_close(cs_ctx* ctx, void* peer_ptr);
+
 /* ShamirGroth16Driver's local phase (co-groth16/src/mpc/shamir.rs:29-119): identical arithmetic to the plain
  * driver on degree-t shares -- every party adds the public terms/points; outputs are degree-2t point shares
  * that the host protocol opens (shamir/pointshare.rs:86-113). */

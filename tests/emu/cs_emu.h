@@ -97,6 +97,16 @@ static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t) { return "emu"; }
 static inline cudaError_t cudaFuncSetAttribute(const void*, int, int) { return cudaSuccess; }
+// IPC within the emulation = the pointer itself (all "processes" share one address space)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess;
+}
+static inline cudaError_t cudaIpcOpenMemHandle(void** out, cudaIpcMemHandle_t h, unsigned) {
+  memcpy(out, h.reserved, sizeof(void*)); return cudaSuccess;
+}
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 #define cudaFuncAttributeMaxDynamicSharedMemorySize 8
 
 #define CS_LAUNCH(kernel, grid, block, smem, stream, ...) \

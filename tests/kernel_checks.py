@@ -420,6 +420,74 @@ def check_rep3_mask_prf(ctx, n=100):
     assert tot == [0] * n
 
 
+def check_rep3_mul_vec_reshare(ctx, n=150, seed=15, use_ipc=False):
+    """mul_vec as one kernel (local_mul_vec + reshare_vec, arithmetic.rs:132-160): three parties in one
+    address space, each storing its z into its own .a and -- through an IPC-mapped pointer -- into the next
+    party's .b.  Checks: z == oracle (share product + ChaCha masks), shares are consistent (b of party i ==
+    a of party i-1) and open to x*y; the staging variant (cs_rep3_set_b) gives the same vectors."""
+    from oracle import chacha as OC
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    xs = [rng.randrange(r) for _ in range(n)]
+    ys = [rng.randrange(r) for _ in range(n)]
+
+    def share(v):
+        s0, s1 = rng.randrange(r), rng.randrange(r)
+        sh = [s0, s1, (v - s0 - s1) % r]
+        return [(sh[p], sh[(p + 2) % 3]) for p in range(3)]  # party p holds (x_p, x_{p-1})  rep3.rs:281-293
+    xsh = [share(v) for v in xs]
+    ysh = [share(v) for v in ys]
+    seeds = [bytes((11 * p + i) & 0xff for i in range(32)) for p in range(3)]
+    pos = [0, 24, 7]
+    d_a, d_b, d_out, d_out2 = [], [], [], []
+    for p in range(3):
+        d_a.append(ctx.to_device(cv.fr([c for i in range(n) for c in xsh[i][p]])))
+        d_b.append(ctx.to_device(cv.fr([c for i in range(n) for c in ysh[i][p]])))
+        d_out.append(ctx.alloc(n * 64))
+        d_out2.append(ctx.alloc(n * 64))
+    # a CUDA IPC handle cannot be opened by the process that exported it: one-process runs on a real GPU pass
+    # the neighbour's pointer directly; the IPC mapping itself is exercised by tests/test_dist_rep3.py on GPUs
+    peers = [ctx.ipc_open(ctx.ipc_export(d_out[(p + 1) % 3])) if use_ipc else d_out[(p + 1) % 3] for p in range(3)]
+    for p in range(3):
+        prev = (p + 2) % 3
+        ctx.rep3_mul_vec_reshare(cv.id, d_a[p], d_b[p], n, (seeds[p], pos[p], seeds[prev], pos[prev], 12), d_out[p], peers[p])
+    ctx.synchronize()
+    got = [cv.fr_back(ctx.d2h(d_out[p], (2 * n, 4))) for p in range(3)]
+    for p in range(3):
+        prev = (p + 2) % 3
+        masks = OC.masking_field_elements_vec(seeds[p], pos[p], seeds[prev], pos[prev], n, r)
+        exp = [(xsh[i][p][0] * ysh[i][p][0] + xsh[i][p][0] * ysh[i][p][1] + xsh[i][p][1] * ysh[i][p][0] + masks[i]) % r
+               for i in range(n)]
+        assert got[p][0::2] == exp, ("z", p)
+        assert got[p][1::2] == got[prev][0::2], ("reshare", p)
+    assert [(got[0][2 * i] + got[1][2 * i] + got[2][2 * i]) % r for i in range(n)] == [x * y % r for x, y in zip(xs, ys)]
+    # staging-buffer variant: same z without a peer pointer, b-halves delivered as contiguous vectors
+    for p in range(3):
+        prev = (p + 2) % 3
+        ctx.rep3_mul_vec_reshare(cv.id, d_a[p], d_b[p], n, (seeds[p], pos[p], seeds[prev], pos[prev], 12), d_out2[p], None)
+    ctx.synchronize()
+    for p in range(3):
+        prev = (p + 2) % 3
+        zprev = ctx.d2h(d_out2[prev], (2 * n, 4))[0::2].copy()
+        d_recv = ctx.to_device(zprev)
+        ctx.rep3_set_b(cv.id, d_recv, n, d_out2[p])
+        ctx.synchronize()
+        ctx.free(d_recv)
+    for p in range(3):
+        assert cv.fr_back(ctx.d2h(d_out2[p], (2 * n, 4))) == got[p], ("staging", p)
+    # no masks (prf NULL) -> plain share product
+    ctx.rep3_mul_vec_reshare(cv.id, d_a[0], d_b[0], n, None, d_out2[0], None)
+    ctx.synchronize()
+    z0 = cv.fr_back(ctx.d2h(d_out2[0], (2 * n, 4)))[0::2]
+    assert z0 == [(xsh[i][0][0] * (ysh[i][0][0] + ysh[i][0][1]) + xsh[i][0][1] * ysh[i][0][0]) % r for i in range(n)]
+    for p in range(3):
+        if use_ipc:
+            ctx.ipc_close(peers[p])
+        for d in (d_a[p], d_b[p], d_out[p], d_out2[p]):
+            ctx.free(d)
+
+
 def check_shamir_degree_reduce(ctx, n=64, seed=12):
     """Shamir king-based degree reduction (shamir/network.rs:150-243) assembled from cs_vec_lincomb, for
     n = 3 parties, t = 1: every party masks its degree-2t product share with r_2t, the king interpolates

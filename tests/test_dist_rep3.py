@@ -154,3 +154,68 @@ def test_rep3_two_gpus_per_party_gloo():
     r_tot = sum(x[4][0] for x in res) % BN254.r
     s_tot = sum(x[5][0] for x in res) % BN254.r
     assert proofs[0] == OG.prove_plain(z, m, w, r_tot, s_tot)
+
+
+def _party_mul(rank, port, emu_path, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from co_snarks_b200 import binding as B
+    from co_snarks_b200.rep3 import Rep3MulVec, Rep3Network, Rep3State
+    from helpers import Conv
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=3)
+    try:
+        ctx = B.Context(0, lib_path=emu_path)
+        cv = Conv("bn254")
+        n = 70
+        rng = random.Random(21)  # same seed everywhere -> consistent sharings of x and y
+        xs = [rng.randrange(cv.r) for _ in range(n)]
+        ys = [rng.randrange(cv.r) for _ in range(n)]
+
+        def mine(vals):
+            out = []
+            for v in vals:
+                s0, s1 = rng.randrange(cv.r), rng.randrange(cv.r)
+                sh = [s0, s1, (v - s0 - s1) % cv.r]
+                out += [sh[rank], sh[(rank + 2) % 3]]
+            return cv.fr(out)
+        d_a, d_b = ctx.to_device(mine(xs)), ctx.to_device(mine(ys))
+        d_out = ctx.alloc(n * 64)
+        net = Rep3Network()
+        state = Rep3State(net, seed=2000 + rank)
+        pos0 = state.prf_args()[1]
+        Rep3MulVec(ctx, net).mul_vec_staged(state, d_a, d_b, n, d_out)
+        assert state.prf_args()[1] == pos0 + 8 * n
+        q.put((rank, cv.fr_back(ctx.d2h(d_out, (2 * n, 4))), xs, ys))
+        for d in (d_a, d_b, d_out):
+            ctx.free(d)
+        ctx.close()
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_rep3_mul_vec_staged_gloo():
+    """mul_vec (arithmetic.rs:165-176) across three processes: shares stay replicated (b_i == a_{i-1}) and
+    open to x*y, i.e. the on-device ChaCha masks of the three parties cancel."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    emu = build_emu.build()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_party_mul, args=(r, port, emu, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from oracle.fields import BN254
+    r = BN254.r
+    xs, ys = res[0][2], res[0][3]
+    sh = [x[1] for x in res]
+    for i in range(3):
+        assert sh[i][1::2] == sh[(i + 2) % 3][0::2]
+    assert [(sh[0][2 * k] + sh[1][2 * k] + sh[2][2 * k]) % r for k in range(len(xs))] == [x * y % r for x, y in zip(xs, ys)]

@@ -90,3 +90,7 @@ def test_emu_prove_cli(emu_ctx, tmp_path):
 
 def test_emu_libsnark_reduction(emu_ctx):
     K.check_libsnark_reduction(emu_ctx, m_vars=20)
+
+
+def test_rep3_mul_vec_reshare(emu_ctx):
+    K.check_rep3_mul_vec_reshare(emu_ctx, use_ipc=True)

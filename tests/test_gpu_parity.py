@@ -108,3 +108,8 @@ def test_prove_cli(gpu_ctx, tmp_path):
 
 def test_libsnark_reduction(gpu_ctx):
     K.check_libsnark_reduction(gpu_ctx, m_vars=3000)
+
+
+@pytest.mark.gpu
+def test_rep3_mul_vec_reshare(gpu_ctx):
+    K.check_rep3_mul_vec_reshare(gpu_ctx)
