@@ -144,9 +144,12 @@ def zkey_matrices(z):
                 num_witness_variables=z["n_vars"] - n_pub1)
 
 
-def read_plonk_zkey(path):
-    """Plonk .zkey (protocol 2): header, additions, wire maps, p_tau points.  Only the parts the
-    round-1 KAT needs (co-plonk/src/round1.rs:109-134,262-272)."""
+def read_plonk_zkey(path, full=True):
+    """Plonk .zkey (protocol 2; parsed in the reference by taceo-circom-types' plonk::Zkey): header with k1, k2
+    and the selector / permutation commitments, additions, wire maps, the selector, sigma and Lagrange
+    polynomials (n coefficients followed by 4n evaluations over the extended domain each) and the p_tau points.
+    Fields used by the prover: co-plonk/src/round1.rs:109-224, round2.rs:99-160, round3.rs:300-420,
+    round4.rs:143-144, round5.rs:120-260."""
     data = open(path, "rb").read()
     secs = _sections(data, b"zkey")
     rd = _Rd(data, secs[1][0])
@@ -162,6 +165,11 @@ def read_plonk_zkey(path):
     z = dict(curve=curve, q=q, r=r, n8q=n8q, n8r=n8r)
     for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints"):
         z[k] = rd.u32()
+    z["k1"] = rd.int(n8r) * Rr_inv % r
+    z["k2"] = rd.int(n8r) * Rr_inv % r
+    for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3"):
+        z["vk_" + k] = _g1(rd, n8q, Rq_inv, q)
+    z["x2"] = _g2(rd, n8q, Rq_inv, q)
     rd = _Rd(data, secs[3][0])
     adds = []
     for _ in range(z["n_additions"]):
@@ -173,10 +181,57 @@ def read_plonk_zkey(path):
     for name, sec in (("map_a", 4), ("map_b", 5), ("map_c", 6)):
         rd = _Rd(data, secs[sec][0])
         z[name] = [rd.u32() for _ in range(z["n_constraints"])]
+    if full:
+        n = z["domain_size"]
+
+        def poly(rd):
+            co = [rd.int(n8r) * Rr_inv % r for _ in range(n)]
+            ev = [rd.int(n8r) * Rr_inv % r for _ in range(4 * n)]
+            return dict(coeffs=co, evals=ev)
+        for name, sec in (("qm", 7), ("ql", 8), ("qr", 9), ("qo", 10), ("qc", 11)):
+            z[name] = poly(_Rd(data, secs[sec][0]))
+        rd = _Rd(data, secs[12][0])
+        z["s1"], z["s2"], z["s3"] = poly(rd), poly(rd), poly(rd)
+        rd = _Rd(data, secs[13][0])
+        z["lagrange"] = [poly(rd) for _ in range(max(1, z["n_public"]))]
+        assert rd.o == secs[13][0] + secs[13][1], "lagrange section size"
     off, ln = secs[14]
     rd = _Rd(data, off)
     z["p_tau"] = [_g1(rd, n8q, Rq_inv, q) for _ in range(ln // (2 * n8q))]
     return z
+
+
+def read_plonk_vk_json(path):
+    d = json.load(open(path))
+    p1 = lambda a: None if int(a[2]) == 0 else (int(a[0]), int(a[1]))
+    vk = dict(n_public=d["nPublic"], power=d["power"], k1=int(d["k1"]), k2=int(d["k2"]), w=int(d["w"]))
+    for k in ("Qm", "Ql", "Qr", "Qo", "Qc", "S1", "S2", "S3"):
+        vk[k.lower()] = p1(d[k])
+    x = d["X_2"]
+    vk["x2"] = ((int(x[0][0]), int(x[0][1])), (int(x[1][0]), int(x[1][1])))
+    return vk
+
+
+def read_plonk_proof_json(path):
+    d = json.load(open(path))
+    p1 = lambda a: None if int(a[2]) == 0 else (int(a[0]), int(a[1]))
+    out = {k.lower(): p1(d[k]) for k in ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")}
+    for k in ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"):
+        out[k] = int(d[k])
+    return out
+
+
+def plonk_proof_to_json(proof, curve_name="bn128"):
+    """PlonkProof as snarkjs writes it (round5.rs:50-70)."""
+    pt = lambda P: ["0", "1", "0"] if P is None else [str(P[0]), str(P[1]), "1"]
+    d = {}
+    for k, name in (("a", "A"), ("b", "B"), ("c", "C"), ("z", "Z"), ("t1", "T1"), ("t2", "T2"), ("t3", "T3")):
+        d[name] = pt(proof[k])
+    for k in ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"):
+        d[k] = str(proof[k])
+    d["Wxi"], d["Wxiw"] = pt(proof["wxi"]), pt(proof["wxiw"])
+    d["protocol"], d["curve"] = "plonk", curve_name
+    return d
 
 
 def read_vk_json(path):

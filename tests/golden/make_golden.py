@@ -135,6 +135,80 @@ def plonk_fixture(curve_dir, name, expected, compress):
     dump("plonk_round1_%s_%s" % (curve_dir, name), obj, compress)
 
 
+# The reference's known answers for the whole prover with deterministic blinders b[i] = i on BN254 multiplier2
+PLONK_KAT = dict(
+    z=((21851995660159341992573113210608672476110709810652234421585224566450425950906,
+        9396597540042847815549199092556045933393323370500084953024302516882239981142), "round2.rs:300-306"),
+    t1=((14195659590223391588638033663362337117591990036333098666602164584829450067964,
+         3556648023705175372561455635244621029434015848660599980046006090530807598362), "round3.rs:611-616"),
+    t2=((3735872884021926351213137728148437717828227598563721199864822205706753909354,
+         18937554230046023488342718793325695277505320264073327441600348965411357658388), "round3.rs:618-623"),
+    t3=((16143856432987537130591639896375147783771732347095191085601174356801897211531,
+         181289684093540268434296060454656362990106137005120511426963659280111589561), "round3.rs:625-630"),
+    eval_a=(9577617118727487156038114503197927927393325100881782676071854181913228129519, "round4.rs:204-209"),
+    eval_b=(20597878711220885145139457487405665380092038394343281979206937623212519986448, "round4.rs:211-216"),
+    eval_c=(15265494263612694384441473331344570152140354050926476508657731330784430744915, "round4.rs:218-223"),
+    eval_zw=(13208748067365350181326696119359571057028048827339239951085850234164749233153, "round4.rs:225-230"),
+    eval_s1=(14333100636430622287126878289812189552775054994479690945797668457655414216377, "round4.rs:232-237"),
+    eval_s2=(5227675743165392606371559215386333900775466821923985579976650047914227054429, "round4.rs:239-244"),
+    wxi=((17714933343167283383757911844657193439824158284537335005582807825912982308761,
+          10956622068891399683012461981563789956666325407769410657364052444385845871778), "round5.rs:394-399"),
+    wxiw=((11975595019949715918668172153793336705506375746143971491421022814159658028345,
+           21836122222240321064812409945656239690711148338716835775906941056446809090474), "round5.rs:401-406"))
+VERIFIER_KAT = dict(  # plonk.rs:266-309, on the snarkjs proof of the same circuit
+    alpha=4763880717866883938312853446651867584882243039496717119981221423729366022837,
+    beta=21441108096646375017416196030970784867168559532405066373711898693160482621553,
+    gamma=18358340056223774859544506185831433076440067236582749990986245668953309272283,
+    xi=7090361968641770615455554153830816431169048885260030244909139672173927785729,
+    v=[20400998993179279999961662359284658174039203383603729825079844045891169320886,
+       14103303087679005329613195828482967369227712227612956336575014332581057266451,
+       21001079402417908449694312728019684919907988335857152136145617358865414540686,
+       4101776369377085261955299986018358717882425962862873747599549657644387577706,
+       2709069871665560223395972486266890200809234039251701259320531117604850964887],
+    u=13260637895132000183831258130762201406791497612259050836989270998713858775580)
+
+
+def plonk_full_fixture(name, compress):
+    """Everything the Plonk prover reads from the zkey (taceo-circom-types plonk::Zkey) + witness, verification
+    key, public inputs, the snarkjs proof, and the reference's round 2-5 / verifier known answers."""
+    from oracle import plonk as OP
+    from oracle.pairing_bn254 import pairing_product_is_one
+    base = "%s/test_vectors/Plonk/bn254/%s/" % (REF, name)
+    z = F.read_plonk_zkey(base + "circuit.zkey")
+    _, w = F.read_wtns(base + "witness.wtns")
+    vk = F.read_plonk_vk_json(base + "verification_key.json")
+    pub = [int(x) for x in json.load(open(base + "public.json"))]
+    sp = F.read_plonk_proof_json(base + "circom.proof")
+    assert OP.verify(z["curve"], vk, sp, pub, pairing_product_is_one), "snarkjs proof must verify"
+    pr = OP.prove(z, w)
+    if name == "multiplier2":
+        for k, (val, _) in PLONK_KAT.items():
+            assert pr[k] == val, k
+        ch = OP.verifier_challenges(z["curve"], vk, sp, pub)
+        assert all(ch[k] == v for k, v in VERIFIER_KAT.items())
+    assert OP.verify(z["curve"], vk, pr, pub, pairing_product_is_one)
+    poly = lambda P: dict(coeffs=[hx(x) for x in P["coeffs"]], evals=[hx(x) for x in P["evals"]])
+    pj = lambda P: {k: (p1(v) if isinstance(v, tuple) or v is None else hx(v)) for k, v in P.items()}
+    obj = dict(source="test_vectors/Plonk/bn254/" + name, curve="bn254",
+               **{k: z[k] for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints")},
+               k1=hx(z["k1"]), k2=hx(z["k2"]), x2=p2(z["x2"]),
+               **{"vk_" + k: p1(z["vk_" + k]) for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")},
+               additions=[[a, b, hx(c), hx(d)] for a, b, c, d in z["additions"]],
+               map_a=z["map_a"], map_b=z["map_b"], map_c=z["map_c"],
+               **{k: poly(z[k]) for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")},
+               lagrange=[poly(P) for P in z["lagrange"]], p_tau=[p1(P) for P in z["p_tau"]],
+               witness=[hx(x) for x in w], public=[hx(x) for x in pub], vk_power=vk["power"],
+               snarkjs_proof=pj(sp), oracle_proof_deterministic_blinders=pj(pr),
+               oracle_proof_json=F.plonk_proof_to_json(pr))
+    if name == "multiplier2":
+        obj["reference_kat"] = {k: dict(value=(p1(v) if isinstance(v, tuple) else hx(v)), source="co-circom/co-plonk/src/" + src)
+                                for k, (v, src) in PLONK_KAT.items()}
+        obj["reference_verifier_kat"] = dict(source="co-circom/co-plonk/src/plonk.rs:266-309",
+                                             **{k: ([hx(x) for x in v] if isinstance(v, list) else hx(v))
+                                                for k, v in VERIFIER_KAT.items()})
+    dump("plonk_full_bn254_" + name, obj, compress)
+
+
 def crs_fixture(n):
     pts = F.read_bn254_crs_g1("%s/co-noir/co-noir-common/src/crs/bn254_g1.dat" % REF, n)
     dump("crs_bn254_g1_first%d" % n, dict(source="co-noir/co-noir-common/src/crs/bn254_g1.dat",
@@ -159,3 +233,5 @@ if __name__ == "__main__":
         (2045702311111033155343546707999313330868835292331631548140598745513449880984849831136790392158415943067742290277175,
          2263708941732971465915801396733005622347769540424301431567098497278413189155761949973582649025461644335372679621757)], True)
     crs_fixture(1024)
+    plonk_full_fixture("multiplier2", False)
+    plonk_full_fixture("poseidon", True)

@@ -103,6 +103,35 @@ def golden_groth16(name):
     return z, m, w, g
 
 
+def golden_plonk(name):
+    """-> (plonk zkey dict in the oracle's conventions, witness ints, golden json)."""
+    g = load_golden("plonk_full_bn254_" + name)
+    c = CURVES["bn254"]
+    z = dict(curve=c, q=c.q, r=c.r)
+    for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints", "map_a", "map_b", "map_c"):
+        z[k] = g[k]
+    z["k1"], z["k2"], z["x2"] = ih(g["k1"]), ih(g["k2"]), gp2(g["x2"])
+    poly = lambda P: dict(coeffs=[ih(x) for x in P["coeffs"]], evals=[ih(x) for x in P["evals"]])
+    for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3"):
+        z["vk_" + k] = gp1(g["vk_" + k])
+        z[k] = poly(g[k])
+    z["lagrange"] = [poly(P) for P in g["lagrange"]]
+    z["additions"] = [(a, b, ih(c), ih(d)) for a, b, c, d in g["additions"]]
+    z["p_tau"] = [gp1(P) for P in g["p_tau"]]
+    return z, [ih(x) for x in g["witness"]], g
+
+
+def plonk_vk_from_zkey(z, power):
+    vk = dict(n_public=z["n_public"], power=power, k1=z["k1"], k2=z["k2"], x2=z["x2"])
+    for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3"):
+        vk[k] = z["vk_" + k]
+    return vk
+
+
+def plonk_proof_from_json(d):
+    return {k: (ih(v) if isinstance(v, str) else gp1(v)) for k, v in d.items()}
+
+
 def make_key(ctx, cv, z, m, window_bits=0):
     mc = dict(num_constraints=m["num_constraints"], num_instance_variables=m["num_instance_variables"],
               num_witness_variables=m["num_witness_variables"], a=cv.csr(m["a"]), b=cv.csr(m["b"]))

@@ -156,7 +156,7 @@ def test_rep3_two_gpus_per_party_gloo():
     assert proofs[0] == OG.prove_plain(z, m, w, r_tot, s_tot)
 
 
-def _party_mul(rank, port, emu_path, q):
+def _party_mul(rank, port, emu_path, q, fused=False):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -165,9 +165,13 @@ def _party_mul(rank, port, emu_path, q):
     from helpers import Conv
     dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=3)
     try:
-        ctx = B.Context(0, lib_path=emu_path)
+        if fused:  # real GPUs: one process per party, on distinct GPUs when the box has three
+            import torch
+            ctx = B.Context(rank % torch.cuda.device_count())
+        else:
+            ctx = B.Context(0, lib_path=emu_path)
         cv = Conv("bn254")
-        n = 70
+        n = 70 if not fused else 5000
         rng = random.Random(21)  # same seed everywhere -> consistent sharings of x and y
         xs = [rng.randrange(cv.r) for _ in range(n)]
         ys = [rng.randrange(cv.r) for _ in range(n)]
@@ -184,9 +188,16 @@ def _party_mul(rank, port, emu_path, q):
         net = Rep3Network()
         state = Rep3State(net, seed=2000 + rank)
         pos0 = state.prf_args()[1]
-        Rep3MulVec(ctx, net).mul_vec_staged(state, d_a, d_b, n, d_out)
+        mv = Rep3MulVec(ctx, net)
+        if fused:
+            mv.connect(d_out)
+            mv.mul_vec_fused(state, d_a, d_b, n, d_out)
+        else:
+            mv.mul_vec_staged(state, d_a, d_b, n, d_out)
         assert state.prf_args()[1] == pos0 + 8 * n
         q.put((rank, cv.fr_back(ctx.d2h(d_out, (2 * n, 4))), xs, ys))
+        if fused:
+            mv.disconnect(d_out)
         for d in (d_a, d_b, d_out):
             ctx.free(d)
         ctx.close()
@@ -195,17 +206,30 @@ def _party_mul(rank, port, emu_path, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.gpu
+def test_rep3_mul_vec_fused_peer_memory():
+    """The fused kernel through a real CUDA IPC mapping: three processes (three GPUs, or one shared GPU), each
+    storing its products into the next process's share vector."""
+    _run_mul_vec(fused=True)
+
+
 def test_rep3_mul_vec_staged_gloo():
     """mul_vec (arithmetic.rs:165-176) across three processes: shares stay replicated (b_i == a_{i-1}) and
     open to x*y, i.e. the on-device ChaCha masks of the three parties cancel."""
+    _run_mul_vec(fused=False)
+
+
+def _run_mul_vec(fused):
     import torch.multiprocessing as mp
-    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
-    import build_emu
-    emu = build_emu.build()
+    emu = None
+    if not fused:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        emu = build_emu.build()
     ctxm = mp.get_context("spawn")
     q = ctxm.Queue()
     port = _free_port()
-    procs = [ctxm.Process(target=_party_mul, args=(r, port, emu, q)) for r in range(3)]
+    procs = [ctxm.Process(target=_party_mul, args=(r, port, emu, q, fused)) for r in range(3)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=300) for _ in range(3))

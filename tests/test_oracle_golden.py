@@ -7,7 +7,7 @@ import random
 
 import pytest
 
-from helpers import golden_groth16, gp1, gp2, ih, load_golden
+from helpers import golden_groth16, golden_plonk, gp1, gp2, ih, load_golden, plonk_proof_from_json, plonk_vk_from_zkey
 from oracle import formats as F
 from oracle import groth16 as OG
 from oracle.ec import g1 as og1
@@ -74,3 +74,61 @@ def test_file_parsers_agree_with_golden():
     assert vk["ic"] == z["ic"] and vk["gamma_g2"] == z["gamma_g2"]
     pts = F.read_bn254_crs_g1(REF + "/co-noir/co-noir-common/src/crs/bn254_g1.dat", 4)
     assert pts[0] == (1, 2) and all(og1(BN254).on_curve(P) for P in pts)
+
+
+def test_keccak_transcript_kat():
+    """co-plonk/src/types.rs:201-236."""
+    from oracle import plonk as OP
+    t = OP.Transcript(BN254)
+    p1_ = (20825949499069110345561489838956415747250622568151984013116057026259498945798,
+           4633888776580597789536778273539625207986785465104156818397550354894072332743)
+    p2_ = (13502414797941204782598195942532580786194839256223737894432362681935424485706,
+           18673738305240077401477088441313771484023070622513584695135539045403188608753)
+    p3_ = (20825949499069110345561489838956415747250622568151984013116057026259498945798,
+           17254354095258677432709627471717649880709525692193666844291487539751153875840)
+    s_ = 18493166935391704183319420574241503914733913248159936156014286513312199455
+    t.add_point(p1_), t.add_point(p2_), t.add_point(None), t.add_scalar(s_), t.add_point(p3_), t.add_scalar(s_)
+    assert t.get_challenge() == 16679357168864952869972350724842033299710155825088243463992129238972103889312
+    assert OP.keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+
+
+def test_plonk_prover_reference_kats():
+    """Rounds 2-5 of the Plain driver with deterministic blinders, bit for bit on the reference's known answers
+    (co-plonk/src/round2.rs:300-306, round3.rs:611-630, round4.rs:204-244, round5.rs:394-406)."""
+    from oracle import plonk as OP
+    from oracle.pairing_bn254 import pairing_product_is_one
+    z, w, g = golden_plonk("multiplier2")
+    pr = OP.prove(z, w)
+    for k, kat in g["reference_kat"].items():
+        exp = gp1(kat["value"]) if isinstance(kat["value"], list) else ih(kat["value"])
+        assert pr[k] == exp, (k, kat["source"])
+    assert F.plonk_proof_to_json(pr) == g["oracle_proof_json"]
+    vk = plonk_vk_from_zkey(z, g["vk_power"])
+    public = [ih(x) for x in g["public"]]
+    snark = plonk_proof_from_json(g["snarkjs_proof"])
+    ch = OP.verifier_challenges(BN254, vk, snark, public)                      # plonk.rs:251-310
+    kat = g["reference_verifier_kat"]
+    assert [ch[k] for k in ("alpha", "beta", "gamma", "xi", "u")] == [ih(kat[k]) for k in ("alpha", "beta", "gamma", "xi", "u")]
+    assert ch["v"] == [ih(x) for x in kat["v"]]
+    assert OP.verify(BN254, vk, snark, public, pairing_product_is_one)           # plonk.rs:312-330
+    assert OP.verify(BN254, vk, pr, public, pairing_product_is_one)              # lib.rs:300-325
+    bad = dict(pr)
+    bad["eval_a"] = (bad["eval_a"] + 1) % BN254.r
+    assert not OP.verify(BN254, vk, bad, public, pairing_product_is_one)
+    # random blinders still verify (the proof is randomised, validity is what the reference tests, lib.rs:300-325)
+    rng = random.Random(3)
+    pr2 = OP.prove(z, w, [rng.randrange(BN254.r) for _ in range(11)])
+    assert pr2 != pr and OP.verify(BN254, vk, pr2, public, pairing_product_is_one)
+
+
+def test_plonk_poseidon_snarkjs_proof_and_oracle_proof_verify():
+    """co-plonk/src/lib.rs:327-356 + plonk.rs:332-350 on the poseidon fixture (domain 4096)."""
+    from oracle import plonk as OP
+    from oracle.pairing_bn254 import pairing_product_is_one
+    z, w, g = golden_plonk("poseidon")
+    vk = plonk_vk_from_zkey(z, g["vk_power"])
+    public = [ih(x) for x in g["public"]]
+    assert OP.verify(BN254, vk, plonk_proof_from_json(g["snarkjs_proof"]), public, pairing_product_is_one)
+    pr = OP.prove(z, w)
+    assert F.plonk_proof_to_json(pr) == g["oracle_proof_json"]
+    assert OP.verify(BN254, vk, pr, public, pairing_product_is_one)
