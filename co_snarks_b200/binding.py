@@ -48,6 +48,19 @@ class KeyDesc(C.Structure):
     ]
 
 
+class PlonkKeyDesc(C.Structure):
+    _fields_ = [
+        ("curve", C.c_int),
+        ("n_vars", C.c_uint32), ("n_public", C.c_uint32), ("domain_size", C.c_uint32), ("n_additions", C.c_uint32),
+        ("n_constraints", C.c_uint32),
+        ("k1_mont", u64p), ("k2_mont", u64p), ("vk_points", u64p),
+        ("additions_ids", u32p), ("additions_factors", u64p),
+        ("map_a", u32p), ("map_b", u32p), ("map_c", u32p),
+        ("q_coeffs", u64p * 5), ("q_evals", u64p * 5), ("s_coeffs", u64p * 3), ("s_evals", u64p * 3),
+        ("lagrange_evals", u64p), ("p_tau", u64p), ("n_p_tau", C.c_size_t),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/cosnarks_gpu.h declares
 SIGNATURES = {
     "cs_last_error": (C.c_char_p, []),
@@ -94,6 +107,11 @@ SIGNATURES = {
     "cs_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cs_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_plonk_pk_create": (C.c_int, [C.c_void_p, C.POINTER(PlonkKeyDesc), C.POINTER(C.c_void_p)]),
+    "cs_plonk_pk_free": (None, [C.c_void_p]),
+    "cs_plonk_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "cs_keccak256": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p]),
     "cs_chacha_keystream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_void_p]),
     "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
@@ -401,6 +419,73 @@ class Domain:
 
 
 # ------------------------------------------------------------------------------------------ Groth16
+class PlonkKey:
+    """Device-resident Plonk proving key (cs_plonk_pk) = circom_types::plonk::Zkey as the prover reads it."""
+
+    def __init__(self, ctx, curve, key):
+        """key: dict with n_vars, n_public, domain_size, n_additions, n_constraints (ints) and Montgomery-form
+        numpy arrays k1, k2 [4], vk_points [8, 2*fq], additions_ids [na, 2] u32, additions_factors [na, 2, 4],
+        map_a/b/c u32, q_coeffs/q_evals (5 arrays each), s_coeffs/s_evals (3 each), lagrange_evals
+        [max(1, n_public) * 4n, 4], p_tau [m, 2*fq]."""
+        self.ctx, self.curve = ctx, curve
+        d = PlonkKeyDesc()
+        d.curve = curve
+        for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints"):
+            setattr(d, k, int(key[k]))
+        keep = []
+
+        def arr(x, dt):
+            a = np.ascontiguousarray(x, dtype=dt)
+            keep.append(a)
+            return a.ctypes.data_as(u64p if dt == np.uint64 else u32p)
+        d.k1_mont, d.k2_mont = arr(key["k1"], np.uint64), arr(key["k2"], np.uint64)
+        d.vk_points = arr(key["vk_points"], np.uint64)
+        d.additions_ids = arr(key["additions_ids"], np.uint32)
+        d.additions_factors = arr(key["additions_factors"], np.uint64)
+        for k in ("map_a", "map_b", "map_c"):
+            setattr(d, k, arr(key[k], np.uint32))
+        for i in range(5):
+            d.q_coeffs[i] = arr(key["q_coeffs"][i], np.uint64)
+            d.q_evals[i] = arr(key["q_evals"][i], np.uint64)
+        for i in range(3):
+            d.s_coeffs[i] = arr(key["s_coeffs"][i], np.uint64)
+            d.s_evals[i] = arr(key["s_evals"][i], np.uint64)
+        d.lagrange_evals = arr(key["lagrange_evals"], np.uint64)
+        pt = np.ascontiguousarray(key["p_tau"], dtype=np.uint64)
+        keep.append(pt)
+        d.p_tau = pt.ctypes.data_as(u64p)
+        d.n_p_tau = pt.shape[0]
+        h = C.c_void_p()
+        ctx._check(ctx.lib.cs_plonk_pk_create(ctx.h, C.byref(d), C.byref(h)))
+        self.h = h
+        self.fq = limbs_of(curve, "fq")
+        del keep
+
+    def prove_plain(self, public_inputs, witness, blinders_mont):
+        """Plonk::plain_prove -> (points [9, 2*fq] A B C Z T1 T2 T3 Wxi Wxiw, evals [6, 4] a b c s1 s2 zw), Montgomery."""
+        pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+        wit = np.ascontiguousarray(witness, dtype=np.uint64).reshape(-1, 4)
+        bl = np.ascontiguousarray(blinders_mont, dtype=np.uint64).reshape(-1, 4)
+        assert bl.shape[0] == 11
+        pts = np.zeros((9, 2 * self.fq), dtype=np.uint64)
+        evs = np.zeros((6, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_plonk_prove_plain(self.ctx.h, self.h, _ptr(pub), pub.shape[0], _ptr(wit), wit.shape[0],
+                                                          _ptr(bl), _ptr(pts), _ptr(evs)))
+        return pts, evs
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.cs_plonk_pk_free(self.h)
+            self.h = None
+
+
+def keccak256(lib, data):
+    out = np.zeros(32, dtype=np.uint8)
+    rc = lib.cs_keccak256(bytes(data), len(data), _ptr(out))
+    assert rc == 0
+    return bytes(out)
+
+
 class Groth16Key:
     """Device-resident proving key + constraint matrices (cs_groth16_pk).
 

@@ -296,6 +296,47 @@ int cs_groth16_shamir_local(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pu
                             uint64_t* out_g_a, uint64_t* out_g1_b, uint64_t* out_g2_b,
                             uint64_t* out_l_acc, uint64_t* out_h_acc);
 
+/* ---- Plonk (snarkjs) prover, plain driver: co-circom/co-plonk/src/lib.rs:80-115 (prove_inner) with
+ * PlainPlonkDriver (mpc/plain.rs) == Plonk::plain_prove (lib.rs:271-281) ----------------------------------
+ * cs_plonk_pk_create uploads circom_types::plonk::Zkey once (fields read by the prover: round1.rs:109-224
+ * additions + wire maps, round2.rs:99-160 sigma evaluations, round3.rs:330-420 selector / sigma / Lagrange
+ * evaluations on the extended domain, round4.rs:143-144 + round5.rs:150-230 coefficient forms, p_tau) and
+ * allocates the per-proof workspace.  All field elements Montgomery, points affine Montgomery, (0,0) = infinity.
+ * Polynomials: `coeffs` = domain_size values, `evals` = 4 * domain_size values (the zkey stores both). */
+typedef struct cs_plonk_pk cs_plonk_pk;
+typedef struct {
+  cs_curve curve;
+  uint32_t n_vars, n_public, domain_size, n_additions, n_constraints;
+  const uint64_t* k1_mont;            /* verifying_key.k1, k2 */
+  const uint64_t* k2_mont;
+  const uint64_t* vk_points;          /* Qm Ql Qr Qo Qc S1 S2 S3 (G1), hashed into the transcript (round2.rs:211-218) */
+  const uint32_t* additions_ids;      /* n_additions x (signal_id1, signal_id2) */
+  const uint64_t* additions_factors;  /* n_additions x (factor1, factor2) */
+  const uint32_t* map_a;              /* n_constraints wire -> signal maps */
+  const uint32_t* map_b;
+  const uint32_t* map_c;
+  const uint64_t* q_coeffs[5];        /* qm ql qr qo qc */
+  const uint64_t* q_evals[5];
+  const uint64_t* s_coeffs[3];        /* sigma 1..3 */
+  const uint64_t* s_evals[3];
+  const uint64_t* lagrange_evals;     /* max(1, n_public) x 4 * domain_size */
+  const uint64_t* p_tau;              /* SRS powers, n_p_tau >= domain_size + 6 G1 points */
+  size_t n_p_tau;
+} cs_plonk_key_desc;
+int cs_plonk_pk_create(cs_ctx* ctx, const cs_plonk_key_desc* desc, cs_plonk_pk** out);
+void cs_plonk_pk_free(cs_plonk_pk* pk);
+/* One proof.  h_public_inputs: n_public + 1 values as in SharedWitness.public_inputs (entry 0, the constant one,
+ * is replaced by zero like types.rs:118-120); h_witness: the remaining n_vars - n_additions - n_public - 1
+ * values; h_blinders_mont: the 11 round-1 blinding scalars b[0..11) (Round1Challenges, round1.rs:45-47) -- the
+ * caller draws them, which is what makes proofs reproducible against the oracle / the reference's KATs.
+ * out_points: 9 G1 affine points A B C Z T1 T2 T3 Wxi Wxiw; out_evals: eval_a eval_b eval_c eval_s1 eval_s2
+ * eval_zw (PlonkProof, round5.rs:50-70).  Errors mirror PlonkProofError (lib.rs:40-69). */
+int cs_plonk_prove_plain(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_public_inputs, size_t n_public_inputs,
+                         const uint64_t* h_witness, size_t n_witness, const uint64_t* h_blinders_mont,
+                         uint64_t* out_points, uint64_t* out_evals);
+/* sha3::Keccak256 of a host buffer (the transcript hash, types.rs:13-14); test hook. */
+int cs_keccak256(const uint8_t* data, size_t len, uint8_t* out32);
+
 /* ---- single-point helpers used by the host-side protocol code (latency-only, run on the host) -----
  * scalar_mul_public_point_hs (mpc/rep3.rs:141-146), point addition / negation for
  * open_half_point (pointshare.rs:152-155) and the final sums (groth16.rs:314-322).

@@ -132,6 +132,34 @@ def plonk_proof_from_json(d):
     return {k: (ih(v) if isinstance(v, str) else gp1(v)) for k, v in d.items()}
 
 
+def make_plonk_key(ctx, cv, z):
+    """oracle-style plonk zkey dict -> device PlonkKey."""
+    na = z["n_additions"]
+    key = dict(n_vars=z["n_vars"], n_public=z["n_public"], domain_size=z["domain_size"], n_additions=na,
+               n_constraints=z["n_constraints"], k1=cv.fr([z["k1"]]), k2=cv.fr([z["k2"]]),
+               vk_points=cv.g1([z["vk_" + k] for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")]),
+               additions_ids=np.array([[a, b] for a, b, _, _ in z["additions"]], dtype=np.uint32).reshape(na, 2),
+               additions_factors=cv.fr([f for _, _, f1, f2 in z["additions"] for f in (f1, f2)]).reshape(na, 2, 4),
+               map_a=np.array(z["map_a"], dtype=np.uint32), map_b=np.array(z["map_b"], dtype=np.uint32),
+               map_c=np.array(z["map_c"], dtype=np.uint32),
+               q_coeffs=[cv.fr(z[k]["coeffs"]) for k in ("qm", "ql", "qr", "qo", "qc")],
+               q_evals=[cv.fr(z[k]["evals"]) for k in ("qm", "ql", "qr", "qo", "qc")],
+               s_coeffs=[cv.fr(z[k]["coeffs"]) for k in ("s1", "s2", "s3")],
+               s_evals=[cv.fr(z[k]["evals"]) for k in ("s1", "s2", "s3")],
+               lagrange_evals=np.concatenate([cv.fr(P["evals"]) for P in z["lagrange"]]),
+               p_tau=cv.g1(z["p_tau"]))
+    return B.PlonkKey(ctx, cv.id, key)
+
+
+def plonk_proof_from_device(cv, pts, evs):
+    names = ("a", "b", "c", "z", "t1", "t2", "t3", "wxi", "wxiw")
+    proof = {k: cv.pt1(pts[i]) for i, k in enumerate(names)}
+    ev = cv.fr_back(evs)
+    for i, k in enumerate(("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw")):
+        proof[k] = ev[i]
+    return proof
+
+
 def make_key(ctx, cv, z, m, window_bits=0):
     mc = dict(num_constraints=m["num_constraints"], num_instance_variables=m["num_instance_variables"],
               num_witness_variables=m["num_witness_variables"], a=cv.csr(m["a"]), b=cv.csr(m["b"]))

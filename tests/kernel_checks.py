@@ -3,6 +3,8 @@ tests (tests/emu build of the same kernels).  Every check compares the C-ABI res
 or with a committed golden vector; integer work => bit-exact equality."""
 import random
 
+import pytest
+
 import numpy as np
 
 from co_snarks_b200 import binding as B
@@ -486,6 +488,43 @@ def check_rep3_mul_vec_reshare(ctx, n=150, seed=15, use_ipc=False):
             ctx.ipc_close(peers[p])
         for d in (d_a[p], d_b[p], d_out[p], d_out2[p]):
             ctx.free(d)
+
+
+def check_keccak(lib):
+    from oracle import plonk as OP
+    for msg in (b"", b"abc", bytes(range(135)), bytes(range(136)), bytes(200) + b"x" * 77):
+        assert B.keccak256(lib, msg) == OP.keccak256(msg)
+    assert B.keccak256(lib, b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
+
+
+def check_plonk_prove(ctx, name="multiplier2", random_blinders=True):
+    """Plonk::plain_prove on the device == the oracle's restatement, field by field, for the reference's
+    deterministic blinders (the KAT setting of co-plonk/src/round{2..5}.rs tests) and for random ones; the proof
+    JSON equals the committed golden one, which the oracle's verifier accepts (tests/test_oracle_golden.py)."""
+    from helpers import golden_plonk, make_plonk_key, plonk_proof_from_device
+    from oracle import plonk as OP
+    from oracle.formats import plonk_proof_to_json
+    cv = Conv("bn254")
+    z, w, g = golden_plonk(name)
+    npub = z["n_public"]
+    pk = make_plonk_key(ctx, cv, z)
+    pub, wit = cv.fr(w[:npub + 1]), cv.fr(w[npub + 1:])
+    pts, evs = pk.prove_plain(pub, wit, cv.fr(list(range(11))))
+    got = plonk_proof_from_device(cv, pts, evs)
+    assert plonk_proof_to_json(got) == g["oracle_proof_json"]
+    if "reference_kat" in g:
+        for k, kat in g["reference_kat"].items():
+            exp = gp1(kat["value"]) if isinstance(kat["value"], list) else ih(kat["value"])
+            assert got[k] == exp, (k, kat["source"])
+    if random_blinders:
+        rng = random.Random(17)
+        bl = [rng.randrange(cv.r) for _ in range(11)]
+        pts, evs = pk.prove_plain(pub, wit, cv.fr(bl))
+        assert plonk_proof_from_device(cv, pts, evs) == OP.prove(z, w, bl)
+    # error behaviour: wrong witness length (PlonkProofError::CorruptedWitness territory, lib.rs:60-62)
+    with pytest.raises(RuntimeError):
+        pk.prove_plain(pub, wit[:-1], cv.fr(list(range(11))))
+    pk.free()
 
 
 def check_shamir_degree_reduce(ctx, n=64, seed=12):

@@ -94,3 +94,15 @@ def test_emu_libsnark_reduction(emu_ctx):
 
 def test_rep3_mul_vec_reshare(emu_ctx):
     K.check_rep3_mul_vec_reshare(emu_ctx, use_ipc=True)
+
+
+def test_keccak(emu_ctx):
+    K.check_keccak(emu_ctx.lib)
+
+
+def test_plonk_prove_multiplier2(emu_ctx):
+    K.check_plonk_prove(emu_ctx, "multiplier2")
+
+
+def test_plonk_prove_poseidon(emu_ctx):
+    K.check_plonk_prove(emu_ctx, "poseidon", random_blinders=False)

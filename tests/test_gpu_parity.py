@@ -113,3 +113,15 @@ def test_libsnark_reduction(gpu_ctx):
 @pytest.mark.gpu
 def test_rep3_mul_vec_reshare(gpu_ctx):
     K.check_rep3_mul_vec_reshare(gpu_ctx)
+
+
+def test_keccak(gpu_ctx):
+    K.check_keccak(gpu_ctx.lib)
+
+
+def test_plonk_prove_multiplier2(gpu_ctx):
+    K.check_plonk_prove(gpu_ctx, "multiplier2")
+
+
+def test_plonk_prove_poseidon(gpu_ctx):
+    K.check_plonk_prove(gpu_ctx, "poseidon")
