@@ -527,6 +527,31 @@ def check_plonk_prove(ctx, name="multiplier2", random_blinders=True):
     pk.free()
 
 
+def check_plonk_synthetic(ctx, log_n, n_public=2, against_oracle=True, seed=5):
+    """Synthetic snarkjs-style key with known tau (workloads/synth_plonk.py): the device proof is accepted by the
+    oracle's verifier (pairing check) and rejected for a wrong public input; at small sizes it also equals the
+    oracle prover's proof bit for bit.  Covers additions with dependency levels, empty rows and n_public = 0."""
+    from helpers import plonk_proof_from_device
+    from oracle import plonk as OP
+    from oracle.pairing_bn254 import pairing_product_is_one
+    from workloads.synth_plonk import SynthPlonk
+    cv = Conv("bn254")
+    syn = SynthPlonk(ctx, log_n, n_public=n_public)
+    pk = syn.make_key()
+    rng = random.Random(seed)
+    bl = [rng.randrange(cv.r) for _ in range(11)]
+    pts, evs = pk.prove_plain(syn.public_inputs, syn.private_witness, cv.fr(bl))
+    got = plonk_proof_from_device(cv, pts, evs)
+    pub = syn.full_witness[1:n_public + 1]
+    vk = syn.vk_ints()
+    assert OP.verify(BN254, vk, got, pub, pairing_product_is_one)
+    if n_public:
+        assert not OP.verify(BN254, vk, got, [(pub[0] + 1) % cv.r] + pub[1:], pairing_product_is_one)
+    if against_oracle:
+        assert OP.prove(syn.oracle_zkey(), syn.full_witness, bl) == got
+    pk.free()
+
+
 def check_shamir_degree_reduce(ctx, n=64, seed=12):
     """Shamir king-based degree reduction (shamir/network.rs:150-243) assembled from cs_vec_lincomb, for
     n = 3 parties, t = 1: every party masks its degree-2t product share with r_2t, the king interpolates

@@ -106,3 +106,8 @@ def test_plonk_prove_multiplier2(emu_ctx):
 
 def test_plonk_prove_poseidon(emu_ctx):
     K.check_plonk_prove(emu_ctx, "poseidon", random_blinders=False)
+
+
+def test_plonk_synthetic_key(emu_ctx):
+    K.check_plonk_synthetic(emu_ctx, 6, n_public=2)
+    K.check_plonk_synthetic(emu_ctx, 5, n_public=0)

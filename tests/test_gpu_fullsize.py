@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from co_snarks_b200 import binding as B
+import kernel_checks as K
 from helpers import Conv
 from oracle.ec import g1 as og1, g2 as og2
 from oracle.fields import BN254, groth16_roots_of_unity
@@ -129,3 +130,12 @@ def test_ntt_plonk_sizes_roundtrip(gpu_ctx, lg, batch):
     assert (gpu_ctx.d2h(da, (n * batch, 4)) == a).all()
     gpu_ctx.free(da)
     dom.free()
+
+
+def test_plonk_synthetic_2p10_equals_oracle(gpu_ctx):
+    K.check_plonk_synthetic(gpu_ctx, 10, n_public=3)
+
+
+def test_plonk_synthetic_2p16_verifies(gpu_ctx):
+    """A 2^16-gate proof (4n = 2^18-point quotient) checked by the oracle's pairing verifier."""
+    K.check_plonk_synthetic(gpu_ctx, 16, n_public=2, against_oracle=False)
