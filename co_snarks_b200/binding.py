@@ -112,6 +112,14 @@ SIGNATURES = {
     "cs_plonk_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "cs_keccak256": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p]),
+    "cs_plonk_rep3_create": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "cs_plonk_rep3_free": (None, [C.c_void_p]),
+    "cs_plonk_rep3_arena": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint)]),
+    "cs_plonk_rep3_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_plonk_rep3_round1": (C.c_int, [C.c_void_p, C.POINTER(Rep3Prf), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                       C.c_void_p, C.c_void_p]),
+    "cs_plonk_rep3_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cs_plonk_rep3_prf_words": (C.c_uint64, [C.c_void_p]),
     "cs_chacha_keystream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_void_p]),
     "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
@@ -476,6 +484,53 @@ class PlonkKey:
     def free(self):
         if self.h:
             self.ctx.lib.cs_plonk_pk_free(self.h)
+            self.h = None
+
+
+# cs_plonk_rep3_step ids (include/cosnarks_gpu.h)
+(R3_ROUND2_A, R3_ROUND2_B, R3_ROUND2_C, R3_ROUND2_D, R3_ROUND2_E, R3_ROUND2_F, R3_ROUND2_G, R3_ROUND3_A, R3_ROUND3_B,
+ R3_ROUND4, R3_ROUND5) = range(1, 12)
+
+
+class PlonkRep3Session:
+    """One party's state of a Rep3 co-Plonk proof (cs_plonk_rep3)."""
+
+    def __init__(self, ctx, pk, party):
+        self.ctx, self.pk, self.party = ctx, pk, party
+        h = C.c_void_p()
+        ctx._check(ctx.lib.cs_plonk_rep3_create(ctx.h, pk.h, party, C.byref(h)))
+        self.h = h
+        p, sb, ns = C.c_void_p(), C.c_size_t(), C.c_uint()
+        ctx._check(ctx.lib.cs_plonk_rep3_arena(self.h, C.byref(p), C.byref(sb), C.byref(ns)))
+        self.arena, self.slot_bytes, self.n_slots = p.value, sb.value, ns.value
+
+    def connect(self, d_next_arena):
+        self.ctx._check(self.ctx.lib.cs_plonk_rep3_connect(self.h, C.c_void_p(d_next_arena) if d_next_arena else None))
+
+    def round1(self, prf_args, public_inputs, witness_shares, blinder_shares):
+        s1, p1, s2, p2, rounds = prf_args
+        prf = Rep3Prf((C.c_uint8 * 32)(*bytes(s1)), p1, (C.c_uint8 * 32)(*bytes(s2)), p2, rounds)
+        pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+        wit = np.ascontiguousarray(witness_shares, dtype=np.uint64).reshape(-1, 8)
+        bl = np.ascontiguousarray(blinder_shares, dtype=np.uint64).reshape(-1, 8)
+        assert bl.shape[0] == 11
+        pts = np.zeros((3, 2 * self.pk.fq), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_plonk_rep3_round1(self.h, C.byref(prf), _ptr(pub), pub.shape[0], _ptr(wit), wit.shape[0],
+                                                          _ptr(bl), _ptr(pts)))
+        return pts
+
+    def step(self, step, h_in=None, out_shape=None):
+        a = None if h_in is None else np.ascontiguousarray(h_in, dtype=np.uint64)
+        out = None if out_shape is None else np.zeros(out_shape, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_plonk_rep3_step(self.h, step, _ptr(a), _ptr(out)))
+        return out
+
+    def prf_words(self):
+        return int(self.ctx.lib.cs_plonk_rep3_prf_words(self.h))
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.cs_plonk_rep3_free(self.h)
             self.h = None
 
 

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include "cs_lib.cuh"
 #include "cs_plonk.cuh"
+#include "cs_plonk_rep3.cuh"
 
 using namespace cs;
 
@@ -114,51 +115,56 @@ int upload(cs_ctx* ctx, DevBuf& buf, const void* src, size_t bytes) {
 template <class HR>
 void put(uint32_t* dst, const HR& v) { memcpy(dst, v.l, sizeof(v.l)); }
 
-template <class FrP, int OP>
-int scan(cs_ctx* ctx, cs_plonk_pk* pk, const uint32_t* in, uint32_t* out, uint32_t n, int rev) {
+// H: anything with DevBuf members `totals` and `small` (the key's or a Rep3 session's scratch)
+template <class FrP, int OP, class H>
+int scan(cs_ctx* ctx, H* pk, const uint32_t* in, uint32_t* out, uint32_t n, int rev) {
   const uint32_t nb = ceil_div(n, SCAN_TILE);
   CS_TRY(pk->totals.reserve((size_t)nb * 32));
   CS_LAUNCH_SYNC(k_scan_block<FrP COMMA OP>, nb, SCAN_THREADS, (size_t)SCAN_THREADS * 32, ctx->stream, in, out, n, rev,
-                 pk->totals.as<uint32_t>());
+                 pk->totals.template as<uint32_t>());
   if (nb > 1) {
-    CS_LAUNCH_SYNC(k_scan_totals<FrP COMMA OP>, 1, 256, (size_t)256 * 32, ctx->stream, pk->totals.as<uint32_t>(), nb);
-    CS_LAUNCH(k_scan_apply<FrP COMMA OP>, ceil_div(n, 256), 256, 0, ctx->stream, out, n, rev, pk->totals.as<uint32_t>());
+    CS_LAUNCH_SYNC(k_scan_totals<FrP COMMA OP>, 1, 256, (size_t)256 * 32, ctx->stream, pk->totals.template as<uint32_t>(), nb);
+    CS_LAUNCH(k_scan_apply<FrP COMMA OP>, ceil_div(n, 256), 256, 0, ctx->stream, out, n, rev, pk->totals.template as<uint32_t>());
   }
   CS_CUDA(cudaGetLastError());
   return 0;
 }
 
 template <class FrP>
-CS_GLOBAL void k_spread4(const uint32_t* __restrict__ in, uint32_t n, uint32_t* __restrict__ out) {
+CS_GLOBAL void k_spread4(const uint32_t* __restrict__ in, uint32_t n, uint32_t batch, uint32_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // over 4n outputs
   if (i >= 4 * n) return;
-  Fp<FrP> v = Fp<FrP>::zero();
-  if ((i & 3) == 0) v = ld_fr<FrP>(in + (size_t)(i >> 2) * FrP::N);
-  st_fr<FrP>(out + (size_t)i * FrP::N, v);
+  for (uint32_t c = 0; c < batch; c++) {
+    Fp<FrP> v = Fp<FrP>::zero();
+    if ((i & 3) == 0) v = ld_fr<FrP>(in + ((size_t)(i >> 2) * batch + c) * FrP::N);
+    st_fr<FrP>(out + ((size_t)i * batch + c) * FrP::N, v);
+  }
 }
 
 // evaluations (natural order, n points) -> coefficients: `poly` natural order, and -- when ev4 != NULL -- the
 // 4n-point evaluations of the same (unblinded) polynomial, without permuting in between.
 template <class Cfg>
-int interpolate_and_extend(cs_ctx* ctx, cs_plonk_pk* pk, uint32_t* poly, uint32_t* ev4) {
+int interpolate_and_extend(cs_ctx* ctx, cs_plonk_pk* pk, uint32_t* poly, uint32_t* ev4, unsigned batch = 1) {
   typedef typename Cfg::FrP FrP;
   const uint32_t n = pk->n;
-  CS_TRY(ntt_run(ctx, pk->dom, poly, 1, true, nullptr, ctx->stream));  // bit-reversed coefficients
+  CS_TRY(ntt_run(ctx, pk->dom, poly, batch, true, nullptr, ctx->stream));  // bit-reversed coefficients
   if (ev4) {
-    CS_LAUNCH(k_spread4<FrP>, ceil_div((size_t)4 * n, 256), 256, 0, ctx->stream, poly, n, ev4);
-    CS_TRY(ntt_run(ctx, pk->dom4, ev4, 1, false, nullptr, ctx->stream));
+    CS_LAUNCH(k_spread4<FrP>, ceil_div((size_t)4 * n, 256), 256, 0, ctx->stream, poly, n, batch, ev4);
+    CS_TRY(ntt_run(ctx, pk->dom4, ev4, batch, false, nullptr, ctx->stream));
   }
-  CS_LAUNCH(k_bit_reverse<FrP>, ceil_div(n, 256), 256, 0, ctx->stream, poly, pk->log_n, 1u);
+  CS_LAUNCH(k_bit_reverse<FrP>, ceil_div(n, 256), 256, 0, ctx->stream, poly, pk->log_n, batch);
   CS_CUDA(cudaGetLastError());
   return 0;
 }
 
+// b: `count` blinders of `batch` components each (component-major per blinder: b[i * batch + c])
 template <class Cfg>
-int blind(cs_ctx* ctx, uint32_t* poly, uint32_t n, const host::HFp<typename Cfg::FrP>* b, int count) {
+int blind(cs_ctx* ctx, uint32_t* poly, uint32_t n, const host::HFp<typename Cfg::FrP>* b, int count, unsigned batch = 1) {
   PlonkBlind rev;
   memset(&rev, 0, sizeof(rev));
-  for (int i = 0; i < count; i++) put(rev.v[i], b[count - 1 - i]);
-  CS_LAUNCH(k_plonk_blind<typename Cfg::FrP>, 1, 32, 0, ctx->stream, poly, n, rev, (uint32_t)count);
+  for (int i = 0; i < count; i++)
+    for (unsigned c = 0; c < batch; c++) put(rev.v[i * batch + c], b[(count - 1 - i) * batch + c]);
+  CS_LAUNCH(k_plonk_blind<typename Cfg::FrP>, 1, 32, 0, ctx->stream, poly, n, batch, rev, (uint32_t)count);
   return 0;
 }
 
@@ -266,8 +272,8 @@ int plonk_pk_create_t(cs_ctx* ctx, const cs_plonk_key_desc* d, cs_plonk_pk* pk) 
 }
 
 // q(X) = p(X) / (X - x) in place over `p` (len entries -> len - 1), optionally subtracting *sub0 from p[0] first
-template <class Cfg>
-int divide_by_linear(cs_ctx* ctx, cs_plonk_pk* pk, uint32_t* p, uint32_t len, const host::HFp<typename Cfg::FrP>& x,
+template <class Cfg, class H>
+int divide_by_linear(cs_ctx* ctx, H* pk, uint32_t* p, uint32_t len, const host::HFp<typename Cfg::FrP>& x,
                      const host::HFp<typename Cfg::FrP>* sub0) {
   typedef typename Cfg::FrP FrP;
   typedef host::HFp<FrP> HR;
@@ -276,7 +282,7 @@ int divide_by_linear(cs_ctx* ctx, cs_plonk_pk* pk, uint32_t* p, uint32_t len, co
   HR a = x, b = x.inverse();
   for (int j = 0; j < 33; j++) { tab[j] = a; tab[33 + j] = b; a = a.sqr(); b = b.sqr(); }
   if (sub0) tab[66] = *sub0;
-  uint32_t* d_tab = pk->small.as<uint32_t>();
+  uint32_t* d_tab = pk->small.template as<uint32_t>();
   CS_CUDA(cudaMemcpyAsync(d_tab, tab.data(), tab.size() * sizeof(HR), cudaMemcpyHostToDevice, ctx->stream));
   CS_CUDA(cudaStreamSynchronize(ctx->stream));  // `tab` is a stack-owned vector
   const unsigned blocks = ceil_div(ceil_div(len, 8), 128);
@@ -310,7 +316,7 @@ int plonk_prove_plain_t(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_pub, con
     uint32_t lo = 0;
     for (uint32_t hi : pk->level_ends) {
       CS_LAUNCH(k_plonk_additions<FrP>, ceil_div(hi - lo, 128), 128, 0, st, pk->add_order.as<uint32_t>(), lo, hi,
-                pk->add_ids.as<uint32_t>(), pk->add_factors.as<uint32_t>(), pk->n_vars - pk->n_additions, w);
+                pk->add_ids.as<uint32_t>(), pk->add_factors.as<uint32_t>(), pk->n_vars - pk->n_additions, 1u, w);
       lo = hi;
     }
   }
@@ -320,7 +326,7 @@ int plonk_prove_plain_t(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_pub, con
   for (int i = 0; i < 3; i++) buf[i] = pk->buf[i].as<uint32_t>();
   for (int i = 0; i < 4; i++) { poly[i] = pk->poly[i].as<uint32_t>(); ev[i] = pk->ev[i].as<uint32_t>(); }
   for (int k = 0; k < 3; k++) {
-    CS_LAUNCH(k_plonk_gather<FrP>, ceil_div(n, 256), 256, 0, st, maps[k], pk->n_constraints, n, w, buf[k]);
+    CS_LAUNCH(k_plonk_gather<FrP>, ceil_div(n, 256), 256, 0, st, maps[k], pk->n_constraints, n, 1u, w, buf[k]);
     CS_CUDA(cudaMemcpyAsync(poly[k], buf[k], (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
     CS_TRY(interpolate_and_extend<Cfg>(ctx, pk, poly[k], ev[k]));
     CS_TRY(blind<Cfg>(ctx, poly[k], n, b + 2 * k, 2));
@@ -468,7 +474,7 @@ int plonk_prove_plain_t(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_pub, con
   li.s1 = pk->s_coeffs[0].as<uint32_t>(); li.s2 = pk->s_coeffs[1].as<uint32_t>(); li.s3 = pk->s_coeffs[2].as<uint32_t>();
   li.pa = poly[0]; li.pb = poly[1]; li.pc = poly[2]; li.pz = poly[3]; li.t1 = t1; li.t2 = t2; li.t3 = t3;
   uint32_t *wxi = pk->tmp0.as<uint32_t>(), *wxiw = pk->tmp1.as<uint32_t>();
-  CS_LAUNCH(k_plonk_wxi_numerator<FrP>, ceil_div(n + 6, 128), 128, 0, st, li, W, n, wxi);
+  CS_LAUNCH(k_plonk_wxi_numerator<FrP>, ceil_div(n + 6, 128), 128, 0, st, li, W, n, 1, wxi);
   CS_TRY(divide_by_linear<Cfg>(ctx, pk, wxi, n + 6, xi, nullptr));
   CS_CUDA(cudaMemcpyAsync(wxiw, poly[3], (size_t)(n + 3) * 32, cudaMemcpyDeviceToDevice, st));
   CS_TRY(divide_by_linear<Cfg>(ctx, pk, wxiw, n + 3, xiw, &ezw));
@@ -478,6 +484,336 @@ int plonk_prove_plain_t(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_pub, con
   }
   HR evs[6] = {ea, eb, ec, es1, es2, ezw};
   memcpy(out_evals, evs, sizeof(evs));
+  return 0;
+}
+
+
+// ======================================================================================================
+// Rep3 co-Plonk: one session per party (Rep3CoPlonk::prove, co-plonk/src/lib.rs:222-240 with
+// Rep3PlonkDriver, mpc/rep3.rs).  The session owns the party's share vectors and the arena that the next
+// party's products are stored into; the host driver (co_snarks_b200/plonk.py) sequences the steps, opens the
+// partial commitments / evaluations / masked vectors and hashes the transcript.  See cs_plonk_rep3.cuh.
+// ======================================================================================================
+}  // namespace
+
+struct cs_plonk_rep3 {
+  cs_ctx* ctx = nullptr;
+  cs_plonk_pk* pk = nullptr;
+  int party = 0;
+  DevBuf w, buf[3], polysh[4], ev[4], polyadd[4], arena, addv, pubv, t, tz, t1, t2, t3, tmp0, tmp1, totals, small;
+  uint32_t* next_arena = nullptr;
+  size_t slot_words = 0;  // 32-bit words per arena slot (4n shares)
+  cs::PrfArgs prf;
+  uint64_t ctr = 0;       // field elements drawn from each stream so far
+  uint64_t rbase = 0;     // first random share of round 2
+  cs::PlonkConsts K;
+  cs::R3Blinders B;
+  std::vector<uint64_t> pub;  // public inputs (Montgomery), without the leading slot
+};
+
+namespace {
+
+constexpr int R3_SLOTS = 12;
+
+template <class Cfg>
+int r3_create_t(cs_plonk_rep3* s) {
+  const cs_plonk_pk* pk = s->pk;
+  const size_t n = pk->n;
+  CS_TRY(s->w.reserve((size_t)pk->n_vars * 64));
+  for (int i = 0; i < 3; i++) CS_TRY(s->buf[i].reserve(n * 64));
+  for (int i = 0; i < 4; i++) {
+    CS_TRY(s->polysh[i].reserve((n + 8) * 64));
+    CS_TRY(s->polyadd[i].reserve((n + 8) * 32));
+    CS_TRY(s->ev[i].reserve(4 * n * 64));
+  }
+  s->slot_words = 4 * n * 2 * 8;
+  CS_TRY(s->arena.reserve((size_t)R3_SLOTS * s->slot_words * 4));
+  CS_CUDA(cudaMemsetAsync(s->arena.p, 0, (size_t)R3_SLOTS * s->slot_words * 4, s->ctx->stream));
+  CS_TRY(s->addv.reserve((2 * n + 2) * 32));
+  CS_TRY(s->pubv.reserve((6 * n + 8) * 32));
+  CS_TRY(s->t.reserve(4 * n * 32));
+  CS_TRY(s->tz.reserve(4 * n * 32));
+  CS_TRY(s->t1.reserve((n + 8) * 32));
+  CS_TRY(s->t2.reserve((n + 8) * 32));
+  CS_TRY(s->t3.reserve((n + 8) * 32));
+  CS_TRY(s->tmp0.reserve((n + 8) * 32));
+  CS_TRY(s->tmp1.reserve((n + 8) * 32));
+  CS_TRY(s->small.reserve(4096));
+  CS_CUDA(cudaStreamSynchronize(s->ctx->stream));
+  return 0;
+}
+
+inline uint32_t* r3_slot(cs_plonk_rep3* s, int k) { return s->arena.as<uint32_t>() + (size_t)k * s->slot_words; }
+inline uint32_t* r3_peer(cs_plonk_rep3* s, int k) { return s->next_arena ? s->next_arena + (size_t)k * s->slot_words : nullptr; }
+
+template <class Cfg>
+R3Round2In r3_round2_in(cs_plonk_rep3* s) {
+  R3Round2In in;
+  in.a = s->buf[0].as<uint32_t>(); in.b = s->buf[1].as<uint32_t>(); in.c = s->buf[2].as<uint32_t>();
+  in.s1 = s->pk->s_evals[0].as<uint32_t>(); in.s2 = s->pk->s_evals[1].as<uint32_t>(); in.s3 = s->pk->s_evals[2].as<uint32_t>();
+  in.tw4 = s->pk->dom4->tw_fwd.template as<uint32_t>();
+  return in;
+}
+
+template <class Cfg>
+int r3_round1_t(cs_plonk_rep3* s, const uint64_t* h_pub, const uint64_t* h_wit_shares, const uint64_t* h_blind, uint64_t* out_points) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HR;
+  constexpr int NW = FrP::N;
+  cs_ctx* ctx = s->ctx;
+  cs_plonk_pk* pk = s->pk;
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = pk->n, npub = pk->n_public;
+  const uint32_t n_priv = pk->n_vars - pk->n_additions - npub - 1;
+  // w = 0 | promote(public) | witness shares | additions   (promote_to_trivial_share, rep3/arithmetic.rs:41-50)
+  std::vector<uint64_t> stage((size_t)(npub + 1) * 2 * HR::N, 0);
+  for (uint32_t j = 1; j <= npub; j++)
+    if (s->party < 2) memcpy(&stage[((size_t)j * 2 + s->party) * HR::N], h_pub + (size_t)j * HR::N, sizeof(HR));
+  s->pub.assign(h_pub + HR::N, h_pub + (size_t)(npub + 1) * HR::N);
+  uint32_t* w = s->w.as<uint32_t>();
+  CS_CUDA(cudaMemcpyAsync(w, stage.data(), stage.size() * 8, cudaMemcpyHostToDevice, st));
+  if (n_priv) CS_CUDA(cudaMemcpyAsync(w + (size_t)(npub + 1) * 2 * NW, h_wit_shares, (size_t)n_priv * 64, cudaMemcpyHostToDevice, st));
+  CS_CUDA(cudaStreamSynchronize(st));  // `stage` is a local vector
+  uint32_t lo = 0;
+  for (uint32_t hi : pk->level_ends) {
+    CS_LAUNCH(k_plonk_additions<FrP>, ceil_div(hi - lo, 128), 128, 0, st, pk->add_order.as<uint32_t>(), lo, hi,
+              pk->add_ids.as<uint32_t>(), pk->add_factors.as<uint32_t>(), pk->n_vars - pk->n_additions, 2u, w);
+    lo = hi;
+  }
+  HR bsh[22];
+  memcpy(bsh, h_blind, sizeof(bsh));
+  memset(&s->K, 0, sizeof(s->K));
+  memset(&s->B, 0, sizeof(s->B));
+  for (int i = 0; i < 11; i++) put(s->K.b[i], bsh[2 * i]);  // additive part of each blinder
+  for (int i = 0; i < 9; i++) { put(s->B.b[i].v[0], bsh[2 * i]); put(s->B.b[i].v[1], bsh[2 * i + 1]); }
+  put(s->K.k1, *reinterpret_cast<const HR*>(pk->k1.data()));
+  put(s->K.k2, *reinterpret_cast<const HR*>(pk->k2.data()));
+  const uint32_t* maps[3] = {pk->map_a.as<uint32_t>(), pk->map_b.as<uint32_t>(), pk->map_c.as<uint32_t>()};
+  const size_t pl = point_limbs64(pk->curve, CS_G1);
+  Commit c[3];
+  for (int k = 0; k < 3; k++) {
+    uint32_t* buf = s->buf[k].as<uint32_t>();
+    uint32_t* ps = s->polysh[k].as<uint32_t>();
+    CS_LAUNCH(k_plonk_gather<FrP>, ceil_div(n, 256), 256, 0, st, maps[k], pk->n_constraints, n, 2u, w, buf);
+    CS_CUDA(cudaMemcpyAsync(ps, buf, (size_t)n * 64, cudaMemcpyDeviceToDevice, st));
+    CS_TRY(interpolate_and_extend<Cfg>(ctx, pk, ps, s->ev[k].as<uint32_t>(), 2));
+    CS_TRY(blind<Cfg>(ctx, ps, n, bsh + 4 * k, 2, 2));
+    CS_LAUNCH(k_extract_component<FrP>, ceil_div(n + 2, 256), 256, 0, st, ps, n + 2, 2u, 0u, s->polyadd[k].as<uint32_t>());
+    c[k] = Commit{s->polyadd[k].as<uint32_t>(), (size_t)n + 2, out_points + k * pl};
+  }
+  CS_TRY(commit_many<Cfg>(ctx, pk, c, 3));
+  return 0;
+}
+
+// elementwise inverse of `cnt` public values at `v` (device) into `out`; scratch: 2 cnt elements at `scr`
+template <class Cfg>
+int r3_batch_inverse(cs_plonk_rep3* s, const uint32_t* v, uint32_t cnt, uint32_t* scr, uint32_t* out) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HR;
+  cs_ctx* ctx = s->ctx;
+  uint32_t *pre = scr, *suf = scr + (size_t)cnt * FrP::N;
+  CS_TRY((scan<FrP, 0>(ctx, s, v, pre, cnt, 0)));
+  CS_TRY((scan<FrP, 0>(ctx, s, v, suf, cnt, 1)));
+  HR total;
+  CS_CUDA(cudaMemcpyAsync(total.l, suf, sizeof(total.l), cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (total.is_zero()) return fail(CS_ERR_ARG, "Cannot invert zero");  // rep3 inv_vec, arithmetic.rs:245-262
+  HR it = total.inverse();
+  uint32_t* d_it = s->small.as<uint32_t>() + 128 * FrP::N;
+  CS_CUDA(cudaMemcpyAsync(d_it, it.l, sizeof(it.l), cudaMemcpyHostToDevice, ctx->stream));
+  CS_LAUNCH(k_batch_inverse<FrP>, ceil_div(cnt, 128), 128, 0, ctx->stream, pre, suf, d_it, cnt, out);
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));  // `it` is a stack variable
+  return 0;
+}
+
+template <class Cfg>
+int r3_step_t(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HR;
+  constexpr int NW = FrP::N;
+  cs_ctx* ctx = s->ctx;
+  cs_plonk_pk* pk = s->pk;
+  cudaStream_t st = ctx->stream;
+  const uint32_t n = pk->n, n4 = 4 * n;
+  const size_t pl = point_limbs64(pk->curve, CS_G1);
+  const unsigned gb = ceil_div(n, 128);
+  uint32_t *addv = s->addv.as<uint32_t>(), *pubv = s->pubv.as<uint32_t>();
+  // public vectors: [0, n) 1/G | [n, 2n+1) 1/Q | then scratch
+  uint32_t *ginv = pubv, *qinv = pubv + (size_t)n * NW, *pscr = pubv + (size_t)(2 * n + 1) * NW;
+  switch (step) {
+    case CS_PLONK_R3_ROUND2_A: {  // in: beta, gamma
+      memcpy(s->K.beta, h_in, 32);
+      memcpy(s->K.gamma, h_in + HR::N, 32);
+      CS_LAUNCH(k_r3_round2_a<FrP>, gb, 128, 0, st, r3_round2_in<Cfg>(s), s->K, n, s->party, s->prf, s->ctr, r3_slot(s, 0),
+                r3_slot(s, 1), r3_peer(s, 0), r3_peer(s, 1));
+      s->ctr += 2 * (uint64_t)n;
+      break;
+    }
+    case CS_PLONK_R3_ROUND2_B: {
+      CS_LAUNCH(k_r3_round2_b<FrP>, gb, 128, 0, st, r3_round2_in<Cfg>(s), s->K, n, s->party, s->prf, s->ctr, r3_slot(s, 0),
+                r3_slot(s, 1), r3_slot(s, 2), r3_slot(s, 3), r3_peer(s, 2), r3_peer(s, 3));
+      s->ctr += 2 * (uint64_t)n;
+      break;
+    }
+    case CS_PLONK_R3_ROUND2_C: {  // out: g (n) | q (n + 1), additive
+      s->rbase = s->ctr;
+      s->ctr += 3 * (uint64_t)n + 2;
+      CS_LAUNCH(k_r3_round2_c<FrP>, ceil_div(n + 1, 128), 128, 0, st, r3_slot(s, 3), n, s->prf, s->rbase, s->ctr, addv,
+                addv + (size_t)n * NW);
+      s->ctr += 2 * (uint64_t)n + 1;
+      CS_CUDA(cudaMemcpyAsync(h_out, addv, (size_t)(2 * n + 1) * 32, cudaMemcpyDeviceToHost, st));
+      CS_CUDA(cudaStreamSynchronize(st));
+      return 0;
+    }
+    case CS_PLONK_R3_ROUND2_D: {  // in: opened G (n) | Q (n + 1)
+      uint32_t* opened = pscr + (size_t)(4 * n + 4) * NW;
+      CS_CUDA(cudaMemcpyAsync(opened, h_in, (size_t)(2 * n + 1) * 32, cudaMemcpyHostToDevice, st));
+      CS_TRY(r3_batch_inverse<Cfg>(s, opened, n, pscr, ginv));
+      CS_TRY(r3_batch_inverse<Cfg>(s, opened + (size_t)n * NW, n + 1, pscr, qinv));
+      CS_LAUNCH(k_r3_round2_d<FrP>, gb, 128, 0, st, r3_slot(s, 2), ginv, qinv, n, s->prf, s->rbase, s->ctr, r3_slot(s, 4),
+                r3_slot(s, 5), r3_peer(s, 4), r3_peer(s, 5));
+      s->ctr += 2 * (uint64_t)n;
+      break;
+    }
+    case CS_PLONK_R3_ROUND2_E: {
+      CS_LAUNCH(k_r3_round2_e<FrP>, gb, 128, 0, st, r3_slot(s, 4), n, s->prf, s->rbase, s->ctr, r3_slot(s, 6), r3_peer(s, 6));
+      s->ctr += n;
+      break;
+    }
+    case CS_PLONK_R3_ROUND2_F: {  // out: y (n), additive
+      CS_LAUNCH(k_r3_round2_f<FrP>, gb, 128, 0, st, r3_slot(s, 6), qinv, n, s->prf, s->rbase, s->ctr, addv);
+      s->ctr += n;
+      CS_CUDA(cudaMemcpyAsync(h_out, addv, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+      CS_CUDA(cudaStreamSynchronize(st));
+      return 0;
+    }
+    case CS_PLONK_R3_ROUND2_G: {  // in: opened Y (n); out: partial [z]
+      uint32_t* y = pscr;
+      CS_CUDA(cudaMemcpyAsync(y, h_in, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+      CS_TRY((scan<FrP, 0>(ctx, s, y, y, n, 0)));
+      uint32_t* ps = s->polysh[3].as<uint32_t>();
+      CS_LAUNCH(k_r3_round2_g<FrP>, gb, 128, 0, st, y, r3_slot(s, 5), n, ps);
+      CS_TRY(interpolate_and_extend<Cfg>(ctx, pk, ps, s->ev[3].as<uint32_t>(), 2));
+      HR bsh[6];
+      for (int i = 0; i < 3; i++) { memcpy(bsh[2 * i].l, s->B.b[6 + i].v[0], 32); memcpy(bsh[2 * i + 1].l, s->B.b[6 + i].v[1], 32); }
+      CS_TRY(blind<Cfg>(ctx, ps, n, bsh, 3, 2));
+      CS_LAUNCH(k_extract_component<FrP>, ceil_div(n + 3, 256), 256, 0, st, ps, n + 3, 2u, 0u, s->polyadd[3].as<uint32_t>());
+      Commit c[1] = {{s->polyadd[3].as<uint32_t>(), (size_t)n + 3, h_out}};
+      return commit_many<Cfg>(ctx, pk, c, 1);
+    }
+    case CS_PLONK_R3_ROUND3_A: {  // in: alpha
+      HR alpha;
+      memcpy(alpha.l, h_in, 32);
+      put(s->K.alpha, alpha);
+      put(s->K.alpha2, alpha.sqr());
+      uint64_t g4[HR::N], unused[HR::N];
+      CS_TRY(cs_groth16_roots_of_unity((cs_curve)pk->curve, 2, g4, unused));
+      HR w4, one = HR::one(), two = one + one, zero = HR::zero();
+      memcpy(w4.l, g4, sizeof(w4.l));
+      HR z1[4] = {zero, w4 - one, zero - two, zero - one - w4};
+      HR z2[4] = {zero, zero - two * w4, two + two, two * w4};
+      HR z3[4] = {zero, two + two * w4, zero - (two + two + two + two), two - two * w4};
+      for (int i = 0; i < 4; i++) { put(s->K.z1[i], z1[i]); put(s->K.z2[i], z2[i]); put(s->K.z3[i], z3[i]); }
+      R3QuotIn qi;
+      qi.a = s->ev[0].as<uint32_t>(); qi.b = s->ev[1].as<uint32_t>(); qi.c = s->ev[2].as<uint32_t>(); qi.z = s->ev[3].as<uint32_t>();
+      qi.tw4 = pk->dom4->tw_fwd.template as<uint32_t>();
+      CS_LAUNCH(k_r3_quot_l1<FrP>, ceil_div(n4, 64), 64, 0, st, qi, s->B, n, s->prf, s->ctr, s->arena.as<uint32_t>(), s->next_arena,
+                s->slot_words);
+      s->ctr += 12 * (uint64_t)n4;
+      break;
+    }
+    case CS_PLONK_R3_ROUND3_B: {  // out: partial [t1] [t2] [t3]
+      R3QuotIn qi;
+      qi.a = s->ev[0].as<uint32_t>(); qi.b = s->ev[1].as<uint32_t>(); qi.c = s->ev[2].as<uint32_t>(); qi.z = s->ev[3].as<uint32_t>();
+      qi.tw4 = pk->dom4->tw_fwd.template as<uint32_t>();
+      R3KeyEvals E;
+      E.qm = pk->q_evals[0].as<uint32_t>(); E.ql = pk->q_evals[1].as<uint32_t>(); E.qr = pk->q_evals[2].as<uint32_t>();
+      E.qo = pk->q_evals[3].as<uint32_t>(); E.qc = pk->q_evals[4].as<uint32_t>();
+      E.s1 = pk->s_evals[0].as<uint32_t>(); E.s2 = pk->s_evals[1].as<uint32_t>(); E.s3 = pk->s_evals[2].as<uint32_t>();
+      E.lagrange = pk->lagrange.as<uint32_t>(); E.buf_a = s->buf[0].as<uint32_t>();
+      uint32_t *t = s->t.as<uint32_t>(), *tz = s->tz.as<uint32_t>();
+      CS_LAUNCH(k_r3_quot_l2<FrP>, ceil_div(n4, 64), 64, 0, st, qi, s->B, E, n, pk->nlag, s->K, s->party, s->prf, s->ctr,
+                s->arena.as<uint32_t>(), s->slot_words, t, tz);
+      s->ctr += 2 * (uint64_t)n4;
+      CS_TRY(ntt_run(ctx, pk->dom4, t, 1, true, nullptr, st));
+      CS_TRY(ntt_run(ctx, pk->dom4, tz, 1, true, nullptr, st));
+      CS_LAUNCH(k_bit_reverse<FrP>, ceil_div(n4, 256), 256, 0, st, t, pk->log_n + 2, 1u);
+      CS_LAUNCH(k_bit_reverse<FrP>, ceil_div(n4, 256), 256, 0, st, tz, pk->log_n + 2, 1u);
+      uint32_t *t1 = s->t1.as<uint32_t>(), *t2 = s->t2.as<uint32_t>(), *t3 = s->t3.as<uint32_t>();
+      CS_LAUNCH(k_plonk_tsplit<FrP>, gb, 128, 0, st, t, tz, n, s->K, t1, t2, t3);
+      Commit c[3] = {{t1, (size_t)n + 1, h_out}, {t2, (size_t)n + 1, h_out + pl}, {t3, (size_t)n + 6, h_out + 2 * pl}};
+      return commit_many<Cfg>(ctx, pk, c, 3);
+    }
+    case CS_PLONK_R3_ROUND4: {  // in: xi; out: partial eval_a eval_b eval_c eval_zw, then public eval_s1 eval_s2
+      HR xi, w_n;
+      memcpy(xi.l, h_in, 32);
+      memcpy(w_n.l, pk->dom->group_gen.data(), sizeof(w_n.l));
+      HR xiw = xi * w_n;
+      for (int k = 0; k < 3; k++)
+        CS_TRY((eval_poly_t<Cfg>(ctx, s->polyadd[k].as<uint64_t>(), (size_t)n + 2, 1, xi.l, h_out + (size_t)k * HR::N)));
+      CS_TRY((eval_poly_t<Cfg>(ctx, s->polyadd[3].as<uint64_t>(), (size_t)n + 3, 1, xiw.l, h_out + 3 * HR::N)));
+      CS_TRY((eval_poly_t<Cfg>(ctx, pk->s_coeffs[0].as<uint64_t>(), (size_t)n, 1, xi.l, h_out + 4 * HR::N)));
+      CS_TRY((eval_poly_t<Cfg>(ctx, pk->s_coeffs[1].as<uint64_t>(), (size_t)n, 1, xi.l, h_out + 5 * HR::N)));
+      return 0;
+    }
+    case CS_PLONK_R3_ROUND5: {  // in: xi, v0, eval_a eval_b eval_c eval_s1 eval_s2 eval_zw (opened); out: partial [Wxi] [Wxiw]
+      HR in[8];
+      memcpy(in, h_in, sizeof(in));
+      const HR xi = in[0], ea = in[2], eb = in[3], ec = in[4], es1 = in[5], es2 = in[6], ezw = in[7];
+      HR v[5], beta, gamma, alpha, alpha2, k1, k2, w_n;
+      v[0] = in[1];
+      for (int i = 1; i < 5; i++) v[i] = v[i - 1] * v[0];
+      memcpy(beta.l, s->K.beta, 32); memcpy(gamma.l, s->K.gamma, 32); memcpy(alpha.l, s->K.alpha, 32); memcpy(alpha2.l, s->K.alpha2, 32);
+      memcpy(k1.l, s->K.k1, 32); memcpy(k2.l, s->K.k2, 32);
+      memcpy(w_n.l, pk->dom->group_gen.data(), sizeof(w_n.l));
+      const HR xiw = xi * w_n;
+      HR xin = xi;
+      for (unsigned q = 0; q < pk->log_n; q++) xin = xin.sqr();
+      const HR zh = xin - HR::one(), nn = HR::from_u64(n);
+      std::vector<HR> ls(pk->nlag);
+      HR wi = HR::one();
+      for (uint32_t i = 0; i < pk->nlag; i++) {
+        HR dnm = nn * (xi - wi);
+        if (dnm.is_zero()) return fail(CS_ERR_ARG, "plonk: xi hit the evaluation domain");
+        ls[i] = wi * zh * dnm.inverse();
+        wi = wi * w_n;
+      }
+      HR eval_pi = HR::zero();
+      for (uint32_t i = 0; i < pk->n_public && i < pk->nlag; i++) {
+        HR val;
+        memcpy(val.l, s->pub.data() + (size_t)i * HR::N, sizeof(val.l));
+        eval_pi = eval_pi - ls[i] * val;
+      }
+      const HR betaxi = beta * xi;
+      const HR e2 = (ea + betaxi + gamma) * (eb + betaxi * k1 + gamma) * (ec + betaxi * k2 + gamma) * alpha;
+      const HR e3 = (ea + beta * es1 + gamma) * (eb + beta * es2 + gamma) * ezw * alpha;
+      const HR e4 = alpha2 * ls[0];
+      const HR r0 = eval_pi - e3 * (ec + gamma) - e4;
+      PlonkLinW W;
+      memset(&W, 0, sizeof(W));
+      put(W.ab, ea * eb); put(W.ea, ea); put(W.eb, eb); put(W.ec, ec); put(W.e3beta, e3 * beta); put(W.e24, e2 + e4);
+      put(W.zh, zh); put(W.xin, xin); put(W.xin2, xin.sqr());
+      for (int i = 0; i < 5; i++) put(W.v[i], v[i]);
+      put(W.c0, r0 - v[0] * ea - v[1] * eb - v[2] * ec - v[3] * es1 - v[4] * es2);
+      PlonkLinIn li;
+      li.qm = pk->q_coeffs[0].as<uint32_t>(); li.ql = pk->q_coeffs[1].as<uint32_t>(); li.qr = pk->q_coeffs[2].as<uint32_t>();
+      li.qo = pk->q_coeffs[3].as<uint32_t>(); li.qc = pk->q_coeffs[4].as<uint32_t>();
+      li.s1 = pk->s_coeffs[0].as<uint32_t>(); li.s2 = pk->s_coeffs[1].as<uint32_t>(); li.s3 = pk->s_coeffs[2].as<uint32_t>();
+      li.pa = s->polyadd[0].as<uint32_t>(); li.pb = s->polyadd[1].as<uint32_t>(); li.pc = s->polyadd[2].as<uint32_t>();
+      li.pz = s->polyadd[3].as<uint32_t>(); li.t1 = s->t1.as<uint32_t>(); li.t2 = s->t2.as<uint32_t>(); li.t3 = s->t3.as<uint32_t>();
+      const int pub = s->party == 0;  // public polynomials and constants enter once (add_with_public on x_0)
+      uint32_t *wxi = s->tmp0.as<uint32_t>(), *wxiw = s->tmp1.as<uint32_t>();
+      CS_LAUNCH(k_plonk_wxi_numerator<FrP>, ceil_div(n + 6, 128), 128, 0, st, li, W, n, pub, wxi);
+      CS_TRY(divide_by_linear<Cfg>(ctx, s, wxi, n + 6, xi, (const HR*)nullptr));
+      CS_CUDA(cudaMemcpyAsync(wxiw, s->polyadd[3].as<uint32_t>(), (size_t)(n + 3) * 32, cudaMemcpyDeviceToDevice, st));
+      CS_TRY(divide_by_linear<Cfg>(ctx, s, wxiw, n + 3, xiw, pub ? &ezw : (const HR*)nullptr));
+      Commit c[2] = {{wxi, (size_t)n + 5, h_out}, {wxiw, (size_t)n + 2, h_out + pl}};
+      return commit_many<Cfg>(ctx, pk, c, 2);
+    }
+    default:
+      return fail(CS_ERR_ARG, "cs_plonk_rep3_step: unknown step %d", step);
+  }
+  CS_CUDA(cudaGetLastError());
   return 0;
 }
 
@@ -554,5 +890,86 @@ int cs_plonk_prove_plain(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_public_
     default: return fail(CS_ERR_ARG, "unsupported curve id %d", pk->curve);
   }
 }
+
+
+int cs_plonk_rep3_create(cs_ctx* ctx, cs_plonk_pk* pk, int party, cs_plonk_rep3** out) {
+  if (!ctx || !pk || !out) return fail(CS_ERR_ARG, "cs_plonk_rep3_create: NULL argument");
+  if (party < 0 || party > 2) return fail(CS_ERR_ARG, "cs_plonk_rep3_create: party id %d", party);
+  CS_CUDA(cudaSetDevice(ctx->device));
+  std::unique_ptr<cs_plonk_rep3> s(new cs_plonk_rep3());
+  s->ctx = ctx; s->pk = pk; s->party = party;
+  memset(&s->prf, 0, sizeof(s->prf));
+  int rc = pk->curve == CS_BN254 ? r3_create_t<Bn254Cfg>(s.get())
+#if defined(CS_ENABLE_BLS12_381)
+           : pk->curve == CS_BLS12_381 ? r3_create_t<Bls381Cfg>(s.get())
+#endif
+           : fail(CS_ERR_ARG, "unsupported curve id %d", pk->curve);
+  if (rc) { cs_plonk_rep3_free(s.release()); return rc; }
+  *out = s.release();
+  return 0;
+}
+
+void cs_plonk_rep3_free(cs_plonk_rep3* s) {
+  if (!s) return;
+  DevBuf* all[] = {&s->w, &s->arena, &s->addv, &s->pubv, &s->t, &s->tz, &s->t1, &s->t2, &s->t3, &s->tmp0, &s->tmp1, &s->totals, &s->small};
+  for (DevBuf* b : all) b->release();
+  for (int i = 0; i < 3; i++) s->buf[i].release();
+  for (int i = 0; i < 4; i++) { s->polysh[i].release(); s->ev[i].release(); s->polyadd[i].release(); }
+  delete s;
+}
+
+int cs_plonk_rep3_arena(cs_plonk_rep3* s, void** d_arena, size_t* slot_bytes, unsigned* n_slots) {
+  if (!s || !d_arena || !slot_bytes || !n_slots) return fail(CS_ERR_ARG, "cs_plonk_rep3_arena: NULL argument");
+  *d_arena = s->arena.p;
+  *slot_bytes = s->slot_words * 4;
+  *n_slots = R3_SLOTS;
+  return 0;
+}
+
+int cs_plonk_rep3_connect(cs_plonk_rep3* s, void* d_next_arena) {
+  if (!s) return fail(CS_ERR_ARG, "cs_plonk_rep3_connect: NULL argument");
+  s->next_arena = reinterpret_cast<uint32_t*>(d_next_arena);
+  return 0;
+}
+
+int cs_plonk_rep3_round1(cs_plonk_rep3* s, const cs_rep3_prf* prf, const uint64_t* h_public_inputs, size_t n_public_inputs,
+                         const uint64_t* h_witness_shares, size_t n_witness, const uint64_t* h_blinder_shares,
+                         uint64_t* out_points) {
+  if (!s || !prf || !h_public_inputs || !h_blinder_shares || !out_points || (n_witness && !h_witness_shares))
+    return fail(CS_ERR_ARG, "cs_plonk_rep3_round1: NULL argument");
+  const cs_plonk_pk* pk = s->pk;
+  if (n_public_inputs != (size_t)pk->n_public + 1)
+    return fail(CS_ERR_ARG, "cs_plonk_rep3_round1: %zu public inputs, the key expects %u", n_public_inputs, pk->n_public + 1);
+  if (n_witness != (size_t)pk->n_vars - pk->n_additions - pk->n_public - 1)
+    return fail(CS_ERR_ARG, "cs_plonk_rep3_round1: %zu witness shares, the key expects %u", n_witness,
+                pk->n_vars - pk->n_additions - pk->n_public - 1);
+  if (prf->rounds == 0 || (prf->rounds & 1) || prf->rounds > 20) return fail(CS_ERR_ARG, "cs_plonk_rep3_round1: bad ChaCha round count");
+  CS_CUDA(cudaSetDevice(s->ctx->device));
+  memcpy(s->prf.keys.k, prf->seed1, 32);
+  memcpy(s->prf.keys.k + 8, prf->seed2, 32);
+  s->prf.pos1 = prf->word_pos1; s->prf.pos2 = prf->word_pos2; s->prf.rounds = prf->rounds;
+  s->ctr = 0;
+  switch (pk->curve) {
+    case CS_BN254: return r3_round1_t<Bn254Cfg>(s, h_public_inputs, h_witness_shares, h_blinder_shares, out_points);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: return r3_round1_t<Bls381Cfg>(s, h_public_inputs, h_witness_shares, h_blinder_shares, out_points);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve id %d", pk->curve);
+  }
+}
+
+int cs_plonk_rep3_step(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out) {
+  if (!s) return fail(CS_ERR_ARG, "cs_plonk_rep3_step: NULL session");
+  CS_CUDA(cudaSetDevice(s->ctx->device));
+  switch (s->pk->curve) {
+    case CS_BN254: return r3_step_t<Bn254Cfg>(s, step, h_in, h_out);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: return r3_step_t<Bls381Cfg>(s, step, h_in, h_out);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve id %d", s->pk->curve);
+  }
+}
+
+uint64_t cs_plonk_rep3_prf_words(const cs_plonk_rep3* s) { return s ? 8 * s->ctr : 0; }
 
 }  // extern "C"

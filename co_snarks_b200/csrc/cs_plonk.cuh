@@ -28,39 +28,56 @@ CS_D Fp<FrP> table_pow(const uint32_t* __restrict__ pw, uint64_t e) {
 }
 
 // additions of one dependency level (round1.rs:191-224): w[first_add + k] = w[s1] f1 + w[s2] f2
+// `batch` components per signal (1 plain, 2 Rep3 share {a, b}: mul_with_public / add act per component)
 template <class FrP>
 CS_GLOBAL void k_plonk_additions(const uint32_t* __restrict__ order, uint32_t lo, uint32_t hi,
                                  const uint32_t* __restrict__ ids, const uint32_t* __restrict__ factors,
-                                 uint32_t first_add, uint32_t* __restrict__ w) {
+                                 uint32_t first_add, uint32_t batch, uint32_t* __restrict__ w) {
   uint32_t t = lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= hi) return;
   uint32_t k = order[t];
-  Fp<FrP> a = ld_fr<FrP>(w + (size_t)ids[2 * k] * FrP::N) * ld_fr<FrP>(factors + (size_t)(2 * k) * FrP::N);
-  Fp<FrP> b = ld_fr<FrP>(w + (size_t)ids[2 * k + 1] * FrP::N) * ld_fr<FrP>(factors + (size_t)(2 * k + 1) * FrP::N);
-  st_fr<FrP>(w + (size_t)(first_add + k) * FrP::N, a + b);
+  Fp<FrP> f1 = ld_fr<FrP>(factors + (size_t)(2 * k) * FrP::N), f2 = ld_fr<FrP>(factors + (size_t)(2 * k + 1) * FrP::N);
+  for (uint32_t c = 0; c < batch; c++) {
+    Fp<FrP> a = ld_fr<FrP>(w + ((size_t)ids[2 * k] * batch + c) * FrP::N) * f1;
+    Fp<FrP> b = ld_fr<FrP>(w + ((size_t)ids[2 * k + 1] * batch + c) * FrP::N) * f2;
+    st_fr<FrP>(w + ((size_t)(first_add + k) * batch + c) * FrP::N, a + b);
+  }
 }
 
 // buffer[i] = w[map[i]] for i < nc, 0 up to n (round1.rs:118-124)
 template <class FrP>
-CS_GLOBAL void k_plonk_gather(const uint32_t* __restrict__ map, uint32_t nc, uint32_t n,
+CS_GLOBAL void k_plonk_gather(const uint32_t* __restrict__ map, uint32_t nc, uint32_t n, uint32_t batch,
                                const uint32_t* __restrict__ w, uint32_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Fp<FrP> v = Fp<FrP>::zero();
-  if (i < nc) v = ld_fr<FrP>(w + (size_t)map[i] * FrP::N);
-  st_fr<FrP>(out + (size_t)i * FrP::N, v);
+  for (uint32_t c = 0; c < batch; c++) {
+    Fp<FrP> v = Fp<FrP>::zero();
+    if (i < nc) v = ld_fr<FrP>(w + ((size_t)map[i] * batch + c) * FrP::N);
+    st_fr<FrP>(out + ((size_t)i * batch + c) * FrP::N, v);
+  }
 }
 
-struct PlonkBlind { uint32_t v[3][8]; };
-// blind_coefficients (lib.rs:163-178): poly[i] -= rev[i], poly[n + i] = rev[i]   (count <= 3, one thread each)
+struct PlonkBlind { uint32_t v[6][8]; };  // count (<= 3) coefficients x batch (<= 2) components
+// blind_coefficients (lib.rs:163-178): poly[i] -= rev[i], poly[n + i] = rev[i]   (one thread per element)
 template <class FrP>
-CS_GLOBAL void k_plonk_blind(uint32_t* __restrict__ poly, uint32_t n, PlonkBlind rev, uint32_t count) {
-  uint32_t i = threadIdx.x;
-  if (i >= count) return;
+CS_GLOBAL void k_plonk_blind(uint32_t* __restrict__ poly, uint32_t n, uint32_t batch, PlonkBlind rev, uint32_t count) {
+  uint32_t t = threadIdx.x;
+  if (t >= count * batch) return;
+  uint32_t i = t / batch, cix = t - i * batch;
   Fp<FrP> c;
-  for (int l = 0; l < FrP::N; l++) c.l[l] = rev.v[i][l];
-  st_fr<FrP>(poly + (size_t)i * FrP::N, ld_fr<FrP>(poly + (size_t)i * FrP::N) - c);
-  st_fr<FrP>(poly + (size_t)(n + i) * FrP::N, c);
+  for (int l = 0; l < FrP::N; l++) c.l[l] = rev.v[t][l];
+  uint32_t* lo = poly + ((size_t)i * batch + cix) * FrP::N;
+  st_fr<FrP>(lo, ld_fr<FrP>(lo) - c);
+  st_fr<FrP>(poly + ((size_t)(n + i) * batch + cix) * FrP::N, c);
+}
+
+// component `comp` of an interleaved share vector as a contiguous vector (the additive share a party works on)
+template <class FrP>
+CS_GLOBAL void k_extract_component(const uint32_t* __restrict__ in, uint32_t n, uint32_t batch, uint32_t comp,
+                                   uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  st_fr<FrP>(out + (size_t)i * FrP::N, ld_fr<FrP>(in + ((size_t)i * batch + comp) * FrP::N));
 }
 
 // Challenges, blinders and the small constants of rounds 2-3, by value (Montgomery limbs)
@@ -318,13 +335,14 @@ struct PlonkLinW {
   uint32_t ab[8], ea[8], eb[8], ec[8], e3beta[8], e24[8], zh[8], xin[8], xin2[8], v[5][8], c0[8];
 };
 template <class FrP>
-CS_GLOBAL void k_plonk_wxi_numerator(PlonkLinIn in, PlonkLinW W, uint32_t n, uint32_t* __restrict__ out) {
+CS_GLOBAL void k_plonk_wxi_numerator(PlonkLinIn in, PlonkLinW W, uint32_t n, int pub, uint32_t* __restrict__ out) {
+  // pub = 0: this party holds additive shares only and contributes no public polynomial / constant terms
   typedef Fp<FrP> F;
   constexpr int NW = FrP::N;
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n + 6) return;
   F acc = F::zero();
-  if (i < n) {
+  if (i < n && pub) {
     acc = ld_fr<FrP>(in.qm + (size_t)i * NW) * cload<FrP>(W.ab) + ld_fr<FrP>(in.ql + (size_t)i * NW) * cload<FrP>(W.ea) +
           ld_fr<FrP>(in.qr + (size_t)i * NW) * cload<FrP>(W.eb) + ld_fr<FrP>(in.qo + (size_t)i * NW) * cload<FrP>(W.ec) +
           ld_fr<FrP>(in.qc + (size_t)i * NW) - ld_fr<FrP>(in.s3 + (size_t)i * NW) * cload<FrP>(W.e3beta) +
@@ -337,7 +355,7 @@ CS_GLOBAL void k_plonk_wxi_numerator(PlonkLinIn in, PlonkLinW W, uint32_t n, uin
   if (i < n + 2)
     acc = acc + ld_fr<FrP>(in.pa + (size_t)i * NW) * cload<FrP>(W.v[0]) + ld_fr<FrP>(in.pb + (size_t)i * NW) * cload<FrP>(W.v[1]) +
           ld_fr<FrP>(in.pc + (size_t)i * NW) * cload<FrP>(W.v[2]);
-  if (i == 0) acc = acc + cload<FrP>(W.c0);
+  if (i == 0 && pub) acc = acc + cload<FrP>(W.c0);
   st_fr<FrP>(out + (size_t)i * NW, acc);
 }
 

@@ -218,6 +218,15 @@ class Rep3State:
         self.rng1 = _ChaChaStream(own.tobytes())
         self.rng2 = _ChaChaStream(np.ascontiguousarray(prev).tobytes())
 
+    @classmethod
+    def from_seeds(cls, party, own_seed32, prev_seed32):
+        """State from already-agreed seeds (three parties in one process: tests, single-GPU runs)."""
+        st = cls.__new__(cls)
+        st.id = party
+        st.rng1 = _ChaChaStream(bytes(own_seed32))
+        st.rng2 = _ChaChaStream(bytes(prev_seed32))
+        return st
+
     def prf_args(self):
         return (self.rng1.seed, self.rng1.pos, self.rng2.seed, self.rng2.pos, 12)
 

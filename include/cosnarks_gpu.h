@@ -334,6 +334,39 @@ void cs_plonk_pk_free(cs_plonk_pk* pk);
 int cs_plonk_prove_plain(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_public_inputs, size_t n_public_inputs,
                          const uint64_t* h_witness, size_t n_witness, const uint64_t* h_blinders_mont,
                          uint64_t* out_points, uint64_t* out_evals);
+/* ---- Rep3 co-Plonk (Rep3CoPlonk::prove, co-plonk/src/lib.rs:222-240; driver traits co-plonk/src/mpc.rs:16-185,
+ * Rep3 implementation mpc/rep3.rs) -- one session per party, stepped by the host protocol driver
+ * (co_snarks_b200/plonk.py), which opens what each step returns and hashes the transcript.
+ * Shares are interleaved {a, b} (4 limbs each).  Products that must become replicated shares again are written
+ * into this party's arena slot (.a) and the NEXT party's (.b): pass the next party's arena (cs_ipc_open'ed or a
+ * same-process pointer) to cs_plonk_rep3_connect, or NULL to move the a-halves yourself (cs_rep3_set_b).
+ * Slots written per step: ROUND2_A {0,1}, ROUND2_B {2,3}, ROUND2_D {4,5}, ROUND2_E {6}: n shares each;
+ * ROUND3_A {0..11}: 4n shares each.  All parties must finish a step before any starts the next one.
+ * Step inputs / outputs (host, Montgomery):
+ *   ROUND2_A in beta, gamma                    ROUND2_B -
+ *   ROUND2_C out g (n) | q (n+1) additive      ROUND2_D in the opened sums G | Q
+ *   ROUND2_E -                                 ROUND2_F out y (n) additive
+ *   ROUND2_G in the opened Y; out partial [z]  ROUND3_A in alpha
+ *   ROUND3_B out partial [t1] [t2] [t3]        ROUND4 in xi; out partial eval a b c zw, then public eval s1 s2
+ *   ROUND5 in xi, v, eval_a eval_b eval_c eval_s1 eval_s2 eval_zw (opened); out partial [Wxi] [Wxiw]
+ * "partial" = this party's additive share of the point / scalar: the sum over the parties is the proof element
+ * (open_point_g1 / open_vec, mpc/rep3.rs:113-138).  round1 takes the party's correlated ChaCha streams
+ * (masks and the random shares of round 2 are drawn on the device); cs_plonk_rep3_prf_words = words consumed. */
+typedef struct cs_plonk_rep3 cs_plonk_rep3;
+enum {
+  CS_PLONK_R3_ROUND2_A = 1, CS_PLONK_R3_ROUND2_B, CS_PLONK_R3_ROUND2_C, CS_PLONK_R3_ROUND2_D, CS_PLONK_R3_ROUND2_E,
+  CS_PLONK_R3_ROUND2_F, CS_PLONK_R3_ROUND2_G, CS_PLONK_R3_ROUND3_A, CS_PLONK_R3_ROUND3_B, CS_PLONK_R3_ROUND4,
+  CS_PLONK_R3_ROUND5
+};
+int cs_plonk_rep3_create(cs_ctx* ctx, cs_plonk_pk* pk, int party, cs_plonk_rep3** out);
+void cs_plonk_rep3_free(cs_plonk_rep3* s);
+int cs_plonk_rep3_arena(cs_plonk_rep3* s, void** d_arena, size_t* slot_bytes, unsigned* n_slots);
+int cs_plonk_rep3_connect(cs_plonk_rep3* s, void* d_next_arena);
+int cs_plonk_rep3_round1(cs_plonk_rep3* s, const cs_rep3_prf* prf, const uint64_t* h_public_inputs, size_t n_public_inputs,
+                         const uint64_t* h_witness_shares, size_t n_witness, const uint64_t* h_blinder_shares,
+                         uint64_t* out_points);
+int cs_plonk_rep3_step(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out);
+uint64_t cs_plonk_rep3_prf_words(const cs_plonk_rep3* s);
 /* sha3::Keccak256 of a host buffer (the transcript hash, types.rs:13-14); test hook. */
 int cs_keccak256(const uint8_t* data, size_t len, uint8_t* out32);
 

@@ -552,6 +552,53 @@ def check_plonk_synthetic(ctx, log_n, n_public=2, against_oracle=True, seed=5):
     pk.free()
 
 
+def _plonk_rep3_in_process(ctx, cv, pk, z_n, vk_points, pub, w_private, blinders, seed=23):
+    """Three Rep3 co-Plonk parties in one process (LocalRep3Comm) on shares of `w_private` and of `blinders`."""
+    from co_snarks_b200.plonk import LocalRep3Comm, Rep3CoPlonk
+    from co_snarks_b200.rep3 import Rep3State
+    rng = random.Random(seed)
+    r = cv.r
+
+    def share(vals):
+        out = [[], [], []]
+        for v in vals:
+            s0, s1 = rng.randrange(r), rng.randrange(r)
+            sh = [s0, s1, (v - s0 - s1) % r]
+            for p in range(3):
+                out[p] += [sh[p], sh[(p + 2) % 3]]  # party p holds (x_p, x_{p-1})  rep3.rs:281-293
+        return [cv.fr(o).reshape(-1, 2, 4) for o in out]
+    wsh = share(w_private)
+    bsh = share(blinders)
+    seeds = [bytes((31 * p + i) & 0xff for i in range(32)) for p in range(3)]
+    provers = [Rep3CoPlonk(ctx, pk, p) for p in range(3)]
+    states = [Rep3State.from_seeds(p, seeds[p], seeds[(p + 2) % 3]) for p in range(3)]
+    comm = LocalRep3Comm(provers)
+    res = comm.run([provers[p].prove(states[p], pub, wsh[p], vk_points, z_n, bsh[p]) for p in range(3)])
+    for p in provers:
+        p.free()
+    # consistent PRF consumption (party p's stream 1 is party p+1's stream 2)
+    assert all(states[p].rng1.pos == states[(p + 1) % 3].rng2.pos for p in range(3))
+    return res
+
+
+def check_plonk_rep3(ctx, name="multiplier2"):
+    """Rep3CoPlonk::prove (co-plonk/src/lib.rs:222-240) with three parties: every party opens the same proof, and
+    it equals the plain prover's (= the oracle's, = the reference's known answers for b = [0..11)) because the
+    blinder shares sum to b and all masks cancel."""
+    from helpers import golden_plonk, make_plonk_key, plonk_proof_from_device
+    from oracle.formats import plonk_proof_to_json
+    cv = Conv("bn254")
+    z, w, g = golden_plonk(name)
+    npub = z["n_public"]
+    pk = make_plonk_key(ctx, cv, z)
+    vkp = cv.g1([z["vk_" + k] for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")])
+    res = _plonk_rep3_in_process(ctx, cv, pk, z["domain_size"], vkp, cv.fr(w[:npub + 1]), w[npub + 1:], list(range(11)))
+    proofs = [plonk_proof_from_device(cv, pts, evs) for pts, evs in res]
+    assert proofs[0] == proofs[1] == proofs[2]
+    assert plonk_proof_to_json(proofs[0]) == g["oracle_proof_json"]
+    pk.free()
+
+
 def check_shamir_degree_reduce(ctx, n=64, seed=12):
     """Shamir king-based degree reduction (shamir/network.rs:150-243) assembled from cs_vec_lincomb, for
     n = 3 parties, t = 1: every party masks its degree-2t product share with r_2t, the king interpolates

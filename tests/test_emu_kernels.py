@@ -111,3 +111,7 @@ def test_plonk_prove_poseidon(emu_ctx):
 def test_plonk_synthetic_key(emu_ctx):
     K.check_plonk_synthetic(emu_ctx, 6, n_public=2)
     K.check_plonk_synthetic(emu_ctx, 5, n_public=0)
+
+
+def test_plonk_rep3_multiplier2(emu_ctx):
+    K.check_plonk_rep3(emu_ctx, "multiplier2")
