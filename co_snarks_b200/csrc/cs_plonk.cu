@@ -530,7 +530,7 @@ int r3_create_t(cs_plonk_rep3* s) {
   CS_TRY(s->arena.reserve((size_t)R3_SLOTS * s->slot_words * 4));
   CS_CUDA(cudaMemsetAsync(s->arena.p, 0, (size_t)R3_SLOTS * s->slot_words * 4, s->ctx->stream));
   CS_TRY(s->addv.reserve((2 * n + 2) * 32));
-  CS_TRY(s->pubv.reserve((6 * n + 8) * 32));
+  CS_TRY(s->pubv.reserve((8 * n + 16) * 32));  // 1/G | 1/Q | scan scratch (2n + 2) | opened vectors (2n + 1)
   CS_TRY(s->t.reserve(4 * n * 32));
   CS_TRY(s->tz.reserve(4 * n * 32));
   CS_TRY(s->t1.reserve((n + 8) * 32));
@@ -538,7 +538,7 @@ int r3_create_t(cs_plonk_rep3* s) {
   CS_TRY(s->t3.reserve((n + 8) * 32));
   CS_TRY(s->tmp0.reserve((n + 8) * 32));
   CS_TRY(s->tmp1.reserve((n + 8) * 32));
-  CS_TRY(s->small.reserve(4096));
+  CS_TRY(s->small.reserve(8192));
   CS_CUDA(cudaStreamSynchronize(s->ctx->stream));
   return 0;
 }

@@ -599,6 +599,27 @@ def check_plonk_rep3(ctx, name="multiplier2"):
     pk.free()
 
 
+def check_plonk_rep3_synthetic(ctx, log_n=5, n_public=2, seed=29):
+    """Rep3 co-Plonk on the synthetic circuit (additions, empty rows) with random blinder shares: the opened proof
+    equals the oracle's plain proof for the summed blinders and is accepted by the verifier."""
+    from helpers import plonk_proof_from_device
+    from oracle import plonk as OP
+    from oracle.pairing_bn254 import pairing_product_is_one
+    from workloads.synth_plonk import SynthPlonk
+    cv = Conv("bn254")
+    syn = SynthPlonk(ctx, log_n, n_public=n_public)
+    pk = syn.make_key()
+    rng = random.Random(seed)
+    bl = [rng.randrange(cv.r) for _ in range(11)]
+    res = _plonk_rep3_in_process(ctx, cv, pk, syn.n, syn.key["vk_points"], syn.public_inputs,
+                                 syn.full_witness[n_public + 1:], bl)
+    proofs = [plonk_proof_from_device(cv, pts, evs) for pts, evs in res]
+    assert proofs[0] == proofs[1] == proofs[2]
+    assert proofs[0] == OP.prove(syn.oracle_zkey(), syn.full_witness, bl)
+    assert OP.verify(BN254, syn.vk_ints(), proofs[0], syn.full_witness[1:n_public + 1], pairing_product_is_one)
+    pk.free()
+
+
 def check_shamir_degree_reduce(ctx, n=64, seed=12):
     """Shamir king-based degree reduction (shamir/network.rs:150-243) assembled from cs_vec_lincomb, for
     n = 3 parties, t = 1: every party masks its degree-2t product share with r_2t, the king interpolates

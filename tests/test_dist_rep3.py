@@ -243,3 +243,87 @@ def _run_mul_vec(fused):
     for i in range(3):
         assert sh[i][1::2] == sh[(i + 2) % 3][0::2]
     assert [(sh[0][2 * k] + sh[1][2 * k] + sh[2][2 * k]) % r for k in range(len(xs))] == [x * y % r for x, y in zip(xs, ys)]
+
+
+def _party_plonk(rank, port, emu_path, q, peer):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from co_snarks_b200 import binding as B
+    from co_snarks_b200.plonk import DistRep3Comm, Rep3CoPlonk
+    from co_snarks_b200.rep3 import Rep3Network, Rep3State
+    from helpers import Conv, golden_plonk, make_plonk_key, plonk_proof_from_device
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=3)
+    try:
+        if peer:
+            import torch
+            ctx = B.Context(rank % torch.cuda.device_count())
+        else:
+            ctx = B.Context(0, lib_path=emu_path)
+        cv = Conv("bn254")
+        z, w, g = golden_plonk("multiplier2")
+        npub = z["n_public"]
+        pk = make_plonk_key(ctx, cv, z)
+        rng = random.Random(41)  # same seed everywhere -> consistent sharings
+
+        def mine(vals):
+            out = []
+            for v in vals:
+                s0, s1 = rng.randrange(cv.r), rng.randrange(cv.r)
+                sh = [s0, s1, (v - s0 - s1) % cv.r]
+                out += [sh[rank], sh[(rank + 2) % 3]]
+            return cv.fr(out).reshape(-1, 2, 4)
+        wsh = mine(w[npub + 1:])
+        bsh = mine(list(range(11)))  # the reference's deterministic blinders, secret-shared
+        net = Rep3Network()
+        state = Rep3State(net, seed=3000 + rank)
+        prover = Rep3CoPlonk(ctx, pk, rank)
+        comm = DistRep3Comm(prover, net, peer=peer)
+        vkp = cv.g1([z["vk_" + k] for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")])
+        pts, evs = comm.run(prover.prove(state, cv.fr(w[:npub + 1]), wsh, vkp, z["domain_size"], bsh))
+        comm.close()
+        q.put((rank, plonk_proof_from_device(cv, pts, evs), net.bytes_sent))
+        prover.free()
+        pk.free()
+        ctx.close()
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _run_plonk(peer):
+    import torch.multiprocessing as mp
+    emu = None
+    if not peer:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+        import build_emu
+        emu = build_emu.build()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_party_plonk, args=(r, port, emu, q, peer)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=600) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import golden_plonk
+    from oracle.formats import plonk_proof_to_json
+    _, _, g = golden_plonk("multiplier2")
+    assert res[0][1] == res[1][1] == res[2][1], "parties disagree on the proof"
+    # shared deterministic blinders -> the reference's known answers (co-plonk/src/round{1..5}.rs tests)
+    assert plonk_proof_to_json(res[0][1]) == g["oracle_proof_json"]
+
+
+def test_co_plonk_rep3_three_processes_gloo():
+    """Rep3CoPlonk::prove across three processes (tests/tests/circom/e2e_tests/rep3.rs:36-137 for Plonk): the
+    products travel through the network (staged reshare), every party opens the reference's known-answer proof."""
+    _run_plonk(peer=False)
+
+
+@pytest.mark.gpu
+def test_co_plonk_rep3_peer_memory():
+    """The same with one process per party on real GPUs and the arena of the next party mapped through CUDA IPC."""
+    _run_plonk(peer=True)

@@ -115,3 +115,8 @@ def test_plonk_synthetic_key(emu_ctx):
 
 def test_plonk_rep3_multiplier2(emu_ctx):
     K.check_plonk_rep3(emu_ctx, "multiplier2")
+
+
+def test_plonk_rep3_synthetic(emu_ctx):
+    K.check_plonk_rep3_synthetic(emu_ctx, 5, n_public=2)
+    K.check_plonk_rep3_synthetic(emu_ctx, 4, n_public=0)

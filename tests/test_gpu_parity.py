@@ -125,3 +125,15 @@ def test_plonk_prove_multiplier2(gpu_ctx):
 
 def test_plonk_prove_poseidon(gpu_ctx):
     K.check_plonk_prove(gpu_ctx, "poseidon")
+
+
+def test_plonk_rep3_multiplier2(gpu_ctx):
+    K.check_plonk_rep3(gpu_ctx, "multiplier2")
+
+
+def test_plonk_rep3_poseidon(gpu_ctx):
+    K.check_plonk_rep3(gpu_ctx, "poseidon")
+
+
+def test_plonk_rep3_synthetic(gpu_ctx):
+    K.check_plonk_rep3_synthetic(gpu_ctx, 9, n_public=3)
