@@ -527,6 +527,38 @@ def check_plonk_prove(ctx, name="multiplier2", random_blinders=True):
     pk.free()
 
 
+def check_plonk_key_errors(ctx):
+    """PlonkProofError behaviour at the boundary (co-plonk/src/lib.rs:40-69, types.rs:79-84): invalid domain size,
+    SRS too short for the blinded polynomials, wire maps / additions that index past the witness."""
+    import copy
+    from helpers import golden_plonk, make_plonk_key
+    cv = Conv("bn254")
+    z, w, g = golden_plonk("multiplier2")
+
+    def expect(mut, text):
+        z2 = copy.deepcopy({k: v for k, v in z.items() if k != "curve"})
+        z2["curve"] = z["curve"]
+        mut(z2)
+        with pytest.raises(RuntimeError) as e:
+            make_plonk_key(ctx, cv, z2).free()
+        assert text in str(e.value), str(e.value)
+
+    def bad_domain(z2):
+        z2["domain_size"] = 6
+    expect(bad_domain, "Invalid domain size")
+
+    def short_srs(z2):
+        z2["p_tau"] = z2["p_tau"][:z2["domain_size"] + 5]
+    expect(short_srs, "SRS points")
+
+    def bad_map(z2):
+        z2["map_b"] = list(z2["map_b"])
+        z2["map_b"][0] = z2["n_vars"]
+    expect(bad_map, "Cannot index into witness")
+    # a well-formed key still loads afterwards
+    make_plonk_key(ctx, cv, z).free()
+
+
 def check_plonk_synthetic(ctx, log_n, n_public=2, against_oracle=True, seed=5):
     """Synthetic snarkjs-style key with known tau (workloads/synth_plonk.py): the device proof is accepted by the
     oracle's verifier (pairing check) and rejected for a wrong public input; at small sizes it also equals the

@@ -120,3 +120,7 @@ def test_plonk_rep3_multiplier2(emu_ctx):
 def test_plonk_rep3_synthetic(emu_ctx):
     K.check_plonk_rep3_synthetic(emu_ctx, 5, n_public=2)
     K.check_plonk_rep3_synthetic(emu_ctx, 4, n_public=0)
+
+
+def test_plonk_key_errors(emu_ctx):
+    K.check_plonk_key_errors(emu_ctx)
