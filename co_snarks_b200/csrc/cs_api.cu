@@ -179,7 +179,7 @@ namespace cs {
 template <class Cfg, int G>
 int bases_upload_t(cs_ctx* ctx, const uint64_t* h_points, size_t n, int window_bits, cs_bases* b) {
   typedef typename GroupOf<Cfg, G>::F F;
-  unsigned c = window_bits ? (unsigned)window_bits : msm_auto_window(n);
+  unsigned c = window_bits ? (unsigned)window_bits : msm_auto_window(n, Cfg::FR_BITS);
   if (c < 2 || c > 22) return fail(CS_ERR_ARG, "cs_bases_upload: window_bits %u out of range [2,22]", c);
   b->sh = msm_shape(Cfg::FR_BITS, c);
   b->n = n;

@@ -427,12 +427,22 @@ static inline MsmShape msm_shape(uint32_t scalar_bits, uint32_t c) {
 // (running sums + the per-segment scalar multiple).  Measured on B200 at n = 2^20 (G1, dense):
 // c = 16: accumulate 2.90 ms, sort 0.42, fold+reduce 0.75;  c = 20: accumulate 2.34 ms but sort 1.32 and
 // fold+reduce 1.0 -- the 2^19-bucket phases eat the gain, so 16 stays the cap (window_bits overrides).
-static inline uint32_t msm_auto_window(size_t n) {
+// Below 2^15 points the window shrinks with the input (lg n - 4) so that tiny MSMs do not pay for 2^15 buckets;
+// from 2^15 on c = 16 wins (B200, G1: 2^16 points 0.75-0.84 ms at c = 15/16 vs 1.35 ms at c = 12; 2^18 points
+// 1.48 ms at c = 16 vs 2.92 ms at c = 14).  A window size whose TOP window is only a few bits wide is avoided:
+// its 2^k digit values send n / 2^k scalars each into the same handful of buckets and their fold becomes a
+// serial chain (the 2.9 ms case above: 254 + 1 = 18 * 14 + 3).
+static inline uint32_t msm_auto_window(size_t n, uint32_t scalar_bits) {
   int lg = 0;
   while ((1ull << (lg + 1)) <= n) lg++;
-  int c = lg - 4;
+  int c = lg >= 15 ? 16 : lg - 4;
   if (c < 4) c = 4;
-  if (c > 16) c = 16;
+  while (c < 16) {
+    const uint32_t W = (scalar_bits + 1 + c - 1) / c;
+    const uint32_t top = scalar_bits + 1 - (W - 1) * c;
+    if (2 * top >= (uint32_t)c) break;
+    c++;
+  }
   return (uint32_t)c;
 }
 static inline uint32_t msm_slice(const MsmShape& sh) {
