@@ -87,25 +87,27 @@ CS_GLOBAL void k_msm_infmask(const Affine<F>* __restrict__ table, uint32_t n, ui
 }
 
 // --------------------------------------------------------------------------- scans (one block)
-// From count[0..B]: start = exclusive scan of count; ns0[b] = ceil(count[b]/S), ns1 = ceil(ns0/S);
-// sstart0 / sstart1 = exclusive scans.  Arrays have B + 2 entries (last = total).
+// From count[0..B]: start = exclusive scan of count; ns0[b] = ceil(count[b]/S), ns1 = ceil(ns0/S),
+// ns2 = ceil(ns1/S) (three fold levels keep the last, serial, per-bucket fold short even when most scalars
+// share one digit: 2^24 entries in ONE bucket leave 512 partials); sstart0 / sstart1 / sstart2 = exclusive scans.  Arrays have B + 2 entries (last = total).
 static CS_GLOBAL void k_msm_scan(const uint32_t* __restrict__ count, uint32_t nb1 /* B + 1 */, uint32_t MSM_SLICE,
                           uint32_t* __restrict__ start, uint32_t* __restrict__ sstart0,
-                          uint32_t* __restrict__ sstart1) {
-  __shared__ uint32_t sm[3][1024];
+                          uint32_t* __restrict__ sstart1, uint32_t* __restrict__ sstart2) {
+  __shared__ uint32_t sm[4][1024];
   const uint32_t T = blockDim.x, t = threadIdx.x;
   const uint32_t per = (nb1 + T - 1) / T;
   const uint32_t lo = t * per, hi = (lo + per < nb1) ? lo + per : nb1;
-  uint32_t a = 0, b = 0, cc = 0;
+  uint32_t a = 0, b = 0, cc = 0, dd = 0;
   for (uint32_t k = lo; k < hi; k++) {
     uint32_t cnt = k ? count[k] : 0;  // bucket 0 (zero digits) is dropped
     uint32_t n0 = (cnt + MSM_SLICE - 1) / MSM_SLICE;
     uint32_t n1 = (n0 + MSM_SLICE - 1) / MSM_SLICE;
-    a += cnt; b += n0; cc += n1;
+    uint32_t n2 = (n1 + MSM_SLICE - 1) / MSM_SLICE;
+    a += cnt; b += n0; cc += n1; dd += n2;
   }
-  sm[0][t] = a; sm[1][t] = b; sm[2][t] = cc;
+  sm[0][t] = a; sm[1][t] = b; sm[2][t] = cc; sm[3][t] = dd;
   __syncthreads();
-  if (t < 3) {
+  if (t < 4) {
     uint32_t run = 0;
     for (uint32_t k = 0; k < T; k++) {
       uint32_t v = sm[t][k];
@@ -114,15 +116,16 @@ static CS_GLOBAL void k_msm_scan(const uint32_t* __restrict__ count, uint32_t nb
     }
   }
   __syncthreads();
-  a = sm[0][t]; b = sm[1][t]; cc = sm[2][t];
+  a = sm[0][t]; b = sm[1][t]; cc = sm[2][t]; dd = sm[3][t];
   for (uint32_t k = lo; k < hi; k++) {
     uint32_t cnt = k ? count[k] : 0;
     uint32_t n0 = (cnt + MSM_SLICE - 1) / MSM_SLICE;
     uint32_t n1 = (n0 + MSM_SLICE - 1) / MSM_SLICE;
-    start[k] = a; sstart0[k] = b; sstart1[k] = cc;
-    a += cnt; b += n0; cc += n1;
+    uint32_t n2 = (n1 + MSM_SLICE - 1) / MSM_SLICE;
+    start[k] = a; sstart0[k] = b; sstart1[k] = cc; sstart2[k] = dd;
+    a += cnt; b += n0; cc += n1; dd += n2;
   }
-  if (hi == nb1 && lo < hi) { start[nb1] = a; sstart0[nb1] = b; sstart1[nb1] = cc; }
+  if (hi == nb1 && lo < hi) { start[nb1] = a; sstart0[nb1] = b; sstart1[nb1] = cc; sstart2[nb1] = dd; }
 }
 
 // --------------------------------------------------------------------------- scatter
@@ -454,7 +457,7 @@ static inline uint32_t msm_slice(const MsmShape& sh) {
 
 constexpr int MSM_NSTAGE = 5;  // digits | scan+scatter | accum0 | accum1+2 | reduce+final
 struct MsmWorkspace {
-  DevBuf dig, sorted, meta, part0, part1, bucket, red, scal, result, order;
+  DevBuf dig, sorted, meta, part0, part1, part2, bucket, red, scal, result, order;
   void* h_result = nullptr;  // pinned, holds one Xyzz
   size_t h_result_cap = 0;
   bool profile = false;      // record CUDA events at the stage boundaries (bench.py roofline)
@@ -470,7 +473,7 @@ struct MsmWorkspace {
       if (ev[i]) cudaEventDestroy(ev[i]);
       ev[i] = nullptr;
     }
-    dig.release(); sorted.release(); meta.release(); part0.release(); part1.release();
+    dig.release(); sorted.release(); meta.release(); part0.release(); part1.release(); part2.release();
     bucket.release(); red.release(); scal.release(); result.release(); order.release();
     if (h_result) cudaFreeHost(h_result);
     h_result = nullptr;
@@ -491,13 +494,15 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   const uint32_t S = msm_slice(sh);
   const size_t max_s0 = nent / S + nb1;
   const size_t max_s1 = max_s0 / S + nb1;
+  const size_t max_s2 = max_s1 / S + nb1;
   CS_TRY(ws.dig.reserve(nent * 4));
   CS_TRY(ws.sorted.reserve(nent * 4));
-  // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1]
-  const size_t meta_words = 2 * (size_t)nb1 + 3 * ((size_t)nb1 + 1);
+  // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1] sstart2[nb1+1]
+  const size_t meta_words = 2 * (size_t)nb1 + 4 * ((size_t)nb1 + 1);
   CS_TRY(ws.meta.reserve(meta_words * 4));
   CS_TRY(ws.part0.reserve(max_s0 * sizeof(Xyzz<F>)));
   CS_TRY(ws.part1.reserve(max_s1 * sizeof(Xyzz<F>)));
+  CS_TRY(ws.part2.reserve(max_s2 * sizeof(Xyzz<F>)));
   CS_TRY(ws.bucket.reserve((size_t)nb1 * sizeof(Xyzz<F>)));
   const uint32_t L = sh.B < MSM_RED_SEG ? sh.B : MSM_RED_SEG;
   const uint32_t nseg = (sh.B + L - 1) / L;
@@ -527,12 +532,13 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   uint32_t* start = cursor + nb1;
   uint32_t* sstart0 = start + nb1 + 1;
   uint32_t* sstart1 = sstart0 + nb1 + 1;
+  uint32_t* sstart2 = sstart1 + nb1 + 1;
   CS_TRY(ws.mark(0, st));
   CS_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nb1 * 4, st));
   CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W, infmask, offset,
             ws.dig.as<uint32_t>(), count);
   CS_TRY(ws.mark(1, st));
-  CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, S, start, sstart0, sstart1);
+  CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, S, start, sstart0, sstart1, sstart2);
   CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
             offset, start, cursor, ws.sorted.as<uint32_t>());
   CS_LAUNCH_SYNC(k_msm_slice_hist, ob, MSM_ORDER_BLOCK, 0, st, count, sstart0, nb1, S, slice_len, slice_bkt, block_hist);
@@ -565,7 +571,9 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_TRY(ws.mark(3, st));
   CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,
             nb1, S, ws.part1.as<Xyzz<F>>());
-  CS_LAUNCH(k_msm_accum2<F>, ceil_div(nb1, 128), 128, 0, st, ws.part1.as<Xyzz<F>>(), sstart1, nb1,
+  CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s2, 128), 128, 0, st, ws.part1.as<Xyzz<F>>(), sstart1, sstart2,
+            nb1, S, ws.part2.as<Xyzz<F>>());
+  CS_LAUNCH(k_msm_accum2<F>, ceil_div(nb1, 128), 128, 0, st, ws.part2.as<Xyzz<F>>(), sstart2, nb1,
             ws.bucket.as<Xyzz<F>>());
   CS_TRY(ws.mark(4, st));
   CS_LAUNCH(k_msm_reduce_seg<F>, ceil_div(nseg, 128), 128, 0, st, ws.bucket.as<Xyzz<F>>(), sh.B, L,

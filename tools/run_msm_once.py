@@ -8,6 +8,7 @@ lg = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 group = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 wb = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+skew = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0  # fraction of scalars set to 1 (witness-like skew)
 n = 1 << lg
 ctx = B.Context(0)
 rng = np.random.Generator(np.random.PCG64(4))
@@ -24,7 +25,12 @@ else:
     gen = B.ints_to_limbs(B.to_mont_ints(g2, Q, 4), 4).reshape(-1)
 pts = ctx.fixed_base_mul(B.CS_BN254, group, gen, rnd(n), montgomery=False)
 bases = ctx.bases_upload(B.CS_BN254, group, pts, wb)
-d = ctx.to_device(rnd(n))
+sc = rnd(n)
+if skew > 0:
+    ones = rng.random(n) < skew
+    sc[ones] = 0
+    sc[ones, 0] = 1
+d = ctx.to_device(sc)
 ctx.msm_profile(True)
 for _ in range(reps):
     out, inf = ctx.msm(bases, d, n=n, montgomery=False, device=True)
