@@ -31,8 +31,10 @@ net = Rep3Network(device="cuda")
 sizes = [int(a) for a in sys.argv[1:]] or [16, 18]
 out = {"world": 3}
 for lg in sizes:
+    t_setup = time.time()
     syn = SynthPlonk(ctx, lg)  # same seeds on every rank -> same circuit and key
     pk = syn.make_key()
+    setup_s = time.time() - t_setup
     npub = syn.n_public
     # replicated sharing of the private witness from a common seed (every rank derives all three shares)
     g = np.random.Generator(np.random.PCG64(7))
@@ -47,7 +49,8 @@ for lg in sizes:
     prover = Rep3CoPlonk(ctx, pk, rank)
     comm = DistRep3Comm(prover, net, peer=True)
     ms = []
-    for i in range(4):
+    reps = int(os.environ.get('CS_CO_PLONK_REPS', '4'))
+    for i in range(reps):
         torch.cuda.synchronize()
         dist.barrier()
         t0 = time.perf_counter()
@@ -65,7 +68,7 @@ for lg in sizes:
         ok = bool(OP.verify(BN254, syn.vk_ints(), proof, syn.full_witness[1:npub + 1], pairing_product_is_one))
     t = sum(ms[1:]) / len(ms[1:])
     out["2p%d" % lg] = {"ms_per_proof": round(t, 2), "proofs_per_s": round(1e3 / t, 2), "verified": ok,
-                        "bytes_sent_per_party": net.bytes_sent // 4}
+                        "bytes_sent_per_party": net.bytes_sent // reps, "setup_s": round(setup_s, 1)}
     net.bytes_sent = 0
     comm.close()
     prover.free()
