@@ -168,28 +168,34 @@ VERIFIER_KAT = dict(  # plonk.rs:266-309, on the snarkjs proof of the same circu
     u=13260637895132000183831258130762201406791497612259050836989270998713858775580)
 
 
-def plonk_full_fixture(name, compress):
+def plonk_full_fixture(name, compress, curve_dir="bn254"):
     """Everything the Plonk prover reads from the zkey (taceo-circom-types plonk::Zkey) + witness, verification
     key, public inputs, the snarkjs proof, and the reference's round 2-5 / verifier known answers."""
     from oracle import plonk as OP
     from oracle.pairing_bn254 import pairing_product_is_one
-    base = "%s/test_vectors/Plonk/bn254/%s/" % (REF, name)
+    base = "%s/test_vectors/Plonk/%s/%s/" % (REF, curve_dir, name)
     z = F.read_plonk_zkey(base + "circuit.zkey")
     _, w = F.read_wtns(base + "witness.wtns")
     vk = F.read_plonk_vk_json(base + "verification_key.json")
     pub = [int(x) for x in json.load(open(base + "public.json"))]
     sp = F.read_plonk_proof_json(base + "circom.proof")
-    assert OP.verify(z["curve"], vk, sp, pub, pairing_product_is_one), "snarkjs proof must verify"
+    bn = curve_dir == "bn254"  # the oracle has a pairing for BN254 only
+    if bn:
+        assert OP.verify(z["curve"], vk, sp, pub, pairing_product_is_one), "snarkjs proof must verify"
+    else:
+        for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3"):
+            assert z["vk_" + k] == vk[k], k
     pr = OP.prove(z, w)
-    if name == "multiplier2":
+    if name == "multiplier2" and bn:
         for k, (val, _) in PLONK_KAT.items():
             assert pr[k] == val, k
         ch = OP.verifier_challenges(z["curve"], vk, sp, pub)
         assert all(ch[k] == v for k, v in VERIFIER_KAT.items())
-    assert OP.verify(z["curve"], vk, pr, pub, pairing_product_is_one)
+    if bn:
+        assert OP.verify(z["curve"], vk, pr, pub, pairing_product_is_one)
     poly = lambda P: dict(coeffs=[hx(x) for x in P["coeffs"]], evals=[hx(x) for x in P["evals"]])
     pj = lambda P: {k: (p1(v) if isinstance(v, tuple) or v is None else hx(v)) for k, v in P.items()}
-    obj = dict(source="test_vectors/Plonk/bn254/" + name, curve="bn254",
+    obj = dict(source="test_vectors/Plonk/%s/%s" % (curve_dir, name), curve=curve_dir,
                **{k: z[k] for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints")},
                k1=hx(z["k1"]), k2=hx(z["k2"]), x2=p2(z["x2"]),
                **{"vk_" + k: p1(z["vk_" + k]) for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")},
@@ -199,14 +205,14 @@ def plonk_full_fixture(name, compress):
                lagrange=[poly(P) for P in z["lagrange"]], p_tau=[p1(P) for P in z["p_tau"]],
                witness=[hx(x) for x in w], public=[hx(x) for x in pub], vk_power=vk["power"],
                snarkjs_proof=pj(sp), oracle_proof_deterministic_blinders=pj(pr),
-               oracle_proof_json=F.plonk_proof_to_json(pr))
-    if name == "multiplier2":
+               oracle_proof_json=F.plonk_proof_to_json(pr, "bn128" if bn else "bls12381"))
+    if name == "multiplier2" and bn:
         obj["reference_kat"] = {k: dict(value=(p1(v) if isinstance(v, tuple) else hx(v)), source="co-circom/co-plonk/src/" + src)
                                 for k, (v, src) in PLONK_KAT.items()}
         obj["reference_verifier_kat"] = dict(source="co-circom/co-plonk/src/plonk.rs:266-309",
                                              **{k: ([hx(x) for x in v] if isinstance(v, list) else hx(v))
                                                 for k, v in VERIFIER_KAT.items()})
-    dump("plonk_full_bn254_" + name, obj, compress)
+    dump("plonk_full_%s_%s" % (curve_dir, name), obj, compress)
 
 
 def crs_fixture(n):
@@ -235,3 +241,4 @@ if __name__ == "__main__":
     crs_fixture(1024)
     plonk_full_fixture("multiplier2", False)
     plonk_full_fixture("poseidon", True)
+    plonk_full_fixture("multiplier2", False, "bls12_381")

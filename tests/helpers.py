@@ -103,10 +103,10 @@ def golden_groth16(name):
     return z, m, w, g
 
 
-def golden_plonk(name):
+def golden_plonk(name, curve="bn254"):
     """-> (plonk zkey dict in the oracle's conventions, witness ints, golden json)."""
-    g = load_golden("plonk_full_bn254_" + name)
-    c = CURVES["bn254"]
+    g = load_golden("plonk_full_%s_%s" % (curve, name))
+    c = CURVES[curve]
     z = dict(curve=c, q=c.q, r=c.r)
     for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints", "map_a", "map_b", "map_c"):
         z[k] = g[k]

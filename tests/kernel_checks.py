@@ -497,21 +497,21 @@ def check_keccak(lib):
     assert B.keccak256(lib, b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
 
 
-def check_plonk_prove(ctx, name="multiplier2", random_blinders=True):
+def check_plonk_prove(ctx, name="multiplier2", random_blinders=True, curve="bn254"):
     """Plonk::plain_prove on the device == the oracle's restatement, field by field, for the reference's
     deterministic blinders (the KAT setting of co-plonk/src/round{2..5}.rs tests) and for random ones; the proof
     JSON equals the committed golden one, which the oracle's verifier accepts (tests/test_oracle_golden.py)."""
     from helpers import golden_plonk, make_plonk_key, plonk_proof_from_device
     from oracle import plonk as OP
     from oracle.formats import plonk_proof_to_json
-    cv = Conv("bn254")
-    z, w, g = golden_plonk(name)
+    cv = Conv(curve)
+    z, w, g = golden_plonk(name, curve)
     npub = z["n_public"]
     pk = make_plonk_key(ctx, cv, z)
     pub, wit = cv.fr(w[:npub + 1]), cv.fr(w[npub + 1:])
     pts, evs = pk.prove_plain(pub, wit, cv.fr(list(range(11))))
     got = plonk_proof_from_device(cv, pts, evs)
-    assert plonk_proof_to_json(got) == g["oracle_proof_json"]
+    assert plonk_proof_to_json(got, g["oracle_proof_json"]["curve"]) == g["oracle_proof_json"]
     if "reference_kat" in g:
         for k, kat in g["reference_kat"].items():
             exp = gp1(kat["value"]) if isinstance(kat["value"], list) else ih(kat["value"])

@@ -124,3 +124,8 @@ def test_plonk_rep3_synthetic(emu_ctx):
 
 def test_plonk_key_errors(emu_ctx):
     K.check_plonk_key_errors(emu_ctx)
+
+
+def test_plonk_prove_bls12_381(emu_ctx):
+    """The BLS12-381 instantiation (255-bit Fr, 6-limb Fq) on the reference's bls12_381/multiplier2 fixture."""
+    K.check_plonk_prove(emu_ctx, "multiplier2", curve="bls12_381")

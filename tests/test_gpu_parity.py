@@ -137,3 +137,8 @@ def test_plonk_rep3_poseidon(gpu_ctx):
 
 def test_plonk_rep3_synthetic(gpu_ctx):
     K.check_plonk_rep3_synthetic(gpu_ctx, 9, n_public=3)
+
+
+def test_plonk_prove_bls12_381(gpu_ctx):
+    """The BLS12-381 instantiation (255-bit Fr, 6-limb Fq) on the reference's bls12_381/multiplier2 fixture."""
+    K.check_plonk_prove(gpu_ctx, "multiplier2", curve="bls12_381")
