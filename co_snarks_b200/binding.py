@@ -116,6 +116,7 @@ SIGNATURES = {
     "cs_plonk_rep3_free": (None, [C.c_void_p]),
     "cs_plonk_rep3_arena": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_uint)]),
     "cs_plonk_rep3_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_plonk_rep3_io": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "cs_plonk_rep3_round1": (C.c_int, [C.c_void_p, C.POINTER(Rep3Prf), C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
                                        C.c_void_p, C.c_void_p]),
     "cs_plonk_rep3_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
@@ -503,6 +504,9 @@ class PlonkRep3Session:
         p, sb, ns = C.c_void_p(), C.c_size_t(), C.c_uint()
         ctx._check(ctx.lib.cs_plonk_rep3_arena(self.h, C.byref(p), C.byref(sb), C.byref(ns)))
         self.arena, self.slot_bytes, self.n_slots = p.value, sb.value, ns.value
+        o, i = C.c_void_p(), C.c_void_p()
+        ctx._check(ctx.lib.cs_plonk_rep3_io(self.h, C.byref(o), C.byref(i)))
+        self.d_out, self.d_in = o.value, i.value  # additive outputs / opened inputs of the masked vectors
 
     def connect(self, d_next_arena):
         self.ctx._check(self.ctx.lib.cs_plonk_rep3_connect(self.h, C.c_void_p(d_next_arena) if d_next_arena else None))

@@ -661,13 +661,13 @@ int r3_step_t(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out)
       CS_LAUNCH(k_r3_round2_c<FrP>, ceil_div(n + 1, 128), 128, 0, st, r3_slot(s, 3), n, s->prf, s->rbase, s->ctr, addv,
                 addv + (size_t)n * NW);
       s->ctr += 2 * (uint64_t)n + 1;
-      CS_CUDA(cudaMemcpyAsync(h_out, addv, (size_t)(2 * n + 1) * 32, cudaMemcpyDeviceToHost, st));
+      if (h_out) CS_CUDA(cudaMemcpyAsync(h_out, addv, (size_t)(2 * n + 1) * 32, cudaMemcpyDeviceToHost, st));
       CS_CUDA(cudaStreamSynchronize(st));
       return 0;
     }
     case CS_PLONK_R3_ROUND2_D: {  // in: opened G (n) | Q (n + 1)
-      uint32_t* opened = pscr + (size_t)(4 * n + 4) * NW;
-      CS_CUDA(cudaMemcpyAsync(opened, h_in, (size_t)(2 * n + 1) * 32, cudaMemcpyHostToDevice, st));
+      uint32_t* opened = pscr + (size_t)(4 * n + 4) * NW;  // h_in == NULL: the driver summed the parties' vectors in place
+      if (h_in) CS_CUDA(cudaMemcpyAsync(opened, h_in, (size_t)(2 * n + 1) * 32, cudaMemcpyHostToDevice, st));
       CS_TRY(r3_batch_inverse<Cfg>(s, opened, n, pscr, ginv));
       CS_TRY(r3_batch_inverse<Cfg>(s, opened + (size_t)n * NW, n + 1, pscr, qinv));
       CS_LAUNCH(k_r3_round2_d<FrP>, gb, 128, 0, st, r3_slot(s, 2), ginv, qinv, n, s->prf, s->rbase, s->ctr, r3_slot(s, 4),
@@ -683,13 +683,14 @@ int r3_step_t(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out)
     case CS_PLONK_R3_ROUND2_F: {  // out: y (n), additive
       CS_LAUNCH(k_r3_round2_f<FrP>, gb, 128, 0, st, r3_slot(s, 6), qinv, n, s->prf, s->rbase, s->ctr, addv);
       s->ctr += n;
-      CS_CUDA(cudaMemcpyAsync(h_out, addv, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+      if (h_out) CS_CUDA(cudaMemcpyAsync(h_out, addv, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
       CS_CUDA(cudaStreamSynchronize(st));
       return 0;
     }
     case CS_PLONK_R3_ROUND2_G: {  // in: opened Y (n); out: partial [z]
       uint32_t* y = pscr;
-      CS_CUDA(cudaMemcpyAsync(y, h_in, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+      if (h_in) CS_CUDA(cudaMemcpyAsync(y, h_in, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+      else CS_CUDA(cudaMemcpyAsync(y, pscr + (size_t)(4 * n + 4) * NW, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
       CS_TRY((scan<FrP, 0>(ctx, s, y, y, n, 0)));
       uint32_t* ps = s->polysh[3].as<uint32_t>();
       CS_LAUNCH(k_r3_round2_g<FrP>, gb, 128, 0, st, y, r3_slot(s, 5), n, ps);
@@ -923,6 +924,13 @@ int cs_plonk_rep3_arena(cs_plonk_rep3* s, void** d_arena, size_t* slot_bytes, un
   *d_arena = s->arena.p;
   *slot_bytes = s->slot_words * 4;
   *n_slots = R3_SLOTS;
+  return 0;
+}
+
+int cs_plonk_rep3_io(cs_plonk_rep3* s, void** d_additive_out, void** d_opened_in) {
+  if (!s || !d_additive_out || !d_opened_in) return fail(CS_ERR_ARG, "cs_plonk_rep3_io: NULL argument");
+  *d_additive_out = s->addv.p;
+  *d_opened_in = s->pubv.as<uint32_t>() + ((size_t)(2 * s->pk->n + 1) + (size_t)(4 * s->pk->n + 4)) * 8;
   return 0;
 }
 

@@ -62,6 +62,7 @@ def fr_mul(lib, curve, a, b):
 class Rep3CoPlonk:
     """One party.  `prove` is a generator: it yields (kind, payload) requests and expects the combined value back:
          ("sum_points", [k, 2 fq])  -> the k opened points          ("sum_vec", [m, 4]) -> the m opened scalars
+         ("sum_dev", m) -> None once sess.d_in holds the sum over the parties of their m-element vectors at sess.d_out
          ("reshare", (slots, count)) -> None once every party's products for these arena slots are in place."""
 
     def __init__(self, ctx, pk, party, curve=B.CS_BN254):
@@ -96,15 +97,15 @@ class Rep3CoPlonk:
         yield ("reshare", ([0, 1], n))
         s.step(B.R3_ROUND2_B)
         yield ("reshare", ([2, 3], n))
-        gq = s.step(B.R3_ROUND2_C, None, (2 * n + 1, 4))
-        GQ = yield ("sum_vec", gq)
-        s.step(B.R3_ROUND2_D, GQ)
+        s.step(B.R3_ROUND2_C)
+        yield ("sum_dev", 2 * n + 1)  # device-resident opening: sess.d_out summed over the parties into sess.d_in
+        s.step(B.R3_ROUND2_D)
         yield ("reshare", ([4, 5], n))
         s.step(B.R3_ROUND2_E)
         yield ("reshare", ([6], n))
-        y = s.step(B.R3_ROUND2_F, None, (n, 4))
-        Y = yield ("sum_vec", y)
-        zp = s.step(B.R3_ROUND2_G, Y, (1, 2 * fq))
+        s.step(B.R3_ROUND2_F)
+        yield ("sum_dev", n)
+        zp = s.step(B.R3_ROUND2_G, None, (1, 2 * fq))
         (Z,) = yield ("sum_points", zp)
         t = Transcript(lib, cv)
         t.add_scalar(beta)
@@ -146,6 +147,17 @@ def _sum_points(lib, curve, parts):
     return np.stack(out)
 
 
+def _vec_add(ctx, curve, d_a, d_b, d_out, m):
+    ctx._check(ctx.lib.cs_vec_add(ctx.h, curve, C.c_void_p(d_a), C.c_void_p(d_b), C.c_void_p(d_out), m))
+
+
+class _CudaView:
+    """Zero-copy torch view of library-owned device memory (CUDA array interface)."""
+
+    def __init__(self, ptr, nwords64):
+        self.__cuda_array_interface__ = {"data": (ptr, False), "shape": (nwords64,), "typestr": "<i8", "version": 2}
+
+
 def _sum_vec(ctx, curve, parts):
     m = parts[0].shape[0]
     d = [ctx.to_device(np.ascontiguousarray(p)) for p in parts]
@@ -179,6 +191,13 @@ class LocalRep3Comm:
                 ans = _sum_points(ctx.lib, curve, [r[1] for r in reqs])
             elif kind == "sum_vec":
                 ans = _sum_vec(ctx, curve, [r[1] for r in reqs])
+            elif kind == "sum_dev":
+                m, ss = reqs[0][1], [pr.sess for pr in self.provers]
+                for p in range(3):
+                    _vec_add(ctx, curve, ss[0].d_out, ss[1].d_out, ss[p].d_in, m)
+                    _vec_add(ctx, curve, ss[p].d_in, ss[2].d_out, ss[p].d_in, m)
+                ctx.synchronize()
+                ans = None
             else:
                 ctx.synchronize()
                 ans = None
@@ -219,6 +238,25 @@ class DistRep3Comm:
         prev, nxt = self.net.broadcast(arr)
         return [arr, prev, nxt]
 
+    def _sum_dev(self, m):
+        """Opens an m-element additive vector without leaving the device when the group's tensors live on the
+        GPU (all_gather straight from the session buffer, two cs_vec_add); through the host otherwise."""
+        ctx, curve, sess = self.prover.ctx, self.prover.curve, self.prover.sess
+        ctx.synchronize()
+        if str(self.net.device).startswith("cuda"):
+            import torch
+            mine = torch.as_tensor(_CudaView(sess.d_out, 4 * m), device="cuda")
+            outs = [torch.empty(4 * m, dtype=torch.int64, device="cuda") for _ in range(3)]
+            self.net.dist.all_gather(outs, mine, group=self.net.group)
+            torch.cuda.synchronize()
+            self.net.bytes_sent += 2 * 32 * m
+            _vec_add(ctx, curve, outs[0].data_ptr(), outs[1].data_ptr(), sess.d_in, m)
+            _vec_add(ctx, curve, sess.d_in, outs[2].data_ptr(), sess.d_in, m)
+            ctx.synchronize()
+        else:
+            parts = self._gather(ctx.d2h(sess.d_out, (m, 4)))
+            ctx.h2d(sess.d_in, _sum_vec(ctx, curve, parts))
+
     def run(self, gen):
         ctx, curve, sess = self.prover.ctx, self.prover.curve, self.prover.sess
         req = next(gen)
@@ -228,6 +266,9 @@ class DistRep3Comm:
                 ans = _sum_points(ctx.lib, curve, self._gather(payload))
             elif kind == "sum_vec":
                 ans = _sum_vec(ctx, curve, self._gather(payload))
+            elif kind == "sum_dev":
+                self._sum_dev(payload)
+                ans = None
             else:
                 slots, count = payload
                 ctx.synchronize()

@@ -362,6 +362,10 @@ int cs_plonk_rep3_create(cs_ctx* ctx, cs_plonk_pk* pk, int party, cs_plonk_rep3*
 void cs_plonk_rep3_free(cs_plonk_rep3* s);
 int cs_plonk_rep3_arena(cs_plonk_rep3* s, void** d_arena, size_t* slot_bytes, unsigned* n_slots);
 int cs_plonk_rep3_connect(cs_plonk_rep3* s, void* d_next_arena);
+/* Device-resident openings of the two large masked vectors: ROUND2_C / ROUND2_F leave their additive output at
+ * *d_additive_out (h_out may be NULL); ROUND2_D / ROUND2_G called with h_in == NULL read the opened sum from
+ * *d_opened_in, where the driver has added up the three parties' vectors (e.g. ncclAllGather + cs_vec_add). */
+int cs_plonk_rep3_io(cs_plonk_rep3* s, void** d_additive_out, void** d_opened_in);
 int cs_plonk_rep3_round1(cs_plonk_rep3* s, const cs_rep3_prf* prf, const uint64_t* h_public_inputs, size_t n_public_inputs,
                          const uint64_t* h_witness_shares, size_t n_witness, const uint64_t* h_blinder_shares,
                          uint64_t* out_points);
