@@ -109,6 +109,7 @@ SIGNATURES = {
     "cs_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_plonk_pk_create": (C.c_int, [C.c_void_p, C.POINTER(PlonkKeyDesc), C.POINTER(C.c_void_p)]),
     "cs_plonk_pk_free": (None, [C.c_void_p]),
+    "cs_plonk_pk_from_zkey": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "cs_plonk_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
     "cs_keccak256": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p]),
@@ -469,6 +470,17 @@ class PlonkKey:
         self.h = h
         self.fq = limbs_of(curve, "fq")
         del keep
+
+    @classmethod
+    def from_zkey(cls, ctx, path, curve=CS_BN254):
+        """snarkjs Plonk .zkey -> device-resident key (cs_plonk_pk_from_zkey)."""
+        self = cls.__new__(cls)
+        self.ctx, self.curve = ctx, curve
+        h, npub, nwit = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        ctx._check(ctx.lib.cs_plonk_pk_from_zkey(ctx.h, str(path).encode(), C.byref(h), C.byref(npub), C.byref(nwit)))
+        self.h, self.n_public, self.n_witness = h, npub.value, nwit.value
+        self.fq = limbs_of(curve, "fq")
+        return self
 
     def prove_plain(self, public_inputs, witness, blinders_mont):
         """Plonk::plain_prove -> (points [9, 2*fq] A B C Z T1 T2 T3 Wxi Wxiw, evals [6, 4] a b c s1 s2 zw), Montgomery."""

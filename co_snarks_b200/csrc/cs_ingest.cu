@@ -175,6 +175,97 @@ int cs_groth16_pk_from_zkey(cs_ctx* ctx, const char* path, int window_bits, cs_g
   return cs_groth16_pk_create(ctx, &k, out);
 }
 
+// Plonk .zkey (protocol 2; circom_types::plonk::Zkey::from_reader, co-circom.rs:1053-1060).  Every field element
+// in the file is already in Montgomery form and every polynomial is stored as `coefficients | 4n evaluations`,
+// so the sections are handed to cs_plonk_pk_create as they lie; only the additions (interleaved ids and
+// factors) and the Lagrange evaluations (interleaved with their coefficients) are regrouped.
+//   2 header: n8q q n8r r nVars nPublic domainSize nAdditions nConstraints k1 k2 Qm Ql Qr Qo Qc S1 S2 S3 X_2
+//   3 additions  4-6 wire maps  7-11 qm ql qr qo qc  12 sigma1..3  13 Lagrange  14 powers of tau
+int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size_t* out_n_public, size_t* out_n_witness) {
+  if (!ctx || !path || !out) return fail(CS_ERR_ARG, "cs_plonk_pk_from_zkey: NULL argument");
+  Sections z;
+  CS_TRY(read_file(path, "zkey", z));
+  for (uint32_t t = 1; t <= 14; t++)
+    if (!z.sec.count(t)) return fail(CS_ERR_ARG, "%s: section %u missing", path, t);
+  const uint8_t* d = z.data.data();
+  if (rd32(d + z.sec[1].first) != 2) return fail(CS_ERR_ARG, "%s: not a Plonk zkey (protocol %u)", path, rd32(d + z.sec[1].first));
+  const uint8_t* h = d + z.sec[2].first;
+  const uint32_t n8q = rd32(h);
+  const uint8_t* q = h + 4;
+  const uint32_t n8r = rd32(q + n8q);
+  const uint8_t* p = q + n8q + 4 + n8r;
+  const int curve = detect_curve(q, n8q);
+  if (curve < 0) return fail(CS_ERR_ARG, "%s: unsupported curve (base field of %u bytes)", path, n8q);
+#if !defined(CS_ENABLE_BLS12_381)
+  if (curve != CS_BN254) return fail(CS_ERR_ARG, "%s: BLS12-381 support is not compiled in", path);
+#endif
+  if (n8r != 32) return fail(CS_ERR_ARG, "%s: unexpected scalar field size %u", path, n8r);
+  cs_plonk_key_desc k;
+  memset(&k, 0, sizeof(k));
+  k.curve = (cs_curve)curve;
+  k.n_vars = rd32(p); k.n_public = rd32(p + 4); k.domain_size = rd32(p + 8); k.n_additions = rd32(p + 12);
+  k.n_constraints = rd32(p + 16);
+  p += 20;
+  const size_t g1 = 2 * (size_t)n8q, g2 = 4 * (size_t)n8q;
+  if ((size_t)(p + 2 * n8r + 8 * g1 + g2 - h) > z.sec[2].second) return fail(CS_ERR_ARG, "%s: header section too short", path);
+  std::vector<std::vector<uint64_t>> realigned;
+  auto aligned = [&](const uint8_t* src, size_t bytes) -> const uint64_t* {
+    if (((uintptr_t)src & 7) == 0) return (const uint64_t*)src;
+    realigned.emplace_back((bytes + 7) / 8);
+    memcpy(realigned.back().data(), src, bytes);
+    return realigned.back().data();
+  };
+  auto aligned32 = [&](const uint8_t* src, size_t bytes) -> const uint32_t* { return (const uint32_t*)aligned(src, bytes); };
+  k.k1_mont = aligned(p, n8r);
+  k.k2_mont = aligned(p + n8r, n8r);
+  k.vk_points = aligned(p + 2 * n8r, 8 * g1);
+  const size_t n = k.domain_size, na = k.n_additions, nc = k.n_constraints;
+  const size_t nlag = k.n_public ? k.n_public : 1;
+  const size_t poly = 5 * n * n8r;  // coefficients + 4n evaluations
+  auto need = [&](uint32_t t, size_t bytes) -> int {
+    if (z.sec[t].second < bytes) return fail(CS_ERR_ARG, "%s: section %u holds %zu bytes, header implies %zu", path, t, z.sec[t].second, bytes);
+    return 0;
+  };
+  CS_TRY(need(3, na * (8 + 2 * (size_t)n8r)));
+  for (uint32_t t = 4; t <= 6; t++) CS_TRY(need(t, nc * 4));
+  for (uint32_t t = 7; t <= 11; t++) CS_TRY(need(t, poly));
+  CS_TRY(need(12, 3 * poly));
+  CS_TRY(need(13, nlag * poly));
+  // additions: (u32 id1, u32 id2, f1, f2) records
+  std::vector<uint32_t> add_ids(2 * na + 2);
+  std::vector<uint64_t> add_f(8 * na + 8);
+  const uint8_t* a = d + z.sec[3].first;
+  for (size_t i = 0; i < na; i++, a += 8 + 2 * n8r) {
+    add_ids[2 * i] = rd32(a);
+    add_ids[2 * i + 1] = rd32(a + 4);
+    memcpy(&add_f[8 * i], a + 8, 2 * (size_t)n8r);
+  }
+  k.additions_ids = add_ids.data();
+  k.additions_factors = add_f.data();
+  k.map_a = aligned32(d + z.sec[4].first, nc * 4);
+  k.map_b = aligned32(d + z.sec[5].first, nc * 4);
+  k.map_c = aligned32(d + z.sec[6].first, nc * 4);
+  for (int i = 0; i < 5; i++) {
+    const uint8_t* s0 = d + z.sec[7 + i].first;
+    k.q_coeffs[i] = aligned(s0, n * n8r);
+    k.q_evals[i] = aligned(s0 + n * n8r, 4 * n * n8r);
+  }
+  for (int i = 0; i < 3; i++) {
+    const uint8_t* s0 = d + z.sec[12].first + (size_t)i * poly;
+    k.s_coeffs[i] = aligned(s0, n * n8r);
+    k.s_evals[i] = aligned(s0 + n * n8r, 4 * n * n8r);
+  }
+  std::vector<uint64_t> lag(nlag * 4 * n * 4);
+  for (size_t j = 0; j < nlag; j++)
+    memcpy(&lag[j * 4 * n * 4], d + z.sec[13].first + j * poly + n * n8r, 4 * n * n8r);
+  k.lagrange_evals = lag.data();
+  k.p_tau = aligned(d + z.sec[14].first, z.sec[14].second);
+  k.n_p_tau = z.sec[14].second / g1;
+  if (out_n_public) *out_n_public = k.n_public;
+  if (out_n_witness) *out_n_witness = (size_t)k.n_vars - k.n_additions - k.n_public - 1;
+  return cs_plonk_pk_create(ctx, &k, out);
+}
+
 int cs_wtns_read(const char* path, cs_curve curve, uint64_t* out_mont, size_t capacity, size_t* out_n) {
   if (!path || !out_n) return fail(CS_ERR_ARG, "cs_wtns_read: NULL argument");
   Sections w;

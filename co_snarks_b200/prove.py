@@ -1,10 +1,12 @@
 """`python -m co_snarks_b200.prove --zkey circuit.zkey --wtns witness.wtns --out proof.json`
 
-The GPU counterpart of `co-circom generate-proof groth16` for the plain driver
+The GPU counterpart of `co-circom generate-proof groth16|plonk` for the plain driver
 (co-circom/co-circom/src/bin/co-circom.rs:966-1066): zkey -> device-resident key, wtns -> witness,
-Groth16::plain_prove with fresh (r, s), proof written in snarkjs' JSON layout (decimal strings, the layout
-of test_vectors/Groth16/bn254/multiplier2/circom.proof) plus public.json.
+Groth16::plain_prove with fresh (r, s) or Plonk::plain_prove with fresh blinders (the protocol is read from
+the zkey), proof written in snarkjs' JSON layout (decimal strings, the layout of
+test_vectors/{Groth16,Plonk}/bn254/multiplier2/circom.proof) plus public.json.
 """
+import struct
 import argparse
 import json
 import secrets
@@ -32,6 +34,35 @@ def proof_json(lib, A, Bp, C):
             "pi_c": [str(c[0]), str(c[1]), "1"], "protocol": "groth16", "curve": "bn128"}
 
 
+def zkey_protocol(path):
+    """1 = Groth16, 2 = Plonk (section 1 of the snarkjs container)."""
+    with open(path, "rb") as f:
+        head = f.read(12)
+        assert head[:4] == b"zkey", "%s: not a zkey file" % path
+        (nsec,) = struct.unpack("<I", head[8:12])
+        for _ in range(nsec):
+            typ, ln = struct.unpack("<IQ", f.read(12))
+            if typ == 1:
+                return struct.unpack("<I", f.read(4))[0]
+            f.seek(ln, 1)
+    raise ValueError("%s: no protocol section" % path)
+
+
+def plonk_proof_json(lib, pts, evs):
+    names = ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")
+    out = {}
+    for k, P in zip(names, pts):
+        c = _canon(lib, P, "fq")
+        out[k] = ["0", "1", "0"] if not any(c) else [str(c[0]), str(c[1]), "1"]
+    e = _canon(lib, evs, "fr")
+    proof = {k: out[k] for k in names[:7]}
+    for k, v in zip(("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"), e):
+        proof[k] = str(v)
+    proof["Wxi"], proof["Wxiw"] = out["Wxi"], out["Wxiw"]
+    proof["protocol"], proof["curve"] = "plonk", "bn128"
+    return proof
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--zkey", required=True)
@@ -43,6 +74,23 @@ def main(argv=None):
     args = ap.parse_args(argv)
     ctx = B.Context(args.device, lib_path=args.lib)
     t0 = time.time()
+    if zkey_protocol(args.zkey) == 2:
+        pk = B.PlonkKey.from_zkey(ctx, args.zkey)
+        wit = B.read_wtns(ctx.lib, args.wtns)
+        t1 = time.time()
+        bl = B.ints_to_limbs(B.to_mont_ints([secrets.randbelow(BN254_R) for _ in range(11)], BN254_R, 4), 4)
+        ni = pk.n_public + 1
+        pts, evs = pk.prove_plain(np.ascontiguousarray(wit[:ni]), np.ascontiguousarray(wit[ni:]), bl)
+        t2 = time.time()
+        with open(args.out, "w") as f:
+            json.dump(plonk_proof_json(ctx.lib, pts, evs), f)
+        if args.public_out:
+            with open(args.public_out, "w") as f:
+                json.dump([str(x) for x in _canon(ctx.lib, wit[1:ni], "fr")], f)
+        print("key+witness load %.1f ms, Generate proof took %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+        pk.free()
+        ctx.close()
+        return
     pk = B.Groth16Key.from_zkey(ctx, args.zkey)
     wit = B.read_wtns(ctx.lib, args.wtns)
     t1 = time.time()

@@ -324,6 +324,9 @@ typedef struct {
   size_t n_p_tau;
 } cs_plonk_key_desc;
 int cs_plonk_pk_create(cs_ctx* ctx, const cs_plonk_key_desc* desc, cs_plonk_pk** out);
+/* The same straight from a snarkjs Plonk .zkey (circom_types::plonk::Zkey::from_reader, co-circom.rs:1053-1060);
+ * out_n_witness = number of private witness values a proof takes (nVars - nAdditions - nPublic - 1). */
+int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size_t* out_n_public, size_t* out_n_witness);
 void cs_plonk_pk_free(cs_plonk_pk* pk);
 /* One proof.  h_public_inputs: n_public + 1 values as in SharedWitness.public_inputs (entry 0, the constant one,
  * is replaced by zero like types.rs:118-120); h_witness: the remaining n_vars - n_additions - n_public - 1

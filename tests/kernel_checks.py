@@ -527,6 +527,35 @@ def check_plonk_prove(ctx, name="multiplier2", random_blinders=True, curve="bn25
     pk.free()
 
 
+def check_plonk_zkey_ingest(ctx, tmp_path, name="multiplier2", curve="bn254"):
+    """cs_plonk_pk_from_zkey: a snarkjs-format Plonk .zkey written from the golden fixture (and the reference's own
+    file when /root/reference is mounted) goes straight to the device layout; the proof equals the golden one."""
+    import os
+    from helpers import golden_plonk, plonk_proof_from_device
+    from oracle import formats as F
+    from zkey_writer import write_plonk_zkey
+    cv = Conv(curve)
+    z, w, g = golden_plonk(name, curve)
+    path = os.path.join(str(tmp_path), "plonk_%s_%s.zkey" % (curve, name))
+    write_plonk_zkey(path, z)
+    back = F.read_plonk_zkey(path)
+    assert all(back[k] == z[k] for k in ("k1", "k2", "map_a", "additions", "qm", "s3", "lagrange", "p_tau", "x2", "vk_s2"))
+    paths = [path]
+    ref = "/root/reference/test_vectors/Plonk/%s/%s/circuit.zkey" % (curve, name)
+    if os.path.exists(ref):
+        paths.append(ref)
+    npub = z["n_public"]
+    for pth in paths:
+        pk = B.PlonkKey.from_zkey(ctx, pth, cv.id)
+        assert pk.n_public == npub and pk.n_witness == len(w) - npub - 1
+        pts, evs = pk.prove_plain(cv.fr(w[:npub + 1]), cv.fr(w[npub + 1:]), cv.fr(list(range(11))))
+        got = plonk_proof_from_device(cv, pts, evs)
+        assert F.plonk_proof_to_json(got, g["oracle_proof_json"]["curve"]) == g["oracle_proof_json"], pth
+        pk.free()
+    with pytest.raises(RuntimeError):
+        B.PlonkKey.from_zkey(ctx, os.path.join(str(tmp_path), "missing.zkey"), cv.id)
+
+
 def check_plonk_key_errors(ctx):
     """PlonkProofError behaviour at the boundary (co-plonk/src/lib.rs:40-69, types.rs:79-84): invalid domain size,
     SRS too short for the blinded polynomials, wire maps / additions that index past the witness."""
@@ -778,6 +807,32 @@ def check_prove_cli(ctx_lib_path, tmp_path, name="multiplier2"):
     assert public == [ih(x) for x in g["public"]]
     assert groth16_verify(OG.vk_from_zkey(z), public, proof)
     assert json.load(open(out))["protocol"] == "groth16"
+
+
+def check_prove_cli_plonk(ctx_lib_path, tmp_path, name="multiplier2"):
+    """The same CLI on a Plonk zkey: snarkjs-layout Plonk proof.json accepted by Plonk::verify (plonk.rs:110-245)."""
+    import json
+    import os
+    import zkey_writer
+    from co_snarks_b200 import prove as P
+    from helpers import golden_plonk, plonk_vk_from_zkey
+    from oracle import plonk as OP
+    from oracle.formats import read_plonk_proof_json
+    from oracle.pairing_bn254 import pairing_product_is_one
+    cv = Conv("bn254")
+    z, w, g = golden_plonk(name)
+    zp, wp = os.path.join(str(tmp_path), "p.zkey"), os.path.join(str(tmp_path), "pw.wtns")
+    zkey_writer.write_plonk_zkey(zp, z)
+    zkey_writer.write_wtns(wp, cv.r, w)
+    out, pub = os.path.join(str(tmp_path), "plonk_proof.json"), os.path.join(str(tmp_path), "plonk_public.json")
+    argv = ["--zkey", zp, "--wtns", wp, "--out", out, "--public-out", pub]
+    if ctx_lib_path:
+        argv += ["--lib", ctx_lib_path]
+    P.main(argv)
+    public = [int(x) for x in json.load(open(pub))]
+    assert public == [ih(x) for x in g["public"]]
+    assert OP.verify(BN254, plonk_vk_from_zkey(z, g["vk_power"]), read_plonk_proof_json(out), public, pairing_product_is_one)
+    assert json.load(open(out))["protocol"] == "plonk"
 
 
 def check_libsnark_reduction(ctx, m_vars=50, seed=14):

@@ -86,6 +86,7 @@ def test_emu_prove_cli(emu_ctx, tmp_path):
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "emu"))
     import build_emu
     K.check_prove_cli(build_emu.OUT, tmp_path)
+    K.check_prove_cli_plonk(build_emu.OUT, tmp_path)
 
 
 def test_emu_libsnark_reduction(emu_ctx):
@@ -129,3 +130,8 @@ def test_plonk_key_errors(emu_ctx):
 def test_plonk_prove_bls12_381(emu_ctx):
     """The BLS12-381 instantiation (255-bit Fr, 6-limb Fq) on the reference's bls12_381/multiplier2 fixture."""
     K.check_plonk_prove(emu_ctx, "multiplier2", curve="bls12_381")
+
+
+def test_plonk_zkey_ingest(emu_ctx, tmp_path):
+    K.check_plonk_zkey_ingest(emu_ctx, tmp_path, "multiplier2")
+    K.check_plonk_zkey_ingest(emu_ctx, tmp_path, "multiplier2", curve="bls12_381")

@@ -104,6 +104,7 @@ def test_zkey_ingest(gpu_ctx, tmp_path):
 
 def test_prove_cli(gpu_ctx, tmp_path):
     K.check_prove_cli(None, tmp_path, "poseidon")
+    K.check_prove_cli_plonk(None, tmp_path, "multiplier2")
 
 
 def test_libsnark_reduction(gpu_ctx):
@@ -142,3 +143,8 @@ def test_plonk_rep3_synthetic(gpu_ctx):
 def test_plonk_prove_bls12_381(gpu_ctx):
     """The BLS12-381 instantiation (255-bit Fr, 6-limb Fq) on the reference's bls12_381/multiplier2 fixture."""
     K.check_plonk_prove(gpu_ctx, "multiplier2", curve="bls12_381")
+
+
+def test_plonk_zkey_ingest(gpu_ctx, tmp_path):
+    K.check_plonk_zkey_ingest(gpu_ctx, tmp_path, "multiplier2")
+    K.check_plonk_zkey_ingest(gpu_ctx, tmp_path, "multiplier2", curve="bls12_381")
