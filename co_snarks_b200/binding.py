@@ -109,6 +109,7 @@ SIGNATURES = {
     "cs_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_plonk_pk_create": (C.c_int, [C.c_void_p, C.POINTER(PlonkKeyDesc), C.POINTER(C.c_void_p)]),
     "cs_plonk_pk_free": (None, [C.c_void_p]),
+    "cs_plonk_pk_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]),
     "cs_plonk_pk_from_zkey": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
     "cs_plonk_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
                                        C.c_void_p, C.c_void_p]),
@@ -481,6 +482,13 @@ class PlonkKey:
         self.h, self.n_public, self.n_witness = h, npub.value, nwit.value
         self.fq = limbs_of(curve, "fq")
         return self
+
+    def info(self):
+        """-> (n_public, n_witness, domain_size, vk_points [8, 2*fq])."""
+        a, b, c = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        vk = np.zeros((8, 2 * self.fq), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_plonk_pk_info(self.h, C.byref(a), C.byref(b), C.byref(c), _ptr(vk)))
+        return a.value, b.value, c.value, vk
 
     def prove_plain(self, public_inputs, witness, blinders_mont):
         """Plonk::plain_prove -> (points [9, 2*fq] A B C Z T1 T2 T3 Wxi Wxiw, evals [6, 4] a b c s1 s2 zw), Montgomery."""

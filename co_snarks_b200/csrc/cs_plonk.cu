@@ -865,6 +865,15 @@ void cs_plonk_pk_free(cs_plonk_pk* pk) {
   delete pk;
 }
 
+int cs_plonk_pk_info(const cs_plonk_pk* pk, size_t* n_public, size_t* n_witness, size_t* domain_size, uint64_t* vk_points) {
+  if (!pk) return fail(CS_ERR_ARG, "cs_plonk_pk_info: NULL key");
+  if (n_public) *n_public = pk->n_public;
+  if (n_witness) *n_witness = (size_t)pk->n_vars - pk->n_additions - pk->n_public - 1;
+  if (domain_size) *domain_size = pk->n;
+  if (vk_points) memcpy(vk_points, pk->vk_points.data(), pk->vk_points.size() * 8);
+  return 0;
+}
+
 int cs_keccak256(const uint8_t* data, size_t len, uint8_t* out32) {
   if ((len && !data) || !out32) return fail(CS_ERR_ARG, "cs_keccak256: NULL argument");
   std::vector<uint8_t> v(data, data + len);

@@ -328,6 +328,9 @@ int cs_plonk_pk_create(cs_ctx* ctx, const cs_plonk_key_desc* desc, cs_plonk_pk**
  * out_n_witness = number of private witness values a proof takes (nVars - nAdditions - nPublic - 1). */
 int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size_t* out_n_public, size_t* out_n_witness);
 void cs_plonk_pk_free(cs_plonk_pk* pk);
+/* what a driver needs to know about an uploaded key: counts and the eight verification-key commitments
+ * (Qm Ql Qr Qo Qc S1 S2 S3, affine Montgomery) that open the transcript; any output pointer may be NULL */
+int cs_plonk_pk_info(const cs_plonk_pk* pk, size_t* n_public, size_t* n_witness, size_t* domain_size, uint64_t* vk_points);
 /* One proof.  h_public_inputs: n_public + 1 values as in SharedWitness.public_inputs (entry 0, the constant one,
  * is replaced by zero like types.rs:118-120); h_witness: the remaining n_vars - n_additions - n_public - 1
  * values; h_blinders_mont: the 11 round-1 blinding scalars b[0..11) (Round1Challenges, round1.rs:45-47) -- the

@@ -75,6 +75,68 @@ def _build_and_run(tmp_path, lib_path):
     assert "checks passed" in out.stdout
 
 
+def _write_plonk_fixture(tmp_path, name="multiplier2"):
+    """-> (zkey path, fixture path): witness, the golden proof for b = [0..11), replicated shares of both."""
+    import zkey_writer
+    from helpers import golden_plonk, plonk_proof_from_json
+    cv = Conv("bn254")
+    z, w, g = golden_plonk(name)
+    npub = z["n_public"]
+    zp, fx = str(tmp_path / "plonk.zkey"), str(tmp_path / "plonk_fixture.bin")
+    zkey_writer.write_plonk_zkey(zp, z)
+    exp = plonk_proof_from_json(g["oracle_proof_deterministic_blinders"])
+    rng = random.Random(61)
+
+    def shares_of(vals):
+        out = [[], [], []]
+        for v in vals:
+            s0, s1 = rng.randrange(cv.r), rng.randrange(cv.r)
+            sh = [s0, s1, (v - s0 - s1) % cv.r]
+            for p in range(3):
+                out[p] += [sh[p], sh[(p + 2) % 3]]
+        return out
+    with open(fx, "wb") as f:
+        def frvec(vals, per=1):
+            a = cv.fr(vals)
+            f.write(struct.pack("<Q", a.shape[0] // per))
+            f.write(a.tobytes())
+        frvec(w[:npub + 1])
+        frvec(w[npub + 1:])
+        pts = cv.g1([exp[k] for k in ("a", "b", "c", "z", "t1", "t2", "t3", "wxi", "wxiw")])
+        f.write(struct.pack("<Q", 9))
+        f.write(pts.tobytes())
+        frvec([exp[k] for k in ("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw")])
+        for part in shares_of(w[npub + 1:]):
+            frvec(part, 2)
+        for part in shares_of(list(range(11))):
+            frvec(part, 2)
+    return zp, fx
+
+
+def _build_and_run_plonk(tmp_path, lib_path):
+    zp, fx = _write_plonk_fixture(tmp_path)
+    exe = str(tmp_path / "test_co_plonk")
+    libdir, libname = os.path.dirname(lib_path), os.path.basename(lib_path)
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "test_co_plonk.cpp"), "-o", exe,
+                           "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe, zp, fx], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "checks passed" in out.stdout
+
+
+def test_cpp_plonk_mirror_on_emulated_kernels(tmp_path):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    _build_and_run_plonk(tmp_path, build_emu.build())
+
+
+@pytest.mark.gpu
+def test_cpp_plonk_mirror_on_gpu(tmp_path):
+    from co_snarks_b200 import binding as B
+    _build_and_run_plonk(tmp_path, B.DEFAULT_LIB)
+
+
 def test_cpp_mirror_on_emulated_kernels(tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
