@@ -108,6 +108,7 @@ SIGNATURES = {
     "cs_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cs_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cs_plonk_pk_create": (C.c_int, [C.c_void_p, C.POINTER(PlonkKeyDesc), C.POINTER(C.c_void_p)]),
+    "cs_bases_from_crs_file": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]),
     "cs_plonk_pk_free": (None, [C.c_void_p]),
     "cs_plonk_pk_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t), C.c_void_p]),
     "cs_plonk_pk_from_zkey": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]),
@@ -277,6 +278,12 @@ class Context:
         self._check(self.lib.cs_bases_upload(self.h, curve, group, _ptr(points_mont), points_mont.shape[0],
                                              window_bits, C.byref(h)))
         return Bases(self, h, curve, group)
+
+    def bases_from_crs_file(self, path, n, offset=0, window_bits=0):
+        """Ignition CRS file (bn254_g1.dat layout) -> device base set (cs_bases_from_crs_file)."""
+        h = C.c_void_p()
+        self._check(self.lib.cs_bases_from_crs_file(self.h, str(path).encode(), offset, n, window_bits, C.byref(h)))
+        return Bases(self, h, CS_BN254, CS_G1)
 
     def msm(self, bases, scalars, offset=0, n=None, montgomery=True, device=False):
         plimbs = limbs_of(bases.curve, "fq") * (2 if bases.group == CS_G1 else 4)

@@ -266,6 +266,30 @@ int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size
   return cs_plonk_pk_create(ctx, &k, out);
 }
 
+// Barretenberg / Ignition CRS file (co-noir/co-noir-common/src/crs/parse.rs:93-101,154-158; bn254_g1.dat):
+// 64 bytes per G1 point, x then y, BIG-endian canonical -- byte-swapped into little-endian limbs, converted to
+// Montgomery on the host and uploaded as a base set for cs_msm (the UltraHonk commitment MSMs).
+int cs_bases_from_crs_file(cs_ctx* ctx, const char* path, size_t offset, size_t n, int window_bits, cs_bases** out) {
+  if (!ctx || !path || !out) return fail(CS_ERR_ARG, "cs_bases_from_crs_file: NULL argument");
+  if (n == 0) return fail(CS_ERR_ARG, "cs_bases_from_crs_file: empty base set");
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return fail(CS_ERR_ARG, "cannot open %s", path);
+  const size_t sz = (size_t)f.tellg();
+  if ((offset + n) * 64 > sz) return fail(CS_ERR_ARG, "%s: holds %zu points, %zu + %zu requested", path, sz / 64, offset, n);
+  std::vector<uint8_t> raw(n * 64);
+  f.seekg((std::streamoff)(offset * 64));
+  if (!f.read((char*)raw.data(), (std::streamsize)raw.size())) return fail(CS_ERR_ARG, "cannot read %s", path);
+  std::vector<uint64_t> canon(n * 8), mont(n * 8);
+  for (size_t i = 0; i < 2 * n; i++)      // each 32-byte coordinate: reverse the bytes
+    for (int l = 0; l < 4; l++) {
+      uint64_t v = 0;
+      for (int b = 0; b < 8; b++) v = (v << 8) | raw[i * 32 + (3 - l) * 8 + b];
+      canon[i * 4 + l] = v;
+    }
+  CS_TRY(cs_fq_to_mont(CS_BN254, canon.data(), mont.data(), 2 * n));
+  return cs_bases_upload(ctx, CS_BN254, CS_G1, mont.data(), n, window_bits, out);
+}
+
 int cs_wtns_read(const char* path, cs_curve curve, uint64_t* out_mont, size_t capacity, size_t* out_n) {
   if (!path || !out_n) return fail(CS_ERR_ARG, "cs_wtns_read: NULL argument");
   Sections w;

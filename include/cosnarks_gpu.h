@@ -324,6 +324,9 @@ typedef struct {
   size_t n_p_tau;
 } cs_plonk_key_desc;
 int cs_plonk_pk_create(cs_ctx* ctx, const cs_plonk_key_desc* desc, cs_plonk_pk** out);
+/* Base set straight from a Barretenberg / Ignition CRS file (co-noir/co-noir-common/src/crs/parse.rs:93-101,
+ * 154-158: 64 B per G1 point, x then y, big-endian canonical): points [offset, offset + n) become a cs_bases. */
+int cs_bases_from_crs_file(cs_ctx* ctx, const char* path, size_t offset, size_t n, int window_bits, cs_bases** out);
 /* The same straight from a snarkjs Plonk .zkey (circom_types::plonk::Zkey::from_reader, co-circom.rs:1053-1060);
  * out_n_witness = number of private witness values a proof takes (nVars - nAdditions - nPublic - 1). */
 int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size_t* out_n_public, size_t* out_n_witness);

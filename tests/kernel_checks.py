@@ -178,6 +178,34 @@ def check_msm_crs(ctx):
     bases.free()
 
 
+def check_crs_file_ingest(ctx, tmp_path):
+    """cs_bases_from_crs_file on a file in the bn254_g1.dat layout (64 B/point, big-endian canonical;
+    co-noir-common/src/crs/parse.rs:93-101) written from the golden Ignition points: MSM == oracle, with an offset."""
+    import os
+    cv = Conv("bn254")
+    g = load_golden("crs_bn254_g1_first1024")
+    pts = [gp1(P) for P in g["points"]][:300]
+    path = os.path.join(str(tmp_path), "g1.dat")
+    with open(path, "wb") as f:
+        for x, y in pts:
+            f.write(x.to_bytes(32, "big") + y.to_bytes(32, "big"))
+    rng = random.Random(12)
+    for off, n in ((0, 300), (7, 200)):
+        bases = ctx.bases_from_crs_file(path, n, off)
+        sc = [rng.randrange(cv.r) for _ in range(n)]
+        out, _ = ctx.msm(bases, cv.fr(sc))
+        assert cv.pt1(out) == og1(BN254).msm(pts[off:off + n], sc)
+        bases.free()
+    with pytest.raises(RuntimeError):
+        ctx.bases_from_crs_file(path, 400)  # more points than the file holds
+    ref = "/root/reference/co-noir/co-noir-common/src/crs/bn254_g1.dat"
+    if os.path.exists(ref):  # the real file, when mounted: first point is the generator
+        bases = ctx.bases_from_crs_file(ref, 64)
+        out, _ = ctx.msm(bases, cv.fr([1] + [0] * 63))
+        assert cv.pt1(out) == (1, 2)
+        bases.free()
+
+
 def check_fixed_base_mul(ctx, n=40):
     cv = Conv("bn254")
     rng = random.Random(6)

@@ -135,3 +135,7 @@ def test_plonk_prove_bls12_381(emu_ctx):
 def test_plonk_zkey_ingest(emu_ctx, tmp_path):
     K.check_plonk_zkey_ingest(emu_ctx, tmp_path, "multiplier2")
     K.check_plonk_zkey_ingest(emu_ctx, tmp_path, "multiplier2", curve="bls12_381")
+
+
+def test_crs_file_ingest(emu_ctx, tmp_path):
+    K.check_crs_file_ingest(emu_ctx, tmp_path)
