@@ -199,10 +199,11 @@ int bases_upload_t(cs_ctx* ctx, const uint64_t* h_points, size_t n, int window_b
 
 template <class Cfg, int G>
 int msm_enqueue_t(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,
-                  const uint32_t* d_scalars, unsigned sstride, size_t n, int mont) {
+                  const uint32_t* d_scalars, unsigned sstride, size_t n, int mont, int sort_slot) {
   typedef typename GroupOf<Cfg, G>::F F;
   return msm_enqueue<F, typename Cfg::FrP>(ctx->msm_ws[slot], b->table.as<Affine<F>>(), b->infmask.as<uint32_t>(), (uint32_t)b->n, b->sh,
-                                           (uint32_t)offset, d_scalars, sstride, (uint32_t)n, mont, st);
+                                           (uint32_t)offset, d_scalars, sstride, (uint32_t)n, mont, st,
+                                           sort_slot >= 0 ? &ctx->msm_ws[sort_slot] : nullptr);
 }
 
 // After the stream has drained: XYZZ (pinned) -> affine on the host.
@@ -216,13 +217,25 @@ void msm_finish_t(cs_ctx* ctx, int slot, uint64_t* out_affine, int* out_inf) {
 }
 
 int msm_enqueue_dyn(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,
-                    const uint32_t* d_scalars, unsigned sstride, size_t n, int mont) {
+                    const uint32_t* d_scalars, unsigned sstride, size_t n, int mont, int sort_slot) {
   CS_DISPATCH_CURVE(b->curve, {
-    if (b->group == CS_G1) return msm_enqueue_t<Cfg, 0>(ctx, slot, st, b, offset, d_scalars, sstride, n, mont);
-    return msm_enqueue_t<Cfg, 1>(ctx, slot, st, b, offset, d_scalars, sstride, n, mont);
+    if (b->group == CS_G1) return msm_enqueue_t<Cfg, 0>(ctx, slot, st, b, offset, d_scalars, sstride, n, mont, sort_slot);
+    return msm_enqueue_t<Cfg, 1>(ctx, slot, st, b, offset, d_scalars, sstride, n, mont, sort_slot);
   });
   return 0;
 }
+int bases_sort_compatible(cs_ctx* ctx, const cs_bases* a, const cs_bases* b, bool* out) {
+  *out = false;
+  if (!a || !b || a->curve != b->curve || a->n != b->n || a->sh.c != b->sh.c || a->sh.W != b->sh.W) return 0;
+  const size_t words = (a->n + 31) / 32;
+  std::vector<uint32_t> ma(words), mb(words);
+  CS_CUDA(cudaMemcpyAsync(ma.data(), a->infmask.p, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaMemcpyAsync(mb.data(), b->infmask.p, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  *out = ma == mb;
+  return 0;
+}
+
 int msm_finish_dyn(cs_ctx* ctx, int slot, const cs_bases* b, uint64_t* out_affine, int* out_inf) {
   CS_DISPATCH_CURVE(b->curve, {
     if (b->group == CS_G1) msm_finish_t<Cfg, 0>(ctx, slot, out_affine, out_inf);

@@ -25,6 +25,7 @@ struct cs_groth16_pk {
   // LibSnarkReduction (reduction.rs:241-342): C matrix, arkworks domain, coset = GENERATOR
   DevBuf c_rowptr, c_col, c_coeff;
   bool have_c = false;
+  bool share_b_sort = false;  // B1 and B2 sort identically (same infinity pattern): B2 reuses B1's sorted entries
   cs_domain* dom_ark = nullptr;
   DevBuf coset_tab_ark, ginv_pows, vinv_over_n;
 };
@@ -268,7 +269,9 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
     // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
     if (do_a) CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
     if (do_b1) CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
-    if (do_b2) CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1));
+    if (do_b2)
+      CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1,
+                             (do_b1 && pk->share_b_sort) ? 1 : -1));
     if (do_l) CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
   }
   if (do_h) {
@@ -430,6 +433,11 @@ int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* d, cs_groth16_p
   CS_TRY(cs_bases_upload(ctx, d->curve, CS_G2, d->b_g2_query, d->b_g2_query_len, wb, &pk->b_g2));
   if (nw) CS_TRY(cs_bases_upload(ctx, d->curve, CS_G1, d->l_query, d->l_query_len, wb, &pk->l_query));
   CS_TRY(cs_bases_upload(ctx, d->curve, CS_G1, d->h_query, n, wb, &pk->h_query));
+  {
+    static int share_env = -1;  // CS_SHARE_B_SORT=0 disables the shared sort (A/B comparison)
+    if (share_env < 0) { const char* e = getenv("CS_SHARE_B_SORT"); share_env = e ? atoi(e) : 1; }
+    if (share_env) CS_TRY(bases_sort_compatible(ctx, pk->b_g1, pk->b_g2, &pk->share_b_sort));
+  }
   switch (d->curve) {
     case CS_BN254: CS_TRY(build_coset_table<Bn254Cfg>(ctx, pk.get())); break;
 #if defined(CS_ENABLE_BLS12_381)

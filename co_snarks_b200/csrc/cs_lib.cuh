@@ -77,8 +77,12 @@ namespace cs {
 std::atomic<uint64_t>& launch_counter();
 int ctx_fork(cs_ctx* ctx, int nside);
 int ctx_join(cs_ctx* ctx, int nside);
+// sort_slot >= 0: reuse the sorted entries of the MSM last enqueued in that workspace slot (same scalars, same
+// table geometry and infinity pattern -- see msm_enqueue)
 int msm_enqueue_dyn(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, size_t offset,
-                    const uint32_t* d_scalars, unsigned sstride, size_t n, int mont);
+                    const uint32_t* d_scalars, unsigned sstride, size_t n, int mont, int sort_slot = -1);
+// both base sets sort identically for equal scalars: same length, window shape and infinity mask
+int bases_sort_compatible(cs_ctx* ctx, const cs_bases* a, const cs_bases* b, bool* out);
 int msm_finish_dyn(cs_ctx* ctx, int slot, const cs_bases* b, uint64_t* out_affine, int* out_inf);
 int ntt_run(cs_ctx* ctx, const cs_domain* d, uint32_t* d_data, unsigned batch, bool inverse_in_to_out,
             const uint32_t* d_post, cudaStream_t st);

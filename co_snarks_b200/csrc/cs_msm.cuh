@@ -462,6 +462,8 @@ struct MsmWorkspace {
   size_t h_result_cap = 0;
   bool profile = false;      // record CUDA events at the stage boundaries (bench.py roofline)
   cudaEvent_t ev[MSM_NSTAGE + 1] = {};
+  cudaEvent_t sorted_ev = nullptr;  // recorded once the sorted entries / slice order of this MSM are final
+  bool sorted_ev_made = false, sorted_once = false;
   int mark(int i, cudaStream_t st) {
     if (!profile) return 0;
     if (!ev[i]) CS_CUDA(cudaEventCreateWithFlags(&ev[i], 0));
@@ -473,6 +475,9 @@ struct MsmWorkspace {
       if (ev[i]) cudaEventDestroy(ev[i]);
       ev[i] = nullptr;
     }
+    if (sorted_ev_made) cudaEventDestroy(sorted_ev);
+    sorted_ev = nullptr;
+    sorted_ev_made = sorted_once = false;
     dig.release(); sorted.release(); meta.release(); part0.release(); part1.release(); part2.release();
     bucket.release(); red.release(); scal.release(); result.release(); order.release();
     if (h_result) cudaFreeHost(h_result);
@@ -483,10 +488,15 @@ struct MsmWorkspace {
 
 // Enqueue one MSM on `st`.  d_scalars: device, n elements of Fr (8 x u32).  The XYZZ result lands in
 // ws.h_result (pinned) after the stream drains.
+// sort_from (optional): another workspace whose MSM was enqueued over the SAME scalars with the same table
+// geometry (nbases, offset, n, window) and the same infinity pattern -- Groth16's B1 / B2 pair.  Its sorted
+// entries and slice order are reused (they index table slots, not points), so this MSM starts at the
+// accumulation; `st` waits for that workspace's sort to finish.
 template <class F, class FrP>
 int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmask, uint32_t nbases, MsmShape sh,
                 uint32_t offset,
-                const uint32_t* d_scalars, uint32_t sstride, uint32_t n, int mont, cudaStream_t st) {
+                const uint32_t* d_scalars, uint32_t sstride, uint32_t n, int mont, cudaStream_t st,
+                MsmWorkspace* sort_from = nullptr) {
   const uint32_t nb1 = sh.B + 1;
   const size_t nent = (size_t)sh.W * n;
   if (nent >= (1ull << 31) || (size_t)sh.W * nbases >= (1ull << 31))
@@ -495,11 +505,14 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   const size_t max_s0 = nent / S + nb1;
   const size_t max_s1 = max_s0 / S + nb1;
   const size_t max_s2 = max_s1 / S + nb1;
-  CS_TRY(ws.dig.reserve(nent * 4));
-  CS_TRY(ws.sorted.reserve(nent * 4));
+  MsmWorkspace& so = sort_from ? *sort_from : ws;  // owner of the sort buffers
   // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1] sstart2[nb1+1]
   const size_t meta_words = 2 * (size_t)nb1 + 4 * ((size_t)nb1 + 1);
-  CS_TRY(ws.meta.reserve(meta_words * 4));
+  if (!sort_from) {
+    CS_TRY(ws.dig.reserve(nent * 4));
+    CS_TRY(ws.sorted.reserve(nent * 4));
+    CS_TRY(ws.meta.reserve(meta_words * 4));
+  }
   CS_TRY(ws.part0.reserve(max_s0 * sizeof(Xyzz<F>)));
   CS_TRY(ws.part1.reserve(max_s1 * sizeof(Xyzz<F>)));
   CS_TRY(ws.part2.reserve(max_s2 * sizeof(Xyzz<F>)));
@@ -514,42 +527,55 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   const uint32_t ob = ceil_div(max_s0, MSM_ORDER_BLOCK);
   const size_t order_words = 4 * max_s0 + (size_t)ob * (MSM_SLICE_MAX + 1) + 2 * (MSM_SLICE_MAX + 1) +
                              (size_t)(MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS;
-  CS_TRY(ws.order.reserve(order_words * 4));
+  if (!sort_from) CS_TRY(ws.order.reserve(order_words * 4));
   if (ws.h_result_cap < sizeof(Xyzz<F>)) {
     if (ws.h_result) cudaFreeHost(ws.h_result);
     CS_CUDA(cudaMallocHost(&ws.h_result, sizeof(Xyzz<F>)));
     ws.h_result_cap = sizeof(Xyzz<F>);
   }
-  uint32_t* slice_len = ws.order.as<uint32_t>();
+  uint32_t* slice_len = so.order.as<uint32_t>();
   uint32_t* slice_bkt = slice_len + max_s0;
   uint32_t* order = slice_bkt + max_s0;
   uint32_t* order_b = order + max_s0;
   uint32_t* block_hist = order_b + max_s0;
   uint32_t* len_base = block_hist + (size_t)ob * (MSM_SLICE_MAX + 1);
   uint32_t* chunk_sum = len_base + 2 * (MSM_SLICE_MAX + 1);
-  uint32_t* count = ws.meta.as<uint32_t>();
+  uint32_t* count = so.meta.as<uint32_t>();
   uint32_t* cursor = count + nb1;
   uint32_t* start = cursor + nb1;
   uint32_t* sstart0 = start + nb1 + 1;
   uint32_t* sstart1 = sstart0 + nb1 + 1;
   uint32_t* sstart2 = sstart1 + nb1 + 1;
-  CS_TRY(ws.mark(0, st));
-  CS_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nb1 * 4, st));
-  CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W, infmask, offset,
-            ws.dig.as<uint32_t>(), count);
-  CS_TRY(ws.mark(1, st));
-  CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, S, start, sstart0, sstart1, sstart2);
-  CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
-            offset, start, cursor, ws.sorted.as<uint32_t>());
-  CS_LAUNCH_SYNC(k_msm_slice_hist, ob, MSM_ORDER_BLOCK, 0, st, count, sstart0, nb1, S, slice_len, slice_bkt, block_hist);
-  {
-    const uint32_t nt = (MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS;
-    CS_LAUNCH(k_msm_slice_off1, ceil_div(nt, 128), 128, 0, st, block_hist, ob, chunk_sum);
-    CS_LAUNCH(k_msm_slice_off2, 1, 128, 0, st, chunk_sum, len_base);
-    CS_LAUNCH(k_msm_slice_off3, ceil_div(nt, 128), 128, 0, st, block_hist, ob, chunk_sum, len_base);
+  if (sort_from) {
+    if (!sort_from->sorted_once) return fail(-1, "msm: the workspace to share a sort with has not been enqueued");
+    CS_TRY(ws.mark(0, st));
+    CS_CUDA(cudaStreamWaitEvent(st, sort_from->sorted_ev, 0));
+    CS_TRY(ws.mark(1, st));
+  } else {
+    CS_TRY(ws.mark(0, st));
+    CS_CUDA(cudaMemsetAsync(count, 0, 2 * (size_t)nb1 * 4, st));
+    CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W, infmask, offset,
+              ws.dig.as<uint32_t>(), count);
+    CS_TRY(ws.mark(1, st));
+    CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, S, start, sstart0, sstart1, sstart2);
+    CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
+              offset, start, cursor, ws.sorted.as<uint32_t>());
+    CS_LAUNCH_SYNC(k_msm_slice_hist, ob, MSM_ORDER_BLOCK, 0, st, count, sstart0, nb1, S, slice_len, slice_bkt, block_hist);
+    {
+      const uint32_t nt = (MSM_SLICE_MAX + 1) * MSM_OFF_CHUNKS;
+      CS_LAUNCH(k_msm_slice_off1, ceil_div(nt, 128), 128, 0, st, block_hist, ob, chunk_sum);
+      CS_LAUNCH(k_msm_slice_off2, 1, 128, 0, st, chunk_sum, len_base);
+      CS_LAUNCH(k_msm_slice_off3, ceil_div(nt, 128), 128, 0, st, block_hist, ob, chunk_sum, len_base);
+    }
+    CS_LAUNCH_SYNC(k_msm_slice_order, ob, MSM_ORDER_BLOCK, 0, st, slice_len, slice_bkt, (uint32_t)max_s0, sstart0, nb1,
+                   block_hist, len_base, order, order_b);
+    if (!ws.sorted_ev_made) {
+      CS_CUDA(cudaEventCreateWithFlags(&ws.sorted_ev, cudaEventDisableTiming));
+      ws.sorted_ev_made = true;
+    }
+    CS_CUDA(cudaEventRecord(ws.sorted_ev, st));
+    ws.sorted_once = true;
   }
-  CS_LAUNCH_SYNC(k_msm_slice_order, ob, MSM_ORDER_BLOCK, 0, st, slice_len, slice_bkt, (uint32_t)max_s0, sstart0, nb1,
-                 block_hist, len_base, order, order_b);
   CS_TRY(ws.mark(2, st));
   {
     // resident blocks per SM (register cap) -- tuned on B200, overridable for experiments
@@ -557,7 +583,7 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
     if (minb_env < 0) { const char* e = getenv("CS_ACCUM0_MINB"); minb_env = e ? atoi(e) : 0; }
     const int minb = minb_env ? minb_env : (sizeof(F) > 32 ? 3 : 4);
 #define CS_ACC0(M)                                                                                              \
-  CS_LAUNCH(k_msm_accum0<F COMMA M>, ceil_div(max_s0, 128), 128, 0, st, table, ws.sorted.as<uint32_t>(), count, \
+  CS_LAUNCH(k_msm_accum0<F COMMA M>, ceil_div(max_s0, 128), 128, 0, st, table, so.sorted.as<uint32_t>(), count, \
             start, sstart0, nb1, S, order, order_b, ws.part0.as<Xyzz<F>>())
     switch (minb) {
       case 2: CS_ACC0(2); break;
