@@ -11,6 +11,10 @@ configs[1]: plain prover, 1xB200): witness map (2 SpMV, 6 NTT of 2^20, 3 element
           collective), barrier + max over ranks, value = N*K / t      ("scaling": "weak")
   --impl reference : the oracle's C restatement of the reference CPU path (oracle/c) on the host cores.
 Prints ONE JSON line on rank 0.
+
+oracle/ is used here only as the checker and the CPU baseline, never inside a timed region and never by the
+product: before timing, rank 0 has the oracle's pairing verifier accept one GPU proof (the "proof
+pairing-verified" flag in `data`), and the cpu_baseline / --impl reference legs time oracle/c on the host.
 """
 import argparse
 import json
