@@ -339,7 +339,9 @@ int cs_plonk_pk_info(const cs_plonk_pk* pk, size_t* n_public, size_t* n_witness,
  * values; h_blinders_mont: the 11 round-1 blinding scalars b[0..11) (Round1Challenges, round1.rs:45-47) -- the
  * caller draws them, which is what makes proofs reproducible against the oracle / the reference's KATs.
  * out_points: 9 G1 affine points A B C Z T1 T2 T3 Wxi Wxiw; out_evals: eval_a eval_b eval_c eval_s1 eval_s2
- * eval_zw (PlonkProof, round5.rs:50-70).  Errors mirror PlonkProofError (lib.rs:40-69). */
+ * eval_zw (PlonkProof, round5.rs:50-70).  Errors mirror PlonkProofError (lib.rs:40-69).
+ * The key object owns the per-proof workspace: one proof at a time per cs_plonk_pk (use one key object per
+ * concurrent prover thread; Rep3 sessions carry their own workspace and may share a key). */
 int cs_plonk_prove_plain(cs_ctx* ctx, cs_plonk_pk* pk, const uint64_t* h_public_inputs, size_t n_public_inputs,
                          const uint64_t* h_witness, size_t n_witness, const uint64_t* h_blinders_mont,
                          uint64_t* out_points, uint64_t* out_evals);
