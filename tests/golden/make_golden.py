@@ -26,7 +26,7 @@ from oracle import formats as F  # noqa: E402
 from oracle import groth16 as OG  # noqa: E402
 from oracle.fields import roots_of_unity  # noqa: E402
 from oracle.ntt import ifft  # noqa: E402
-from oracle.pairing_bn254 import groth16_verify  # noqa: E402
+from oracle.pairing_bn254 import groth16_verify as groth16_verify_bn254  # noqa: E402
 from oracle.plonk_round1 import round1_commitments  # noqa: E402
 
 REF = "/root/reference"
@@ -56,8 +56,11 @@ def dump(name, obj, compress=False):
     print(path, os.path.getsize(path))
 
 
-def groth16_fixture(name, r_s_list, compress):
-    base = "%s/test_vectors/Groth16/bn254/%s/" % (REF, name)
+def groth16_fixture(name, r_s_list, compress, curve_dir="bn254"):
+    groth16_verify = groth16_verify_bn254
+    if curve_dir == "bls12_381":
+        from oracle.pairing_bls12_381 import groth16_verify
+    base = "%s/test_vectors/Groth16/%s/%s/" % (REF, curve_dir, name)
     z = F.read_groth16_zkey(base + "circuit.zkey")
     m = F.zkey_matrices(z)
     _, w = F.read_wtns(base + "witness.wtns")
@@ -70,11 +73,11 @@ def groth16_fixture(name, r_s_list, compress):
         pr = OG.prove_plain(z, m, w, r_, s_)
         assert groth16_verify(vk, pub, pr), "oracle proof must verify"
         proofs.append(dict(r=hx(r_), s=hx(s_), a=p1(pr[0]), b=p2(pr[1]), c=p1(pr[2]),
-                           json=F.proof_to_json(*pr)))
+                           json=F.proof_to_json(*pr, "bn128" if curve_dir == "bn254" else "bls12381")))
     ni = m["num_instance_variables"]
     h = OG.witness_map_plain(m, w[:ni], w[ni:], z["r"], z["curve"].two_adicity)
     obj = dict(
-        source="test_vectors/Groth16/bn254/%s" % name, curve="bn254",
+        source="test_vectors/Groth16/%s/%s" % (curve_dir, name), curve=curve_dir,
         n_vars=z["n_vars"], n_public=z["n_public"], domain_size=z["domain_size"],
         num_constraints=m["num_constraints"], num_instance_variables=ni,
         num_witness_variables=m["num_witness_variables"],
@@ -90,7 +93,7 @@ def groth16_fixture(name, r_s_list, compress):
         snarkjs_proof=dict(a=p1(sp[0]), b=p2(sp[1]), c=p1(sp[2])),
         h=[hx(x) for x in h], oracle_proofs=proofs,
     )
-    dump("groth16_bn254_" + name, obj, compress)
+    dump("groth16_%s_%s" % (curve_dir, name), obj, compress)
 
 
 def plonk_fixture(curve_dir, name, expected, compress):
@@ -242,3 +245,4 @@ if __name__ == "__main__":
     plonk_full_fixture("multiplier2", False)
     plonk_full_fixture("poseidon", True)
     plonk_full_fixture("multiplier2", False, "bls12_381")
+    groth16_fixture("multiplier2", [(0, 0), (11, 13)], False, "bls12_381")

@@ -82,10 +82,10 @@ class Conv:
         return (np.array(rp, dtype=np.uint32), np.array(col, dtype=np.uint32), self.fr(cf))
 
 
-def golden_groth16(name):
+def golden_groth16(name, curve="bn254"):
     """-> (zkey-like dict, matrices dict, witness ints, golden json) in the oracle's conventions."""
-    g = load_golden("groth16_bn254_" + name)
-    z = dict(curve=CURVES["bn254"], q=CURVES["bn254"].q, r=CURVES["bn254"].r, n_vars=g["n_vars"],
+    g = load_golden("groth16_%s_%s" % (curve, name))
+    z = dict(curve=CURVES[curve], q=CURVES[curve].q, r=CURVES[curve].r, n_vars=g["n_vars"],
              n_public=g["n_public"], domain_size=g["domain_size"])
     for k in ("alpha_g1", "beta_g1", "delta_g1"):
         z[k] = gp1(g[k])

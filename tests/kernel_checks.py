@@ -242,10 +242,13 @@ def check_plonk_round1_kat(ctx, curve="bn254", name="multiplier2"):
     dom.free()
 
 
-def check_groth16_fixture(ctx, name, rep3=True, window_bits=0):
-    cv = Conv("bn254")
+def check_groth16_fixture(ctx, name, rep3=True, window_bits=0, curve="bn254"):
+    cv = Conv(curve)
     r = cv.r
-    z, m, w, g = golden_groth16(name)
+    z, m, w, g = golden_groth16(name, curve)
+    verify = groth16_verify
+    if curve == "bls12_381":
+        from oracle.pairing_bls12_381 import groth16_verify as verify
     ni = m["num_instance_variables"]
     pk = make_key(ctx, cv, z, m, window_bits)
     assert pk.domain_size() == g["domain_size"]
@@ -258,8 +261,9 @@ def check_groth16_fixture(ctx, name, rep3=True, window_bits=0):
         A, Bp, Cp = pk.prove_plain(pub, wit, cv.fr([ih(pr["r"])]), cv.fr([ih(pr["s"])]))
         proof = (cv.pt1(A), cv.pt2(Bp), cv.pt1(Cp))
         from oracle.formats import proof_to_json
-        assert proof_to_json(*proof) == pr["json"], "proof bytes differ from the oracle for fixed (r, s)"
-        assert groth16_verify(vk, public, proof)
+        assert proof_to_json(*proof, "bn128" if curve == "bn254" else "bls12381") == pr["json"], \
+            "proof bytes differ from the oracle for fixed (r, s)"
+        assert verify(vk, public, proof)
     if rep3:
         check_groth16_rep3_local(ctx, pk, cv, z, m, w, h_exp, vk, public)
     pk.free()

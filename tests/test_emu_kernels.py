@@ -139,3 +139,9 @@ def test_plonk_zkey_ingest(emu_ctx, tmp_path):
 
 def test_crs_file_ingest(emu_ctx, tmp_path):
     K.check_crs_file_ingest(emu_ctx, tmp_path)
+
+
+def test_emu_groth16_bls12_381(emu_ctx):
+    """Groth16 on BLS12-381 (6-limb Fq, 255-bit Fr): witness map and proof bytes == oracle on the reference's
+    bls12_381/multiplier2 fixture, proof accepted by the BLS12-381 pairing check under the snarkjs key."""
+    K.check_groth16_fixture(emu_ctx, "multiplier2", rep3=False, curve="bls12_381")

@@ -132,3 +132,31 @@ def test_plonk_poseidon_snarkjs_proof_and_oracle_proof_verify():
     pr = OP.prove(z, w)
     assert F.plonk_proof_to_json(pr) == g["oracle_proof_json"]
     assert OP.verify(BN254, vk, pr, public, pairing_product_is_one)
+
+
+def test_bls12_381_fixtures_verify():
+    """The reference's BLS12-381 acceptance tests (co-groth16/src/lib.rs:93-160, co-plonk/src/lib.rs): the snarkjs
+    Groth16 and Plonk proofs of bls12_381/multiplier2 verify under their keys with the oracle's BLS12-381 pairing,
+    tampered inputs are rejected, and the oracle's own proofs verify."""
+    from oracle import plonk as OP
+    from oracle.fields import BLS12_381
+    from oracle.pairing_bls12_381 import groth16_verify as verify_bls, pairing_product_is_one as ppio
+    z, m, w, g = golden_groth16("multiplier2", "bls12_381")
+    vk = OG.vk_from_zkey(z)
+    public = [ih(x) for x in g["public"]]
+    sp = g["snarkjs_proof"]
+    snark = (gp1(sp["a"]), gp2(sp["b"]), gp1(sp["c"]))
+    assert verify_bls(vk, public, snark)
+    assert not verify_bls(vk, [public[0] + 1] + public[1:], snark)
+    pr = g["oracle_proofs"][-1]
+    proof = OG.prove_plain(z, m, w, ih(pr["r"]), ih(pr["s"]))
+    assert F.proof_to_json(*proof, "bls12381") == pr["json"] and verify_bls(vk, public, proof)
+    zp, wp, gp = golden_plonk("multiplier2", "bls12_381")
+    vkp = plonk_vk_from_zkey(zp, gp["vk_power"])
+    pubp = [ih(x) for x in gp["public"]]
+    assert OP.verify(BLS12_381, vkp, plonk_proof_from_json(gp["snarkjs_proof"]), pubp, ppio)
+    own = OP.prove(zp, wp)
+    assert OP.verify(BLS12_381, vkp, own, pubp, ppio)
+    bad = dict(own)
+    bad["eval_b"] = (bad["eval_b"] + 1) % BLS12_381.r
+    assert not OP.verify(BLS12_381, vkp, bad, pubp, ppio)
