@@ -160,3 +160,41 @@ def test_bls12_381_fixtures_verify():
     bad = dict(own)
     bad["eval_b"] = (bad["eval_b"] + 1) % BLS12_381.r
     assert not OP.verify(BLS12_381, vkp, bad, pubp, ppio)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+def test_bls12_381_poseidon_fixtures_from_the_reference_tree():
+    """co-groth16/src/lib.rs:122-160 (poseidon on BLS12-381): the snarkjs proof verifies; the oracle's proof from the
+    fixture's zkey + witness verifies too.  Plonk: the snarkjs proof verifies (co-plonk/src/plonk.rs:332-350)."""
+    from oracle import plonk as OP
+    from oracle.fields import BLS12_381
+    from oracle.pairing_bls12_381 import groth16_verify as verify_bls, pairing_product_is_one as ppio
+    base = REF + "/test_vectors/Groth16/bls12_381/poseidon/"
+    vk = F.read_vk_json(base + "verification_key.json")
+    public = [int(x) for x in json.load(open(base + "public.json"))]
+    assert verify_bls(vk, public, F.read_proof_json(base + "circom.proof"))
+    z = F.read_groth16_zkey(base + "circuit.zkey")
+    _, w = F.read_wtns(base + "witness.wtns")
+    proof = OG.prove_plain(z, F.zkey_matrices(z), w, 1234567, 7654321)
+    assert verify_bls(vk, public, proof)
+    base = REF + "/test_vectors/Plonk/bls12_381/poseidon/"
+    pvk = F.read_plonk_vk_json(base + "verification_key.json")
+    ppub = [int(x) for x in json.load(open(base + "public.json"))]
+    assert OP.verify(BLS12_381, pvk, F.read_plonk_proof_json(base + "circom.proof"), ppub, ppio)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+def test_plonk_prover_bls12_381_poseidon_against_round1_kat_and_verifier():
+    """The full oracle prover on the BLS12-381 poseidon fixture (domain 4096): its round-1 commitments are the
+    reference's known answers (co-plonk/src/round1.rs:397-417) and the whole proof passes Plonk::verify."""
+    from oracle import plonk as OP
+    from oracle.fields import BLS12_381
+    from oracle.pairing_bls12_381 import pairing_product_is_one as ppio
+    base = REF + "/test_vectors/Plonk/bls12_381/poseidon/"
+    z = F.read_plonk_zkey(base + "circuit.zkey")
+    _, w = F.read_wtns(base + "witness.wtns")
+    pr = OP.prove(z, w)
+    g = load_golden("plonk_round1_bls12_381_poseidon")
+    assert [pr["a"], pr["b"], pr["c"]] == [gp1(P) for P in g["expected_commitments"]]
+    vk = F.read_plonk_vk_json(base + "verification_key.json")
+    assert OP.verify(BLS12_381, vk, pr, [int(x) for x in json.load(open(base + "public.json"))], ppio)
