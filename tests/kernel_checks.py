@@ -645,7 +645,7 @@ def check_plonk_synthetic(ctx, log_n, n_public=2, against_oracle=True, seed=5):
     pk.free()
 
 
-def _plonk_rep3_in_process(ctx, cv, pk, z_n, vk_points, pub, w_private, blinders, seed=23):
+def _plonk_rep3_in_process(ctx, cv, pk, z_n, vk_points, pub, w_private, blinders, seed=23, draw_blinders=False):
     """Three Rep3 co-Plonk parties in one process (LocalRep3Comm) on shares of `w_private` and of `blinders`."""
     from co_snarks_b200.plonk import LocalRep3Comm, Rep3CoPlonk
     from co_snarks_b200.rep3 import Rep3State
@@ -661,7 +661,7 @@ def _plonk_rep3_in_process(ctx, cv, pk, z_n, vk_points, pub, w_private, blinders
                 out[p] += [sh[p], sh[(p + 2) % 3]]  # party p holds (x_p, x_{p-1})  rep3.rs:281-293
         return [cv.fr(o).reshape(-1, 2, 4) for o in out]
     wsh = share(w_private)
-    bsh = share(blinders)
+    bsh = [None] * 3 if draw_blinders else share(blinders)  # None: Round1Challenges::random via T::rand (round1.rs:82-92)
     seeds = [bytes((31 * p + i) & 0xff for i in range(32)) for p in range(3)]
     provers = [Rep3CoPlonk(ctx, pk, p) for p in range(3)]
     states = [Rep3State.from_seeds(p, seeds[p], seeds[(p + 2) % 3]) for p in range(3)]
@@ -689,6 +689,24 @@ def check_plonk_rep3(ctx, name="multiplier2"):
     proofs = [plonk_proof_from_device(cv, pts, evs) for pts, evs in res]
     assert proofs[0] == proofs[1] == proofs[2]
     assert plonk_proof_to_json(proofs[0]) == g["oracle_proof_json"]
+    pk.free()
+
+
+def check_plonk_rep3_drawn_blinders(ctx, name="multiplier2"):
+    """The production path: each party draws its blinder shares from its correlated streams (arithmetic::rand).
+    All parties open the same proof and Plonk::verify accepts it."""
+    from helpers import golden_plonk, make_plonk_key, plonk_proof_from_device, plonk_vk_from_zkey
+    from oracle import plonk as OP
+    from oracle.pairing_bn254 import pairing_product_is_one
+    cv = Conv("bn254")
+    z, w, g = golden_plonk(name)
+    npub = z["n_public"]
+    pk = make_plonk_key(ctx, cv, z)
+    vkp = cv.g1([z["vk_" + k] for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")])
+    res = _plonk_rep3_in_process(ctx, cv, pk, z["domain_size"], vkp, cv.fr(w[:npub + 1]), w[npub + 1:], None, draw_blinders=True)
+    proofs = [plonk_proof_from_device(cv, pts, evs) for pts, evs in res]
+    assert proofs[0] == proofs[1] == proofs[2]
+    assert OP.verify(BN254, plonk_vk_from_zkey(z, g["vk_power"]), proofs[0], [ih(x) for x in g["public"]], pairing_product_is_one)
     pk.free()
 
 

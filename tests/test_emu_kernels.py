@@ -116,6 +116,7 @@ def test_plonk_synthetic_key(emu_ctx):
 
 def test_plonk_rep3_multiplier2(emu_ctx):
     K.check_plonk_rep3(emu_ctx, "multiplier2")
+    K.check_plonk_rep3_drawn_blinders(emu_ctx, "multiplier2")
 
 
 def test_plonk_rep3_synthetic(emu_ctx):
