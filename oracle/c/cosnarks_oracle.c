@@ -411,5 +411,7 @@ int oracle_groth16_prove_plain(const key_desc* d, const u64* pub_, const u64* wi
   return 0;
 }
 
+#include "plonk.inc"
+
 int oracle_num_threads(void) { return omp_get_max_threads(); }
 void oracle_set_threads(int n) { omp_set_num_threads(n); }

@@ -207,3 +207,45 @@ def reference_arm(log_m=20, target_log_m=20, steps=1, warmup=0):
             "config": {"workload": "plain Groth16 prover, BN254, synthetic R1CS 2^%d constraints, host CPU" % target_log_m},
             "cpu_baseline": {"value": v, "unit": "proofs/s", "cores": int(cores), "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def plonk_prove(key, public_inputs, witness, blinders_mont):
+    """oracle_plonk_prove: `key` = the dict co_snarks_b200.binding.PlonkKey takes (Montgomery numpy arrays, BN254).
+    -> (points [9, 8], evals [6, 4])."""
+    from co_snarks_b200.binding import PlonkKeyDesc, u32p, u64p  # type definition only
+    d = PlonkKeyDesc()
+    keep = []
+
+    def arr(x, dt):
+        a = np.ascontiguousarray(x, dtype=dt)
+        keep.append(a)
+        return a.ctypes.data_as(u64p if dt == np.uint64 else u32p)
+    d.curve = 0
+    for k in ("n_vars", "n_public", "domain_size", "n_additions", "n_constraints"):
+        setattr(d, k, int(key[k]))
+    d.k1_mont, d.k2_mont, d.vk_points = arr(key["k1"], np.uint64), arr(key["k2"], np.uint64), arr(key["vk_points"], np.uint64)
+    d.additions_ids, d.additions_factors = arr(key["additions_ids"], np.uint32), arr(key["additions_factors"], np.uint64)
+    for k in ("map_a", "map_b", "map_c"):
+        setattr(d, k, arr(key[k], np.uint32))
+    for i in range(5):
+        d.q_coeffs[i], d.q_evals[i] = arr(key["q_coeffs"][i], np.uint64), arr(key["q_evals"][i], np.uint64)
+    for i in range(3):
+        d.s_coeffs[i], d.s_evals[i] = arr(key["s_coeffs"][i], np.uint64), arr(key["s_evals"][i], np.uint64)
+    d.lagrange_evals = arr(key["lagrange_evals"], np.uint64)
+    pt = np.ascontiguousarray(key["p_tau"], dtype=np.uint64)
+    d.p_tau, d.n_p_tau = pt.ctypes.data_as(u64p), pt.shape[0]
+    pub = np.ascontiguousarray(public_inputs, dtype=np.uint64)
+    wit = np.ascontiguousarray(witness, dtype=np.uint64)
+    bl = np.ascontiguousarray(blinders_mont, dtype=np.uint64)
+    pts, evs = np.zeros((9, 8), dtype=np.uint64), np.zeros((6, 4), dtype=np.uint64)
+    rc = lib().oracle_plonk_prove(C.byref(d), _p(pub), _p(wit), _p(bl), _p(pts), _p(evs))
+    assert rc == 0, "oracle_plonk_prove failed (%d)" % rc
+    return pts, evs
+
+
+def time_plonk(key, public_inputs, witness, blinders_mont, reps=1):
+    """seconds per Plonk proof of the C restatement (CPU baseline of the Plonk row)."""
+    t0 = time.time()
+    for _ in range(reps):
+        plonk_prove(key, public_inputs, witness, blinders_mont)
+    return (time.time() - t0) / reps

@@ -132,10 +132,10 @@ def plonk_proof_from_json(d):
     return {k: (ih(v) if isinstance(v, str) else gp1(v)) for k, v in d.items()}
 
 
-def make_plonk_key(ctx, cv, z):
-    """oracle-style plonk zkey dict -> device PlonkKey."""
+def plonk_key_arrays(cv, z):
+    """oracle-style plonk zkey dict -> the Montgomery limb arrays of cs_plonk_key_desc."""
     na = z["n_additions"]
-    key = dict(n_vars=z["n_vars"], n_public=z["n_public"], domain_size=z["domain_size"], n_additions=na,
+    return dict(n_vars=z["n_vars"], n_public=z["n_public"], domain_size=z["domain_size"], n_additions=na,
                n_constraints=z["n_constraints"], k1=cv.fr([z["k1"]]), k2=cv.fr([z["k2"]]),
                vk_points=cv.g1([z["vk_" + k] for k in ("qm", "ql", "qr", "qo", "qc", "s1", "s2", "s3")]),
                additions_ids=np.array([[a, b] for a, b, _, _ in z["additions"]], dtype=np.uint32).reshape(na, 2),
@@ -148,7 +148,11 @@ def make_plonk_key(ctx, cv, z):
                s_evals=[cv.fr(z[k]["evals"]) for k in ("s1", "s2", "s3")],
                lagrange_evals=np.concatenate([cv.fr(P["evals"]) for P in z["lagrange"]]),
                p_tau=cv.g1(z["p_tau"]))
-    return B.PlonkKey(ctx, cv.id, key)
+
+
+def make_plonk_key(ctx, cv, z):
+    """oracle-style plonk zkey dict -> device PlonkKey."""
+    return B.PlonkKey(ctx, cv.id, plonk_key_arrays(cv, z))
 
 
 def plonk_proof_from_device(cv, pts, evs):

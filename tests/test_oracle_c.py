@@ -72,3 +72,15 @@ def test_c_groth16_equals_golden_proof(name):
         sh = cv.fr([x for ab in wsh[party] for x in ab])
         got = cv.fr_back(OC.witness_map(desc, 1, party, pub, sh, cv.fr(m1), cv.fr(m2)))
         assert got == OG.witness_map_rep3(party, m, w[:ni], wsh[party], m1, m2, cv.r, 28)
+
+
+@pytest.mark.parametrize("name", ["multiplier2", "poseidon"])
+def test_c_plonk_prover_matches_python_oracle_and_kats(name):
+    """oracle/c/plonk.inc (the CPU baseline of the Plonk row) == oracle/plonk.py == the reference's known answers."""
+    from helpers import golden_plonk, plonk_key_arrays, plonk_proof_from_device
+    from oracle.formats import plonk_proof_to_json
+    cv = Conv("bn254")
+    z, w, g = golden_plonk(name)
+    npub = z["n_public"]
+    pts, evs = OC.plonk_prove(plonk_key_arrays(cv, z), cv.fr(w[:npub + 1]), cv.fr(w[npub + 1:]), cv.fr(list(range(11))))
+    assert plonk_proof_to_json(plonk_proof_from_device(cv, pts, evs)) == g["oracle_proof_json"]

@@ -41,8 +41,15 @@ for lg in sizes:
         from oracle.pairing_bn254 import pairing_product_is_one
         proof = plonk_proof_from_device(Conv("bn254"), pts, evs)
         ok = bool(OP.verify(BN254, syn.vk_ints(), proof, syn.full_witness[1:syn.n_public + 1], pairing_product_is_one))
+    cpu = None
+    if os.environ.get("CS_PLONK_CPU", "0") == "1" and lg <= int(os.environ.get("CS_PLONK_CPU_MAX_LG", "18")):
+        # CPU baseline of the Plonk row: the C/OpenMP restatement (oracle/c/plonk.inc) on the host cores, same key
+        from oracle.c import run as OC
+        cpu_s = OC.time_plonk(syn.key, syn.public_inputs, syn.private_witness, bl, reps=1)
+        cpu = {"seconds_per_proof": round(cpu_s, 3), "cores": OC.lib().oracle_num_threads(), "kind": "port"}
     t = sum(ms[2:]) / len(ms[2:])
     out["2p%d" % lg] = {"ms_per_proof": round(t, 3), "proofs_per_s": round(1e3 / t, 2), "verified": ok,
-                        "n_additions": syn.n_additions, "setup_s": round(setup_s, 1), "launches": ctx.launch_count()}
+                        "n_additions": syn.n_additions, "setup_s": round(setup_s, 1), "launches": ctx.launch_count(),
+                        "cpu_baseline": cpu}
     pk.free()
 print(json.dumps(out))
