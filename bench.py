@@ -445,6 +445,7 @@ def run_reference(args):
         return
     from oracle.c import run as oc
     res = oc.reference_arm(log_m=args.cpu_log_m, target_log_m=args.log_m, steps=args.steps, warmup=args.warmup)
+    res["n_gpus"] = args.gpus  # the launch it mirrors (the arm itself runs on host cores only, rank 0)
     print(json.dumps(res))
 
 
