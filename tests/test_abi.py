@@ -65,3 +65,33 @@ def test_host_helpers_work_without_gpu():
     assert cv.fr_back(gen) == [eg] and cv.fr_back(shift) == [es]
     assert lib.cs_groth16_roots_of_unity(cv.id, 29, B._ptr(gen), B._ptr(shift)) != 0
     assert b"Polynomial Degree too large" in lib.cs_last_error()
+
+
+def test_argument_errors_come_back_as_codes_not_crashes():
+    """Every entry point validates its arguments before touching CUDA: NULL handles / buffers give a negative
+    code and a message through cs_last_error (no panics across the boundary)."""
+    import ctypes as C
+    import numpy as np
+    lib = B.load()
+    null = None
+    out = C.c_void_p()
+    calls = [
+        lambda: lib.cs_plonk_pk_create(null, null, C.byref(out)),
+        lambda: lib.cs_plonk_pk_from_zkey(null, b"/nonexistent.zkey", C.byref(out), null, null),
+        lambda: lib.cs_plonk_prove_plain(null, null, null, 0, null, 0, null, null, null),
+        lambda: lib.cs_plonk_rep3_create(null, null, 0, C.byref(out)),
+        lambda: lib.cs_plonk_rep3_step(null, 1, null, null),
+        lambda: lib.cs_plonk_rep3_round1(null, null, null, 0, null, 0, null, null),
+        lambda: lib.cs_rep3_mul_vec_reshare(null, 0, null, null, 4, null, null, null),
+        lambda: lib.cs_ipc_export(null, null, null),
+        lambda: lib.cs_bases_from_crs_file(null, b"/nonexistent.dat", 0, 4, 0, C.byref(out)),
+        lambda: lib.cs_groth16_pk_from_zkey(null, b"/nonexistent.zkey", 0, C.byref(out), null),
+        lambda: lib.cs_msm(null, null, 0, null, 4, 1, null, null),
+        lambda: lib.cs_plonk_pk_info(null, null, null, null, null),
+    ]
+    for i, call in enumerate(calls):
+        assert call() < 0, "call %d accepted NULL arguments" % i
+        assert len(lib.cs_last_error()) > 0
+    d = np.zeros(32, dtype=np.uint8)
+    assert lib.cs_keccak256(b"abc", 3, B._ptr(d)) == 0
+    assert bytes(d).hex() == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45"  # Keccak-256("abc")
