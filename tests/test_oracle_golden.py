@@ -183,7 +183,8 @@ def test_bls12_381_poseidon_fixtures_from_the_reference_tree():
     assert OP.verify(BLS12_381, pvk, F.read_plonk_proof_json(base + "circom.proof"), ppub, ppio)
 
 
-@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not mounted (GPU box)")
+@pytest.mark.skipif(not os.path.isdir(REF) or os.environ.get("CS_FULL_CPU_TESTS", "0") != "1",
+                    reason="needs the reference tree and takes ~20 s of big-int arithmetic: set CS_FULL_CPU_TESTS=1")
 def test_plonk_prover_bls12_381_poseidon_against_round1_kat_and_verifier():
     """The full oracle prover on the BLS12-381 poseidon fixture (domain 4096): its round-1 commitments are the
     reference's known answers (co-plonk/src/round1.rs:397-417) and the whole proof passes Plonk::verify."""
