@@ -52,13 +52,6 @@ class Transcript:
         return _conv(self.lib, "cs_fr_to_mont", self.curve, B.ints_to_limbs([v], 4))[0]
 
 
-def fr_mul(lib, curve, a, b):
-    out = np.zeros(4, dtype=np.uint64)
-    rc = lib.cs_fr_mul(curve, B._ptr(np.ascontiguousarray(a, dtype=np.uint64)), B._ptr(np.ascontiguousarray(b, dtype=np.uint64)), B._ptr(out))
-    assert rc == 0
-    return out
-
-
 class Rep3CoPlonk:
     """One party.  `prove` is a generator: it yields (kind, payload) requests and expects the combined value back:
          ("sum_points", [k, 2 fq])  -> the k opened points          ("sum_vec", [m, 4]) -> the m opened scalars
@@ -68,7 +61,6 @@ class Rep3CoPlonk:
     def __init__(self, ctx, pk, party, curve=B.CS_BN254):
         self.ctx, self.pk, self.party, self.curve = ctx, pk, party, curve
         self.sess = B.PlonkRep3Session(ctx, pk, party)
-        self.n = None
 
     def free(self):
         self.sess.free()

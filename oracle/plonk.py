@@ -14,7 +14,7 @@ Pinned against the reference's known-answer tests with deterministic blinders b[
 transcript KAT (types.rs:201-236) and the verifier-challenge KAT (plonk.rs:251-310); see
 tests/test_oracle_golden.py.  All values are canonical python ints; points are affine tuples or None.
 """
-from .ec import g1 as _g1, g2 as _g2
+from .ec import g1 as _g1
 from .fields import inv, roots_of_unity
 from .ntt import fft, ifft
 

@@ -4,7 +4,6 @@ launch: python -m torch.distributed.run --nnodes=1 --nproc-per-node 3 --master-a
         tools/time_co_plonk.py [log_n ...]"""
 import json
 import os
-import random
 import sys
 import time
 
