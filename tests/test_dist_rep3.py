@@ -327,3 +327,68 @@ def test_co_plonk_rep3_three_processes_gloo():
 def test_co_plonk_rep3_peer_memory():
     """The same with one process per party on real GPUs and the arena of the next party mapped through CUDA IPC."""
     _run_plonk(peer=True)
+
+
+def _party_shamir(rank, port, emu_path, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    from co_snarks_b200 import binding as B
+    from co_snarks_b200.shamir import ShamirCoGroth16, ShamirNetwork
+    from helpers import Conv, golden_groth16, make_key
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=3)
+    try:
+        ctx = B.Context(0, lib_path=emu_path)
+        cv = Conv("bn254")
+        z, m, w, g = golden_groth16("multiplier2")
+        ni = m["num_instance_variables"]
+        pk = make_key(ctx, cv, z, m)
+        rng = random.Random(77)  # same seed everywhere -> consistent degree-1 sharings of the witness
+        mine = []
+        for v in w[ni:]:
+            a = rng.randrange(cv.r)
+            mine.append((v + a * (rank + 1)) % cv.r)
+        net = ShamirNetwork()
+        prover = ShamirCoGroth16(ctx, pk)
+        A, Bp, Cp = prover.prove(net, cv.fr(w[:ni]), cv.fr(mine), cv.g1([z["delta_g1"]])[0])
+        q.put((rank, cv.pt1(A), cv.pt2(Bp), cv.pt1(Cp), prover.last_randomness, net.bytes_sent))
+        pk.free()
+        ctx.close()
+    finally:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def test_shamir_co_groth16_three_parties_gloo():
+    """ShamirCoGroth16::prove for t = 1, n = 3 (tests/tests/circom/e2e_tests/shamir.rs:37-91): all parties open the
+    same proof, it verifies, and it is the plain proof for r = r(0), s = s(0) of the jointly drawn sharings."""
+    import torch.multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import build_emu
+    emu = build_emu.build()
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_party_shamir, args=(r, port, emu, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(3))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from co_snarks_b200.shamir import lagrange_at_zero
+    from helpers import golden_groth16, ih
+    from oracle import groth16 as OG
+    from oracle.fields import BN254
+    from oracle.pairing_bn254 import groth16_verify
+    proofs = [(a, b, c) for _, a, b, c, _, _ in res]
+    assert proofs[0] == proofs[1] == proofs[2], "parties disagree on the proof"
+    z, m, w, g = golden_groth16("multiplier2")
+    assert groth16_verify(OG.vk_from_zkey(z), [ih(x) for x in g["public"]], proofs[0])
+    lam = lagrange_at_zero(3)
+    assert lam == [3, BN254.r - 3, 1]
+    r0 = sum(l * x[4][0] for l, x in zip(lam, res)) % BN254.r
+    s0 = sum(l * x[4][1] for l, x in zip(lam, res)) % BN254.r
+    assert proofs[0] == OG.prove_plain(z, m, w, r0, s0)
+    assert all(x[5] < 4096 for x in res)  # point- and scalar-sized messages only
