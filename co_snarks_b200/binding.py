@@ -61,8 +61,36 @@ class PlonkKeyDesc(C.Structure):
     ]
 
 
+NET_SEND_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
+NET_RECV_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_size_t)
+
+
+class NetCallbacks(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("send", NET_SEND_FN), ("recv", NET_RECV_FN)]
+
+
 # name -> (restype, argtypes); every symbol include/cosnarks_gpu.h declares
 SIGNATURES = {
+    "cs_net_from_callbacks": (C.c_int, [C.c_int, C.c_int, C.POINTER(NetCallbacks), C.POINTER(C.c_void_p)]),
+    "cs_net_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "cs_net_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_net_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cs_net_peer_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cs_net_send": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "cs_net_recv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "cs_net_bytes_sent": (C.c_uint64, [C.c_void_p]),
+    "cs_net_free": (None, [C.c_void_p]),
+    "cs_rep3_state_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cs_rep3_state_from_seeds": (C.c_int, [C.c_int, C.c_char_p, C.c_uint64, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "cs_rep3_state_fork": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "cs_rep3_state_prf": (C.c_int, [C.c_void_p, C.POINTER(Rep3Prf)]),
+    "cs_rep3_state_advance": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "cs_rep3_state_rand": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "cs_rep3_state_free": (None, [C.c_void_p]),
+    "cs_os_random": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "cs_groth16_rep3_prove": (C.c_int, [C.c_void_p] * 12),
+    "cs_groth16_rep3_prove_main": (C.c_int, [C.c_void_p] * 13),
+    "cs_groth16_rep3_prove_helper": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5),
     "cs_last_error": (C.c_char_p, []),
     "cs_version": (C.c_char_p, []),
     "cs_ctx_create": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -690,6 +718,30 @@ class Groth16Key:
             _ptr(l), _ptr(h)))
         return ga, gb1, gb2, l, h
 
+    def rep3_prove(self, net0, net1, state, public_inputs, witness_shares=None, d_witness_shares=None, pair=None,
+                   want_rs=False):
+        """Rep3CoGroth16::prove for this party inside the library (cs_groth16_rep3_prove[_main]).
+        -> (A, B, C[, rs]) affine Montgomery; rs = [r.a, r.b, s.a, s.b]."""
+        a = np.zeros(2 * self.fq, dtype=np.uint64)
+        b = np.zeros(4 * self.fq, dtype=np.uint64)
+        c = np.zeros(2 * self.fq, dtype=np.uint64)
+        rs = np.zeros((4, 4), dtype=np.uint64)
+        dw = C.c_void_p(d_witness_shares) if d_witness_shares else None
+        if pair is None:
+            rc = self.ctx.lib.cs_groth16_rep3_prove(self.ctx.h, self.h, net0.h, net1.h, state.h, _ptr(public_inputs),
+                                                    _ptr(witness_shares), dw, _ptr(a), _ptr(b), _ptr(c), _ptr(rs))
+        else:
+            rc = self.ctx.lib.cs_groth16_rep3_prove_main(self.ctx.h, self.h, net0.h, net1.h, pair.h, state.h,
+                                                         _ptr(public_inputs), _ptr(witness_shares), dw, _ptr(a), _ptr(b),
+                                                         _ptr(c), _ptr(rs))
+        self.ctx._check(rc)
+        return (a, b, c, rs) if want_rs else (a, b, c)
+
+    def rep3_prove_helper(self, party, pair, state, public_inputs, witness_shares=None, d_witness_shares=None):
+        dw = C.c_void_p(d_witness_shares) if d_witness_shares else None
+        self.ctx._check(self.ctx.lib.cs_groth16_rep3_prove_helper(self.ctx.h, self.h, party, pair.h, state.h,
+                                                                  _ptr(public_inputs), _ptr(witness_shares), dw))
+
     def shamir_local(self, public_inputs, witness_shares, r_share, s_share):
         g1 = lambda: np.zeros(2 * self.fq, dtype=np.uint64)
         ga, gb1, gb2, l, h = g1(), g1(), np.zeros(4 * self.fq, dtype=np.uint64), g1(), g1()
@@ -702,6 +754,143 @@ class Groth16Key:
         if self.h:
             self.ctx.lib.cs_groth16_pk_free(self.h)
             self.h = None
+
+
+class Net:
+    """cs_net: one n-party mesh (mpc_net::Network).  Build with Net.peer (mailboxes in GPU memory, CUDA IPC /
+    NVLink) or Net.callbacks (any Python transport: send(to, bytes), recv(frm, nbytes) -> bytes)."""
+
+    def __init__(self, lib, h, id, n, keep=None):
+        self.lib, self.h, self.id, self.n, self._keep = lib, h, id, n, keep
+
+    @classmethod
+    def callbacks(cls, lib, id, n, send, recv):
+        def _send(_u, to, data, nbytes):
+            try:
+                send(to, C.string_at(data, nbytes))
+                return 0
+            except Exception:  # noqa: BLE001 -- must not unwind through the C frame
+                import traceback
+                traceback.print_exc()
+                return -1
+
+        def _recv(_u, frm, data, nbytes):
+            try:
+                b = recv(frm, nbytes)
+                if len(b) != nbytes:
+                    return -2
+                C.memmove(data, b, nbytes)
+                return 0
+            except Exception:  # noqa: BLE001
+                import traceback
+                traceback.print_exc()
+                return -1
+        cb = NetCallbacks(None, NET_SEND_FN(_send), NET_RECV_FN(_recv))
+        h = C.c_void_p()
+        if lib.cs_net_from_callbacks(id, n, C.byref(cb), C.byref(h)):
+            raise CsError(lib.cs_last_error().decode())
+        return cls(lib, h, id, n, keep=cb)
+
+    @classmethod
+    def peer(cls, ctx, id, n):
+        h = C.c_void_p()
+        ctx._check(ctx.lib.cs_net_peer_create(ctx.h, id, n, C.byref(h)))
+        return cls(ctx.lib, h, id, n)
+
+    def _check(self, rc):
+        if rc:
+            raise CsError(self.lib.cs_last_error().decode())
+
+    def handle(self):
+        out = np.zeros(64, dtype=np.uint8)
+        self._check(self.lib.cs_net_peer_handle(self.h, _ptr(out)))
+        return out
+
+    def connect(self, handles):
+        """handles: [n][64] uint8, indexed by party id (other processes' cs_net_peer_handle)."""
+        arr = np.ascontiguousarray(handles, dtype=np.uint8).reshape(self.n, 64)
+        self._check(self.lib.cs_net_peer_connect(self.h, _ptr(arr)))
+
+    def connect_local(self, nets):
+        """nets: the n Net objects living in this process, indexed by party id."""
+        arr = (C.c_void_p * self.n)(*[x.h if x is not None else None for x in nets])
+        self._check(self.lib.cs_net_peer_connect_local(self.h, arr))
+
+    def send(self, to, data):
+        b = bytes(data)
+        self._check(self.lib.cs_net_send(self.h, to, b, len(b)))
+
+    def recv(self, frm, nbytes):
+        buf = C.create_string_buffer(nbytes)
+        self._check(self.lib.cs_net_recv(self.h, frm, buf, nbytes))
+        return buf.raw
+
+    @property
+    def bytes_sent(self):
+        return int(self.lib.cs_net_bytes_sent(self.h))
+
+    def free(self):
+        if self.h:
+            self.lib.cs_net_free(self.h)
+            self.h = None
+
+
+def connect_peer_nets_over_dist(nets, group=None, device="cpu"):
+    """Exchange the CUDA IPC handles of per-process peer nets over torch.distributed (bootstrap only) and
+    connect them.  `nets`: this process's Net objects (e.g. [net0, net1]), same order on every rank of the group."""
+    import torch
+    import torch.distributed as dist
+    n = dist.get_world_size(group)
+    for net in nets:
+        t = torch.from_numpy(net.handle().copy()).to(device)
+        outs = [torch.empty_like(t) for _ in range(n)]
+        dist.all_gather(outs, t, group=group)
+        net.connect(np.stack([o.cpu().numpy() for o in outs]))
+    dist.barrier(group=group)
+
+
+class Rep3StateC:
+    """cs_rep3_state: Rep3State's correlated randomness inside the library (two ChaCha12 streams)."""
+
+    def __init__(self, lib, h, id):
+        self.lib, self.h, self.id = lib, h, id
+
+    @classmethod
+    def create(cls, net):
+        """Rep3State::new: OS-entropy seed, exchanged with net.reshare (rep3.rs:55-75)."""
+        h = C.c_void_p()
+        if net.lib.cs_rep3_state_create(net.h, C.byref(h)):
+            raise CsError(net.lib.cs_last_error().decode())
+        return cls(net.lib, h, net.id)
+
+    @classmethod
+    def from_seeds(cls, lib, party, own32, prev32, pos_own=0, pos_prev=0):
+        h = C.c_void_p()
+        if lib.cs_rep3_state_from_seeds(party, bytes(own32), pos_own, bytes(prev32), pos_prev, C.byref(h)):
+            raise CsError(lib.cs_last_error().decode())
+        return cls(lib, h, party)
+
+    def prf(self):
+        p = Rep3Prf()
+        if self.lib.cs_rep3_state_prf(self.h, C.byref(p)):
+            raise CsError(self.lib.cs_last_error().decode())
+        return bytes(p.seed1), int(p.word_pos1), bytes(p.seed2), int(p.word_pos2), int(p.rounds)
+
+    def clone(self):
+        s1, p1, s2, p2, _ = self.prf()
+        return Rep3StateC.from_seeds(self.lib, self.id, s1, s2, p1, p2)
+
+    def free(self):
+        if self.h:
+            self.lib.cs_rep3_state_free(self.h)
+            self.h = None
+
+
+def os_random(lib, nbytes):
+    out = np.zeros(nbytes, dtype=np.uint8)
+    if lib.cs_os_random(_ptr(out), nbytes):
+        raise CsError(lib.cs_last_error().decode())
+    return out.tobytes()
 
 
 def read_wtns(lib, path, curve=CS_BN254):

@@ -7,7 +7,9 @@
 // results stays in HBM; only points come back.  Single-point work (scalar_mul_public_point_hs,
 // add_assign_points_public_hs, the public-input MSM over query[1..=pub], the final sums) runs on
 // the host while the GPU works -- it is latency-only in the reference too.
+#include <functional>
 #include "cs_lib.cuh"
+#include "cs_net.h"
 
 using namespace cs;
 
@@ -251,7 +253,7 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
                 const uint64_t* d_wit_in, const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
                 uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h,
                 unsigned parts = CS_PART_ALL, const cs_rep3_prf* prf = nullptr, const uint64_t* rs_mont = nullptr,
-                uint64_t* out_rs_delta = nullptr) {
+                uint64_t* out_rs_delta = nullptr, const std::function<void()>* overlap = nullptr) {
   typedef HostGroup<Cfg, 0> H1;
   typedef HostGroup<Cfg, 1> H2;
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
@@ -331,6 +333,7 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
   }
   if (rs_mont && out_rs_delta)  // (r s) * delta_1 (groth16.rs:297-298), also while the GPU is busy
     H1::store(out_rs_delta, H1::mul(H1::load(pk->delta_g1.data()), rs_mont));
+  if (overlap) (*overlap)();  // caller's single-point work that does not depend on the MSM results
   CS_CUDA(cudaStreamSynchronize(ctx->stream));
   uint64_t tmp[24];
   int inf = 0;
@@ -374,9 +377,164 @@ int prove_plain_t(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const u
   return 0;
 }
 
+
+// Rep3CoGroth16::prove for one party (groth16.rs:360-379, prove_inner :125-177, create_proof_with_assignment
+// :207-338 with Rep3Groth16Driver, mpc/rep3.rs).  role: 0 = the whole party on one GPU, 1 = the party's
+// protocol GPU ({A, B1, L} + both network legs; receives g2_b and h_acc from the helper over `pair`),
+// 2 = the helper GPU ({witness map -> H, B2}).
+template <class Cfg>
+int rep3_prove_t(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_net* pair, int role, int party,
+                 cs_rep3_state* state0, const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit,
+                 uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs) {
+  typedef HostGroup<Cfg, 0> H1;
+  typedef HostGroup<Cfg, 1> H2;
+  typedef host::HFp<typename Cfg::FrP> HR;
+  typedef typename Cfg::FrP FrP;
+  constexpr size_t G1L = 2 * H1::HF::N, G2L = 4 * H1::HF::N;  // 64-bit limbs of an affine point
+  const size_t n = pk->n;
+  // state1 = state0.fork(0) (groth16.rs:368): the scalar_mul leg draws its EC mask from the fork
+  cs_rep3_state* st1p = nullptr;
+  CS_TRY(cs_rep3_state_fork(state0, &st1p));
+  std::unique_ptr<cs_rep3_state> state1(st1p);
+  // ---- correlated randomness in the order the reference consumes it
+  // two n-element mask vectors of the witness map (reduction.rs:160,182): drawn on the device from
+  // (seed, word position); the streams move past the 2 x 8n words
+  cs_rep3_prf prf;
+  CS_TRY(cs_rep3_state_prf(state0, &prf));
+  CS_TRY(cs_rep3_state_advance(state0, 16 * (uint64_t)n));
+  uint64_t r_sh[2 * HR::N], s_sh[2 * HR::N];  // T::rand x2 (groth16.rs:157)
+  CS_TRY(cs_rep3_state_rand(state0, (cs_curve)pk->curve, r_sh));
+  CS_TRY(cs_rep3_state_rand(state0, (cs_curve)pk->curve, s_sh));
+  if (out_rs) { memcpy(out_rs, r_sh, sizeof(r_sh)); memcpy(out_rs + 2 * HR::N, s_sh, sizeof(s_sh)); }
+  // rs = local_mul_vec([r], [s]) (groth16.rs:297): r.a s.a + r.a s.b + r.b s.a + (F(rng1) - F(rng2))
+  HR ra, rb, sa, sb;
+  memcpy(ra.l, r_sh, sizeof(ra.l)); memcpy(rb.l, r_sh + HR::N, sizeof(rb.l));
+  memcpy(sa.l, s_sh, sizeof(sa.l)); memcpy(sb.l, s_sh + HR::N, sizeof(sb.l));
+  HR m1 = state0->rng1.template fr_be_mod_order<FrP>(), m2 = state0->rng2.template fr_be_mod_order<FrP>();
+  HR rs = ra * (sa + sb) + rb * sa + (m1 - m2);
+  // EC mask of scalar_mul_local (pointshare.rs:119-125, rngs.rs:177-186): C::rand(rng1) - C::rand(rng2), realised
+  // as k1 P - k2 P with k_i = F::rand(rng_i) and P = alpha_1 of the key, a public generator of the prime-order
+  // group, so k P is uniform (arkworks samples curve points by x-coordinate; the three parties' masks cancel
+  // either way)
+  uint64_t k1[HR::N], k2[HR::N];
+  state1->rng1.template fr_rand<FrP>(k1, Cfg::FR_BITS);
+  state1->rng2.template fr_rand<FrP>(k2, Cfg::FR_BITS);
+  if (role == 2) {
+    // helper GPU: {witness map -> H, B2}; same draws as the main GPU (lock-step), results over the pair link
+    uint64_t a[G1L], b1[G1L], b2[G2L], l[G1L], h[G1L];
+    CS_TRY((local_phase<Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit, d_wit, nullptr, nullptr, r_sh, s_sh, a, b1, b2, l, h,
+                             CS_PART_B2 | CS_PART_H, &prf)));
+    uint64_t msg[G2L + G1L];
+    memcpy(msg, b2, G2L * 8);
+    memcpy(msg + G2L, h, G1L * 8);
+    return cs_net_send(pair, 0, msg, sizeof(msg));
+  }
+  typename H1::X ec_mask = H1::X::inf();
+  std::function<void()> overlap = [&]() {
+    typename H1::X g = H1::load(pk->alpha_g1.data());
+    HR a1, a2;
+    memcpy(a1.l, k1, sizeof(a1.l)); memcpy(a2.l, k2, sizeof(a2.l));
+    HR d = a1 - a2;  // (k1 - k2) G: one scalar multiplication instead of two
+    HR dc = d.from_mont();
+    ec_mask = host::hmul(g, dc.l, HR::N);
+  };
+  uint64_t g_a[G1L], g1_b[G1L], g2_b[G2L], l_acc[G1L], h_acc[G1L], rsd[G1L];
+  const unsigned parts = role == 1 ? (CS_PART_A | CS_PART_B1 | CS_PART_L) : CS_PART_ALL;
+  CS_TRY((local_phase<Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit, d_wit, nullptr, nullptr, r_sh, s_sh, g_a, g1_b, g2_b,
+                           l_acc, h_acc, parts, role == 1 ? nullptr : &prf, rs.l, rsd, &overlap)));
+  if (role == 1) {
+    uint64_t msg[G2L + G1L];
+    CS_TRY(cs_net_recv(pair, 1, msg, sizeof(msg)));
+    memcpy(g2_b, msg, G2L * 8);
+    memcpy(h_acc, msg + G2L, G1L * 8);
+  }
+  Rep3Net n0(net0), n1(net1);
+  // ---- network round 1 (groth16.rs:305-308): open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1.
+  // All sends first (they do not block), then the receives.
+  CS_TRY(n0.send_next(g_a, G1L * 8));
+  CS_TRY(n0.send_prev(g_a, G1L * 8));
+  CS_TRY(n1.send_next(g1_b, G1L * 8));
+  // what can be done before the answers arrive: rhs.a * self.b
+  typename H1::X B1 = H1::load(g1_b);
+  typename H1::X t = H1::mul(B1, r_sh + HR::N);
+  uint64_t ga_prev[G1L], ga_next[G1L], g1b_prev[G1L];
+  CS_TRY(n0.recv_prev(ga_prev, G1L * 8));
+  CS_TRY(n0.recv_next(ga_next, G1L * 8));
+  CS_TRY(n1.recv_prev(g1b_prev, G1L * 8));
+  typename H1::X A_open = host::hadd(host::hadd(H1::load(g_a), H1::load(ga_prev)), H1::load(ga_next));
+  // scalar_mul_local: b * point + mask, (a, b) * (pa, pb) = pa b.a + pb b.a + pa b.b  (rep3 share product)
+  typename H1::X r_g1_b = host::hadd(host::hadd(H1::mul(host::hadd(B1, H1::load(g1b_prev)), r_sh), t), ec_mask);
+  // ---- groth16.rs:314-322
+  typename H1::X g_c = H1::mul(A_open, s_sh);
+  g_c = host::hadd(g_c, r_g1_b);
+  g_c = host::hadd(g_c, host::hneg(H1::load(rsd)));
+  g_c = host::hadd(g_c, H1::load(l_acc));
+  g_c = host::hadd(g_c, H1::load(h_acc));
+  uint64_t gc[G1L];
+  H1::store(gc, g_c);
+  // ---- network round 2 (groth16.rs:325-328): open_half_point(g_c) on net0 | open_half_point(g2_b) on net1
+  CS_TRY(n0.send_next(gc, G1L * 8));
+  CS_TRY(n0.send_prev(gc, G1L * 8));
+  CS_TRY(n1.send_next(g2_b, G2L * 8));
+  CS_TRY(n1.send_prev(g2_b, G2L * 8));
+  uint64_t gc_prev[G1L], gc_next[G1L], b2_prev[G2L], b2_next[G2L];
+  CS_TRY(n0.recv_prev(gc_prev, G1L * 8));
+  CS_TRY(n0.recv_next(gc_next, G1L * 8));
+  CS_TRY(n1.recv_prev(b2_prev, G2L * 8));
+  CS_TRY(n1.recv_next(b2_next, G2L * 8));
+  H1::store(out_a, A_open);
+  H1::store(out_c, host::hadd(host::hadd(g_c, H1::load(gc_prev)), H1::load(gc_next)));
+  H2::store(out_b, host::hadd(host::hadd(H2::load(g2_b), H2::load(b2_prev)), H2::load(b2_next)));
+  return 0;
+}
+
+int rep3_prove_dispatch(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_net* pair, int role, int party,
+                        cs_rep3_state* state, const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit,
+                        uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs) {
+  if (!ctx || !pk || !state || !h_pub) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: NULL argument");
+  if (pk->nw && !h_wit == !d_wit) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: pass the witness shares either on the host or on the device");
+  if (role != 2) {
+    if (!net0 || !net1 || !out_a || !out_b || !out_c) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: NULL argument");
+    if (net0->n != 3 || net1->n != 3 || net0->id != net1->id) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: net0/net1 must be 3-party meshes of the same party");
+    if (net0->id != state->id) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: state belongs to party %d, net to party %d", state->id, net0->id);
+  }
+  if (role != 0 && (!pair || pair->n != 2 || pair->id != role - 1)) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: pair must be the 2-party link (id %d)", role - 1);
+  if (party < 0 || party > 2) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove: party must be 0..2");
+  switch (pk->curve) {
+    case CS_BN254:
+      return rep3_prove_t<Bn254Cfg>(ctx, pk, net0, net1, pair, role, party, state, h_pub, h_wit, d_wit, out_a, out_b, out_c, out_rs);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381:
+      return rep3_prove_t<Bls381Cfg>(ctx, pk, net0, net1, pair, role, party, state, h_pub, h_wit, d_wit, out_a, out_b, out_c, out_rs);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int cs_groth16_rep3_prove(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_rep3_state* state,
+                          const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit, uint64_t* out_a,
+                          uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs) {
+  return rep3_prove_dispatch(ctx, pk, net0, net1, nullptr, 0, state ? state->id : 0, state, h_pub, h_wit, d_wit, out_a, out_b,
+                             out_c, out_rs);
+}
+
+int cs_groth16_rep3_prove_main(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_net* pair,
+                               cs_rep3_state* state, const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit,
+                               uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs) {
+  return rep3_prove_dispatch(ctx, pk, net0, net1, pair, 1, state ? state->id : 0, state, h_pub, h_wit, d_wit, out_a, out_b,
+                             out_c, out_rs);
+}
+
+int cs_groth16_rep3_prove_helper(cs_ctx* ctx, cs_groth16_pk* pk, int party, cs_net* pair, cs_rep3_state* state,
+                                 const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit) {
+  if (state && state->id != party) return fail(CS_ERR_ARG, "cs_groth16_rep3_prove_helper: state belongs to party %d", state->id);
+  return rep3_prove_dispatch(ctx, pk, nullptr, nullptr, pair, 2, party, state, h_pub, h_wit, d_wit, nullptr, nullptr, nullptr,
+                             nullptr);
+}
 
 int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* d, cs_groth16_pk** out) {
   if (!ctx || !d || !out) return fail(CS_ERR_ARG, "cs_groth16_pk_create: NULL argument");

@@ -288,6 +288,84 @@ int cs_ipc_export(cs_ctx* ctx, const void* d_ptr, uint8_t* out_handle64);
 int cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** out_peer_ptr);
 int cs_ipc_close(cs_ctx* ctx, void* peer_ptr);
 
+/* ---- party-to-party transport: mpc_net::Network (mpc-net/src/lib.rs:34-63: id / send / recv) -------------
+ * A cs_net is one n-party mesh.  Two implementations:
+ *  (1) callbacks -- the host language hands over its own transport (the Rust shim wraps `&N: Network`,
+ *      the CPU tests wrap torch.distributed/gloo); `send` must not block on the receiver (mpc-net queues),
+ *      `recv` blocks until `bytes` bytes from `from_party` have arrived.  Return 0 on success.
+ *  (2) peer mailboxes -- mpc-net replaced on-box: every party owns a small mailbox in the HBM of its GPU;
+ *      a send is a copy into the RECEIVER's mailbox through a CUDA-IPC mapping (NVLink peer memory; same-GPU
+ *      processes work too), ordered payload-then-sequence-number on a dedicated copy stream, with credits so
+ *      a slow receiver is never overrun.  Messages of any size (chunked); the Groth16 legs send 64..192 bytes.
+ *      Bootstrap: create, exchange the 64-byte handles by any means (torch.distributed, files), connect.
+ *      Parties living in ONE process (threads) connect with cs_net_peer_connect_local instead. */
+typedef struct cs_net cs_net;
+typedef struct {
+  void* user;
+  int (*send)(void* user, int to_party, const void* data, size_t bytes);
+  int (*recv)(void* user, int from_party, void* data, size_t bytes);
+} cs_net_callbacks;
+int cs_net_from_callbacks(int id, int n_parties, const cs_net_callbacks* cb, cs_net** out);
+int cs_net_peer_create(cs_ctx* ctx, int id, int n_parties, cs_net** out);
+int cs_net_peer_handle(cs_net* net, uint8_t* out_handle64);
+/* handles: n_parties x 64 bytes, indexed by party id (the own entry is ignored) */
+int cs_net_peer_connect(cs_net* net, const uint8_t* handles);
+int cs_net_peer_connect_local(cs_net* net, cs_net* const* peers /* n_parties entries, own may be NULL */);
+int cs_net_send(cs_net* net, int to_party, const void* data, size_t bytes);
+int cs_net_recv(cs_net* net, int from_party, void* data, size_t bytes);
+uint64_t cs_net_bytes_sent(const cs_net* net);
+void cs_net_free(cs_net* net);
+
+/* ---- Rep3State (mpc-core/src/protocols/rep3.rs:43-75): the party's correlated randomness --------------
+ * rng1 = this party's ChaCha12 stream, rng2 = the previous party's (Rep3Rand, rngs.rs:86-98).
+ * cs_rep3_state_create draws seed1 from the OS entropy pool (getrandom(2); the reference:
+ * ChaCha12Rng::from_entropy) and exchanges it exactly like setup_prf: seed2 = net.reshare(seed1).
+ * cs_rep3_state_from_seeds is the deterministic constructor for tests and for callers whose Rust side
+ * already holds a Rep3State (pass the two seeds and word positions).  fork mirrors MpcState::fork:
+ * both parties derive the child seeds from their streams, no communication. */
+typedef struct cs_rep3_state cs_rep3_state;
+int cs_rep3_state_create(cs_net* net, cs_rep3_state** out);
+int cs_rep3_state_from_seeds(int party, const uint8_t* seed_own32, uint64_t word_pos_own,
+                             const uint8_t* seed_prev32, uint64_t word_pos_prev, cs_rep3_state** out);
+int cs_rep3_state_fork(cs_rep3_state* st, cs_rep3_state** out);
+/* current (seed, word position) of both streams -- what cs_*_prf entry points take */
+int cs_rep3_state_prf(const cs_rep3_state* st, cs_rep3_prf* out);
+int cs_rep3_state_advance(cs_rep3_state* st, uint64_t nwords);
+/* arithmetic::rand (rep3/arithmetic.rs:357-360): share (a, b) = (F::rand(rng1), F::rand(rng2)), Montgomery;
+ * ark-ff's Fp::rand = rejection sampling on the top-masked 64-bit limbs. */
+int cs_rep3_state_rand(cs_rep3_state* st, cs_curve curve, uint64_t* out_share /* a || b */);
+void cs_rep3_state_free(cs_rep3_state* st);
+/* 32 bytes from the OS entropy pool (seeds for tests that want fresh randomness; r, s of plain_prove) */
+int cs_os_random(uint8_t* out, size_t bytes);
+
+/* ---- Rep3CoGroth16::prove (co-groth16/src/groth16.rs:360-379 -> prove_inner :125-177 ->
+ * create_proof_with_assignment :207-338), the whole party: local phase on the GPU, then the reference's two
+ * network legs inside the library -- round 1: open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1
+ * (:305-308); round 2: open_half_point(g_c) on net0 | open_half_point(g2_b) on net1 (:325-328) -- four
+ * point-sized messages per party, and the final sums (:314-322) on the host while nothing else waits.
+ *   net0, net1  two 3-party meshes as in the CLI's TcpNetwork::networks::<2> (co-circom.rs:1003); the same
+ *               handle may be passed twice.
+ *   state       Rep3State of this party (consumed: advanced by the 16 n mask words + the r, s, rs-mask and
+ *               EC-mask draws, in the reference's order).
+ *   witness     h_witness_shares (host, [nw][a||b]) or d_witness_shares (already resident); exactly one.
+ *   out_rs      optional [4][limbs]: r.a, r.b, s.a, s.b -- lets a test reconstruct r = sum r_i.a.
+ * Every party returns the same opened proof (A, B, C affine Montgomery). */
+int cs_groth16_rep3_prove(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_rep3_state* state,
+                          const uint64_t* h_public_inputs, const uint64_t* h_witness_shares,
+                          const uint64_t* d_witness_shares, uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                          uint64_t* out_rs);
+/* Two GPUs per party: the party's second GPU runs {witness map -> H, B2} and hands the two
+ * points to the first through `pair` (a 2-party cs_net: id 0 = the protocol GPU, id 1 = the helper); the first
+ * runs {A, B1, L} and the protocol.  Both are given states with identical seeds (cs_rep3_state_from_seeds from
+ * cs_rep3_state_prf of the main's state) so that their draws stay in lock-step. */
+int cs_groth16_rep3_prove_main(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_net* pair,
+                               cs_rep3_state* state, const uint64_t* h_public_inputs,
+                               const uint64_t* h_witness_shares, const uint64_t* d_witness_shares,
+                               uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs);
+int cs_groth16_rep3_prove_helper(cs_ctx* ctx, cs_groth16_pk* pk, int party, cs_net* pair, cs_rep3_state* state,
+                                 const uint64_t* h_public_inputs, const uint64_t* h_witness_shares,
+                                 const uint64_t* d_witness_shares);
+
 /* ShamirGroth16Driver's local phase (co-groth16/src/mpc/shamir.rs:29-119): identical arithmetic to the plain
  * driver on degree-t shares -- every party adds the public terms/points; outputs are degree-2t point shares
  * that the host protocol opens (shamir/pointshare.rs:86-113). */
