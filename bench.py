@@ -81,6 +81,242 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def _rep3_shares(ctx, syn, cvid):
+    """Replicated sharing of the private witness (rep3.rs:281-293): x = x0 + x1 + x2, party i holds (x_i, x_{i-1}).
+    Deterministic (PCG64 seed 5) so that every rank derives the same sharing without communication."""
+    import numpy as np
+    from co_snarks_b200.rep3 import random_field_limbs
+    lib = ctx.lib
+    share_rng = np.random.Generator(np.random.PCG64(5))
+    nw = syn.private_witness.shape[0]
+    x0, x1 = random_field_limbs(share_rng, nw), random_field_limbs(share_rng, nw)
+    d0, d1, dw = ctx.to_device(x0), ctx.to_device(x1), ctx.to_device(syn.private_witness)
+    ctx._check(lib.cs_vec_sub(ctx.h, cvid, dw, d0, dw, nw))
+    ctx._check(lib.cs_vec_sub(ctx.h, cvid, dw, d1, dw, nw))
+    x2 = ctx.d2h(dw, (nw, 4))
+    for d in (d0, d1, dw):
+        ctx.free(d)
+    return (x0, x1, x2)
+
+
+def _party_shares(xs, pid, pinned=True):
+    import numpy as np
+    import torch
+    sh = np.ascontiguousarray(np.concatenate([xs[pid], xs[(pid + 2) % 3]], axis=1))
+    if not pinned:
+        return sh
+    t = torch.empty(sh.shape, dtype=torch.int64).pin_memory()
+    t.numpy().view(np.uint64)[:] = sh
+    return t.numpy().view(np.uint64), t
+
+
+def _verify_proof(syn, proof):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import Conv
+    from oracle.pairing_bn254 import groth16_verify
+    cv = Conv("bn254")
+    return bool(groth16_verify(syn.vk_ints(), syn.witness[1:2], (cv.pt1(proof[0]), cv.pt2(proof[1]), cv.pt1(proof[2]))))
+
+
+def rep3_threads_one_gpu(args, ctx, pk, syn):
+    """BASELINE's metric config (co-Groth16, 3-party Rep3, 2^20) when only ONE GPU is available: the three parties
+    run as three host threads sharing the GPU, each with its own context, device-resident key and streams, the
+    whole protocol inside the library (cs_groth16_rep3_prove) over in-process mailbox nets."""
+    import threading
+    import numpy as np
+    import torch
+    from co_snarks_b200 import binding as B
+    lib = ctx.lib
+    t0 = time.time()
+    ctxs = [ctx] + [B.Context(ctx.device) for _ in range(2)]
+    pks = [pk] + [B.Groth16Key(c, B.CS_BN254, syn.matrices, syn.points, args.window_bits) for c in ctxs[1:]]
+    key_s = time.time() - t0
+    xs = _rep3_shares(ctx, syn, B.CS_BN254)
+    host_sh = [_party_shares(xs, i) for i in range(3)]
+    dev_sh = [ctxs[i].to_device(host_sh[i][0]) for i in range(3)]
+    nets0 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    nets1 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    for i in range(3):
+        nets0[i].connect_local(nets0)
+        nets1[i].connect_local(nets1)
+    seeds = [B.os_random(lib, 32) for _ in range(3)]
+    states = [B.Rep3StateC.from_seeds(lib, i, seeds[i], seeds[(i + 2) % 3]) for i in range(3)]
+    pub = syn.public_inputs
+
+    def run(steps, device):
+        res, errs = {}, []
+        bar = threading.Barrier(3)
+
+        def party(i):
+            try:
+                bar.wait()
+                for _ in range(steps):
+                    res[i] = pks[i].rep3_prove(nets0[i], nets1[i], states[i], pub,
+                                               None if device else host_sh[i][0], dev_sh[i] if device else None)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+                bar.abort()
+        th = [threading.Thread(target=party, args=(i,)) for i in range(3)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        if errs:
+            raise errs[0]
+        return (time.perf_counter() - t0) * 1e3, res
+    _, res = run(1, True)
+    agree = all(all((res[i][k] == res[0][k]).all() for k in range(3)) for i in (1, 2))
+    ok = None if (args.fast_setup or args.no_verify) else _verify_proof(syn, res[0])
+    if not agree or ok is False:
+        raise SystemExit("bench rep3 (1 GPU): proof invalid or parties disagree")
+    run(max(1, args.warmup - 1), True)
+    sent0 = nets0[0].bytes_sent + nets1[0].bytes_sent
+    ms_dev, _ = run(args.steps, True)
+    sent = (nets0[0].bytes_sent + nets1[0].bytes_sent - sent0) // args.steps
+    ms_host, _ = run(args.steps, False)
+    out = {"layout": "3 parties as 3 host threads sharing 1xB200 (one context, key and stream set per party)",
+           "gpus": 1, "groups": 1, "gpus_per_party": "1/3",
+           "ms_per_proof": ms_dev / args.steps, "proofs_per_s": args.steps / (ms_dev * 1e-3),
+           "e2e_ms_per_proof": ms_host / args.steps, "e2e_proofs_per_s": args.steps / (ms_host * 1e-3),
+           "h2d_bytes_per_party_per_proof": int(host_sh[0][0].nbytes + pub.nbytes),
+           "net_bytes_per_party_per_proof": int(sent), "parties_agree": bool(agree), "pairing_verified": ok,
+           "transport": "mailboxes in HBM, in-process (cs_net_peer_connect_local)", "protocol": "cs_groth16_rep3_prove (C++, in-library)",
+           "extra_key_upload_s": round(key_s, 2)}
+    for i in range(3):
+        ctxs[i].free(dev_sh[i])
+        nets0[i].free()
+        nets1[i].free()
+        states[i].free()
+    for p_, c_ in zip(pks[1:], ctxs[1:]):
+        p_.free()
+        c_.close()
+    return out
+
+
+def rep3_multi_gpu(args, ctx, pk, syn, groups, gpp, rank, world, local_rank):
+    """One Rep3 proving group per entry of `groups` (global ranks, party-major: [p0 main, (p0 helper), p1 main, ...]);
+    one process per GPU, party exchange through CUDA-IPC mailboxes in peer HBM (NVLink), protocol in the library.
+    Every rank of the world calls this (ranks outside all groups only take part in the collectives)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from co_snarks_b200 import binding as B
+    lib = ctx.lib
+    mine = None
+    for g, mem in enumerate(groups):
+        if rank in mem:
+            k = mem.index(rank)
+            mine = (g, k // gpp, k % gpp)  # group, party, role (0 = protocol GPU, 1 = helper)
+    net0 = net1 = pair = None
+    z64 = np.zeros(64, dtype=np.uint8)
+    if mine:
+        _, pid, role = mine
+        if role == 0:
+            net0, net1 = B.Net.peer(ctx, pid, 3), B.Net.peer(ctx, pid, 3)
+        if gpp == 2:
+            pair = B.Net.peer(ctx, role, 2)
+    # bootstrap: every rank publishes its three handles (zeros where it has none)
+    hs = np.stack([net0.handle() if net0 else z64, net1.handle() if net1 else z64, pair.handle() if pair else z64])
+    t = torch.from_numpy(hs.copy()).cuda()
+    allh = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(allh, t)
+    allh = [x.cpu().numpy() for x in allh]
+    if mine:
+        g, pid, role = mine
+        mem = groups[g]
+        if role == 0:
+            mains = [mem[p * gpp] for p in range(3)]
+            net0.connect(np.stack([allh[r][0] for r in mains]))
+            net1.connect(np.stack([allh[r][1] for r in mains]))
+        if gpp == 2:
+            pr = [mem[pid * 2], mem[pid * 2 + 1]]
+            pair.connect(np.stack([allh[r][2] for r in pr]))
+    torch.cuda.synchronize()
+    dist.barrier()
+    state = None
+    res = None
+    pub = syn.public_inputs
+    host_sh = dev_sh = None
+    if mine:
+        g, pid, role = mine
+        xs = _rep3_shares(ctx, syn, B.CS_BN254)
+        host_sh = _party_shares(xs, pid)
+        dev_sh = ctx.to_device(host_sh[0])
+        if role == 0:
+            state = B.Rep3StateC.create(net0)  # OS entropy, seeds exchanged over the mailboxes (Rep3State::new)
+            if gpp == 2:  # the helper GPU mirrors the party's streams
+                s1, p1, s2, p2, _ = state.prf()
+                pair.send(1, s1 + s2 + int(p1).to_bytes(8, "little") + int(p2).to_bytes(8, "little"))
+        else:
+            b = pair.recv(0, 80)
+            state = B.Rep3StateC.from_seeds(lib, pid, b[:32], b[32:64], int.from_bytes(b[64:72], "little"),
+                                            int.from_bytes(b[72:80], "little"))
+
+    def one(device):
+        if not mine:
+            return None
+        _, pid, role = mine
+        hw = None if device else host_sh[0]
+        dw = dev_sh if device else None
+        if role == 1:
+            pk.rep3_prove_helper(pid, pair, state, pub, hw, dw)
+            return None
+        return pk.rep3_prove(net0, net1, state, pub, hw, dw, pair=pair)
+
+    def timed(steps, device):
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        r = None
+        for _ in range(steps):
+            r = one(device)
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) * 1e3 if mine else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        return float(dt.item()), r
+    _, res = timed(1, True)
+    # agreement: all protocol ranks of a group hold the same opened proof
+    flat = np.concatenate([x.reshape(-1) for x in res]) if res is not None else np.zeros(32, dtype=np.uint64)
+    tt = torch.from_numpy(flat.view(np.int64).copy()).cuda()
+    outs = [torch.empty_like(tt) for _ in range(world)]
+    dist.all_gather(outs, tt)
+    agree = True
+    for mem in groups:
+        mains = [mem[p * gpp] for p in range(3)]
+        agree = agree and all(bool((outs[r] == outs[mains[0]]).all()) for r in mains)
+    ok = None
+    if rank == 0 and not (args.fast_setup or args.no_verify):
+        ok = _verify_proof(syn, res)
+        if not ok or not agree:
+            raise SystemExit("bench rep3: proof invalid or parties disagree")
+    timed(max(1, args.warmup - 1), True)
+    sent0 = (net0.bytes_sent + net1.bytes_sent) if net0 else 0
+    ms_dev, _ = timed(args.steps, True)
+    sent = ((net0.bytes_sent + net1.bytes_sent - sent0) // args.steps) if net0 else 0
+    ms_host, _ = timed(args.steps, False)
+    ng = len(groups)
+    out = {"layout": "%d group(s) of 3 parties x %d GPU(s) per party, one process per GPU" % (ng, gpp),
+           "gpus": ng * 3 * gpp, "groups": ng, "gpus_per_party": gpp,
+           "ms_per_proof": ms_dev / args.steps, "proofs_per_s": ng * args.steps / (ms_dev * 1e-3),
+           "e2e_ms_per_proof": ms_host / args.steps, "e2e_proofs_per_s": ng * args.steps / (ms_host * 1e-3),
+           "h2d_bytes_per_party_per_proof": int((host_sh[0].nbytes if host_sh else 0) + pub.nbytes) * gpp,
+           "net_bytes_per_party_per_proof": int(sent), "parties_agree": bool(agree), "pairing_verified": ok,
+           "transport": "CUDA-IPC mailboxes in peer HBM (NVLink peer copies), 4 point-sized messages per party",
+           "protocol": "cs_groth16_rep3_prove (C++, in-library)"}
+    dist.barrier()
+    if mine:
+        ctx.free(dev_sh)
+        for n_ in (net0, net1, pair):
+            if n_:
+                n_.free()
+        state.free()
+    return out
+
+
 def run_ours(args):
     import numpy as np
     import torch
@@ -175,6 +411,20 @@ def run_ours(args):
     clk = clocks.stop()
     barrier()
 
+    # ---- the metric's own configuration in the same run: co-Groth16, 3-party Rep3 (BASELINE configs[2]),
+    # whole protocol inside the library.  N = 1: three party threads share the GPU; N >= 3: one party per GPU
+    # (N // 3 proving groups); N >= 6 additionally 3 parties x 2 GPUs.
+    rep3 = rep3_split = None
+    if not args.no_rep3:
+        if world == 1:
+            rep3 = rep3_threads_one_gpu(args, ctx, pk, syn)
+        elif world >= 3:
+            groups = [[3 * g, 3 * g + 1, 3 * g + 2] for g in range(world // 3)]
+            rep3 = rep3_multi_gpu(args, ctx, pk, syn, groups, 1, rank, world, local_rank)
+            if world >= 6:
+                rep3_split = rep3_multi_gpu(args, ctx, pk, syn, [list(range(6))], 2, rank, world, local_rank)
+        barrier()
+
     out = None
     if rank == 0:
         # ---- kernel roofline (rank 0, single stream): standalone G1 MSM over a_query with stage events
@@ -259,7 +509,10 @@ def run_ours(args):
                     "int_pipe_frac": n * lg / 2 / (ntt_avg * 1e-3) / 1e9 / gmul_peak,
                     "note": "n/2 log n butterflies of one Montgomery product each: integer-pipe bound like the MSM"},
             "cpu_baseline": cpu_baseline(args) if world == 1 else None,  # rank 0 at N = 1 only
+            "rep3": rep3 if rep3 is not None else ("skipped (--no-rep3)" if args.no_rep3 else "needs 1 or >= 3 GPUs"),
         }
+        if rep3_split is not None:
+            out["rep3_2gpu_per_party"] = rep3_split
     pk.free()
     ctx.close()
     if world > 1:
@@ -285,15 +538,12 @@ def ncu_traffic():
 
 
 def run_rep3(args):
-    """BASELINE.json configs[2]: co-Groth16 Rep3, 3 parties on 3 GPUs of one box, point exchange over NCCL.
-    Launch: torchrun --nproc-per-node 3 bench.py --mode rep3 --gpus 3.  One step = one collaborative proof."""
-    import numpy as np
+    """Standalone BASELINE configs[2]: torchrun --nproc-per-node 3 (or 6 with --gpus-per-party 2) bench.py --mode rep3.
+    One step = one collaborative proof; the same code path as the `rep3` block of the default run."""
     import torch
     import torch.distributed as dist
     from co_snarks_b200 import binding as B
-    from co_snarks_b200.rep3 import Rep3CoGroth16, Rep3Network, Rep3State, random_field_limbs
     from workloads.synth_groth16 import SynthGroth16
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -301,113 +551,32 @@ def run_rep3(args):
     assert gpp in (1, 2) and world % (3 * gpp) == 0, "rep3 mode needs 3 (or 6) ranks per proving group"
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    blk = 3 * gpp
-    role = rank % gpp  # 0 = the party's protocol GPU, 1 = its helper GPU ({witness map -> H, B2})
-    all_groups = {}
-    for g in range(world // blk):
-        for ro in range(gpp):
-            all_groups[(g, ro)] = dist.new_group([g * blk + p * gpp + ro for p in range(3)])
-    group = all_groups[(rank // blk, role)]
     stream = torch.cuda.Stream()
     ctx = B.Context(local_rank, stream=stream.cuda_stream)
-    lg = args.log_m
-    n = 1 << lg
     t0 = time.time()
-    syn = SynthGroth16(ctx, lg, seed=1, setup_seed=2, valid=not args.fast_setup)
+    syn = SynthGroth16(ctx, args.log_m, seed=1, setup_seed=2, valid=not args.fast_setup)
     pk = syn.make_key(args.window_bits)
     setup_s = time.time() - t0
-    net = Rep3Network(group, device="cuda")
-    pid = net.id
-    state = Rep3State(net, seed=4242 + (rank // blk) * 3 + pid)  # both GPUs of a party: identical streams
-    link = None
-    if gpp == 2:
-        from co_snarks_b200.rep3 import PairLink
-        link = PairLink(rank + 1 if role == 0 else rank - 1, device="cuda")
-    cvid = B.CS_BN254
-    lib = ctx.lib
-
-    def dev_sub(x, y):  # (x - y) mod r on the device, host arrays in/out
-        dx, dy = ctx.to_device(x), ctx.to_device(y)
-        ctx._check(lib.cs_vec_sub(ctx.h, cvid, dx, dy, dx, x.shape[0]))
-        out = ctx.d2h(dx, x.shape)
-        ctx.free(dx)
-        ctx.free(dy)
-        return out
-
-    # replicated sharing of the witness (rep3.rs:281-293): x = x0 + x1 + x2, party i holds (x_i, x_{i-1})
-    share_rng = np.random.Generator(np.random.PCG64(5))
-    nw = syn.m - syn.ni
-    x0, x1 = random_field_limbs(share_rng, nw), random_field_limbs(share_rng, nw)
-    x2 = dev_sub(dev_sub(syn.private_witness, x0), x1)
-    xs = (x0, x1, x2)
-    shares = np.ascontiguousarray(np.concatenate([xs[pid], xs[(pid + 2) % 3]], axis=1))
-    sh_pinned = torch.empty(shares.shape, dtype=torch.int64).pin_memory()
-    sh_pinned.numpy().view(np.uint64)[:] = shares
-    shares = sh_pinned.numpy().view(np.uint64)
-    # the two n-element mask vectors are drawn on the device from the party's ChaCha12 streams inside the
-    # timed local phase (cs_groth16_rep3_local_prf), as the reference draws them inside prove()
-    masks = None
-    prover = Rep3CoGroth16(ctx, pk)
-    delta = syn.points["delta_g1"][0]
-    pub = syn.public_inputs
-
-    def gather_eq(arrs):
-        t = torch.from_numpy(np.concatenate([a.reshape(-1) for a in arrs]).view(np.int64).copy()).cuda()
-        outs = [torch.empty_like(t) for _ in range(3)]
-        dist.all_gather(outs, t, group=group)
-        return all(bool((o == outs[0]).all()) for o in outs)
-
-    def one_proof():
-        if role == 1:
-            prover.helper_step(pid, state, pub, shares, link.send, masks)
-            return None
-        return prover.prove(net, state, pub, shares, delta, masks,
-                            pair_recv=(lambda: link.recv(6 * 4)) if link else None)
-
-    proof = one_proof()
-    same = gather_eq(proof) if role == 0 else True
-    ok = None
-    if rank == 0 and not args.fast_setup and not args.no_verify:
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from helpers import Conv
-        from oracle.pairing_bn254 import groth16_verify
-        cv = Conv("bn254")
-        ok = bool(groth16_verify(syn.vk_ints(), syn.witness[1:2], (cv.pt1(proof[0]), cv.pt2(proof[1]), cv.pt1(proof[2]))))
-        if not ok or not same:
-            raise SystemExit("bench rep3: proof invalid or parties disagree")
-    for _ in range(args.warmup):
-        one_proof()
-    torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
+    blk = 3 * gpp
+    groups = [list(range(g * blk, (g + 1) * blk)) for g in range(world // blk)]
     clocks = ClockSampler(local_rank)
     l0 = ctx.launch_count()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        one_proof()
-    torch.cuda.synchronize()
-    dt = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
-    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    ms = float(dt.item())
+    r = rep3_multi_gpu(args, ctx, pk, syn, groups, gpp, rank, world, local_rank)
     launches = ctx.launch_count() - l0
     clk = clocks.stop()
     if rank == 0:
-        nproofs = args.steps * (world // blk)
-        h2d = shares.nbytes + pub.nbytes
         print(json.dumps({
-            "metric": METRIC, "value": nproofs / (ms * 1e-3), "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": r["proofs_per_s"], "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_proof"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery, integer)",
-            "data": "synthetic (seeded R1CS + known-toxic-waste key; proof pairing-verified: %s; parties agree: %s)" % (ok, same),
-            "config": {"workload": "co-Groth16 Rep3, BN254, synthetic R1CS 2^%d constraints, 3 parties x %d GPU(s) on %dxB200, "
-                                   "NCCL point exchange (BASELINE.json configs[2])" % (lg, gpp, blk),
-                       "groups": world // blk, "gpus_per_party": gpp, "mask_prf": "ChaCha12 masks drawn on the device inside the timed region", "setup_s": round(setup_s, 1),
+            "data": "synthetic (seeded R1CS + known-toxic-waste key; proof pairing-verified: %s; parties agree: %s)" % (
+                r["pairing_verified"], r["parties_agree"]),
+            "config": {"workload": "co-Groth16 Rep3, BN254, synthetic R1CS 2^%d constraints, 3 parties x %d GPU(s), "
+                                   "(BASELINE.json configs[2])" % (args.log_m, gpp), "setup_s": round(setup_s, 1),
                        "l2": "working set exceeds L2"},
-            "e2e": {"value": nproofs / (ms * 1e-3), "unit": "proofs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 1344,
-                    "note": "host (pinned) share buffers uploaded every step; timed by wall clock between synchronisations"},
-            "gpu_launches": int(launches), "clocks": clk,
-            "net_bytes_per_party_per_proof": net.bytes_sent // (args.steps + args.warmup + 1),
-        }))
+            "e2e": {"value": r["e2e_proofs_per_s"], "unit": "proofs/s", "h2d_bytes_per_step": r["h2d_bytes_per_party_per_proof"],
+                    "d2h_bytes_per_step": 1344},
+            "gpu_launches": int(launches), "clocks": clk, "rep3": r}))
     pk.free()
     ctx.close()
     dist.barrier()
@@ -462,6 +631,7 @@ def main():
     ap.add_argument("--gpus-per-party", type=int, default=1)
     ap.add_argument("--fast-setup", action="store_true", help="random (invalid) key: skips the host-side QAP setup")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-rep3", action="store_true", help="skip the Rep3 block of the default run")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -1,4 +1,7 @@
-"""Rep3 co-Groth16 party driver: the host-side mirror of `Rep3Groth16Driver` + `Rep3CoGroth16::prove`.
+"""Rep3 co-Groth16 party driver in Python (round-1 driver, kept for the transport-agnostic tests and co-Plonk):
+the host-side mirror of `Rep3Groth16Driver` + `Rep3CoGroth16::prove`.  The product path is the same protocol
+INSIDE the library -- `cs_groth16_rep3_prove` (binding.Groth16Key.rep3_prove) over `cs_net`; bench.py and the GPU
+tests use that one.
 
 Reference: co-circom/co-groth16/src/groth16.rs:125-177 (prove_inner), :207-338
 (create_proof_with_assignment), :360-379 (Rep3CoGroth16::prove); driver co-groth16/src/mpc/rep3.rs;
@@ -211,8 +214,15 @@ class Rep3State:
     """Correlated randomness of one party: rng1 = own ChaCha12 stream, rng2 = the previous party's
     (Rep3Rand, rngs.rs:86-156; seeds exchanged once over the network, rep3.rs:71-110)."""
 
-    def __init__(self, net, seed):
-        own = np.random.Generator(np.random.PCG64([seed, net.id])).integers(0, 2 ** 63, size=4, dtype=np.uint64)
+    def __init__(self, net, seed=None):
+        """seed=None (the default): 32 bytes from the OS entropy pool, as the reference's ChaCha12Rng::from_entropy
+        (rep3.rs:57).  An integer seed gives a reproducible stream for TESTS ONLY -- a guessable seed lets the other
+        parties recompute the one key they must not know and strip every mask."""
+        if seed is None:
+            import secrets
+            own = np.frombuffer(secrets.token_bytes(32), dtype=np.uint64).copy()
+        else:
+            own = np.random.Generator(np.random.PCG64([seed, net.id])).integers(0, 2 ** 63, size=4, dtype=np.uint64)
         prev = net.reshare(own)
         self.id = net.id
         self.rng1 = _ChaChaStream(own.tobytes())

@@ -61,6 +61,27 @@ class ShamirNetwork:
         self.bytes_sent += 2 * t.numel() * 8
         return [o.cpu().numpy().view(np.uint64).reshape(np.shape(arr)) for o in outs]
 
+    def scatter_private(self, per_recipient):
+        """per_recipient[j] = what this party deals to party j.  Point-to-point only: party j receives its own
+        row from every dealer and nothing else (a dealer's rows for the OTHER recipients never leave it -- two
+        evaluations would determine a degree-1 polynomial).  -> list over dealers of the rows dealt to me."""
+        import torch
+        rows = [torch.from_numpy(np.ascontiguousarray(per_recipient[j]).view(np.int64).copy()).to(self.device) for j in range(3)]
+        got = [torch.empty_like(rows[self.id]) for _ in range(3)]
+        ops = []
+        for j in range(3):
+            if j == self.id:
+                continue
+            peer = self.dist.get_global_rank(self.group, j) if self.group is not None else j
+            ops.append(self.dist.P2POp(self.dist.isend, rows[j], peer, self.group))
+            ops.append(self.dist.P2POp(self.dist.irecv, got[j], peer, self.group))
+        for w in self.dist.batch_isend_irecv(ops):
+            w.wait()
+        got[self.id] = rows[self.id]
+        self.bytes_sent += 2 * rows[0].numel() * 8
+        self.last_received = [g.cpu().numpy().view(np.uint64).reshape(np.shape(per_recipient[0])) for g in got]
+        return self.last_received
+
 
 class ShamirCoGroth16:
     def __init__(self, ctx, pk, curve=B.CS_BN254):
@@ -74,8 +95,8 @@ class ShamirCoGroth16:
         for k in range(count):
             v, a = secrets.randbelow(R_MOD), secrets.randbelow(R_MOD)
             deal[:, k, :] = B.ints_to_limbs([(v + a * (j + 1)) % R_MOD for j in range(3)], 4)
-        got = net.all_gather(deal)  # got[p][me] = what party p dealt to me
-        mine = [sum(B.limbs_to_ints(got[p][net.id, k].reshape(1, 4))[0] for p in range(3)) % R_MOD for k in range(count)]
+        got = net.scatter_private(deal)  # got[p] = the row party p dealt to me (and only that row)
+        mine = [sum(B.limbs_to_ints(got[p][k].reshape(1, 4))[0] for p in range(3)) % R_MOD for k in range(count)]
         return mine  # canonical ints
 
     def _open_points(self, net, point, group):

@@ -15,7 +15,7 @@
 //   Rep3CoGroth16::prove (groth16.rs:360-379)                  Rep3CoGroth16::prove(net0, net1, pk, witness)
 //   mpc_net::Network (mpc-net/src/lib.rs:34-63)                mpc_net::Network (id/send/recv)
 //   mpc_net::local::LocalNetwork::new_3_parties (local.rs)     mpc_net::LocalNetwork::new_3_parties
-//   Rep3State / Rep3Rand (rep3.rs:43-128, rngs.rs:86-156)      Rep3State (two correlated PRF streams)
+//   Rep3State / Rep3Rand (rep3.rs:43-128, rngs.rs:86-156)      Rep3State (cs_rep3_state: two ChaCha12 streams, OS-entropy seeds)
 //   eyre::Result / bail!                                       std::runtime_error with the same messages
 //
 // tests/cpp/test_co_groth16.cpp drives this exactly like tests/tests/circom/e2e_tests/rep3.rs drives
@@ -28,7 +28,6 @@
 #include <deque>
 #include <memory>
 #include <mutex>
-#include <random>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -178,57 +177,62 @@ template <class T> inline std::pair<T, T> broadcast(mpc_net::Network& net, const
   return {p, n};
 }
 
-// Rep3Rand (rngs.rs:86-156): rng1 = own stream, rng2 = previous party's stream, seeds exchanged once
-// (rep3.rs:71-110).  The reference uses ChaCha12; the correlation structure is what the protocol needs.
-struct Rep3State {
-  PartyID id;
-  std::mt19937_64 rng1, rng2;
-  Rep3State(mpc_net::Network& net, uint64_t seed) : id{net.id()} {
-    uint64_t own = seed * 4 + net.id();
-    uint64_t prev = reshare(net, own);
-    rng1.seed(own);
-    rng2.seed(prev);
+// uniform field element from the OS entropy pool (PlainGroth16Driver::rand = thread_rng, mpc/plain.rs:23-26):
+// rejection sampling on 254-bit draws, like ark-ff's Fp::rand; the accepted limbs are taken as the Montgomery form
+inline Fr fr_rand() {
+  static const Fr R = {0x43e1f593f0000001ull, 0x2833e84879b97091ull, 0xb85045b68181585dull, 0x30644e72e131a029ull};
+  for (;;) {
+    Fr v;
+    check(cs_os_random(reinterpret_cast<uint8_t*>(v.data()), 32));
+    v[3] &= (1ull << 62) - 1;
+    for (int i = 3; i >= 0; i--) {
+      if (v[i] < R[i]) return v;
+      if (v[i] > R[i]) break;
+    }
   }
-  static Fr draw(std::mt19937_64& g) {  // uniform 253-bit value (< r), taken as a canonical integer
-    Fr c{g(), g(), g(), g() & ((1ull << 61) - 1)};
-    return fr_from_canonical(c);
+}
+
+// mpc_net::Network -> the library's transport handle (cs_net over callbacks).  `send` queues, `recv` blocks.
+struct NetAdapter {
+  mpc_net::Network& net;
+  cs_net* h = nullptr;
+  explicit NetAdapter(mpc_net::Network& n) : net(n) {
+    cs_net_callbacks cb{this, &NetAdapter::send_cb, &NetAdapter::recv_cb};
+    check(cs_net_from_callbacks((int)n.id(), 3, &cb, &h));
   }
-  std::pair<Fr, Fr> random_fes() { Fr a = draw(rng1); Fr b = draw(rng2); return {a, b}; }      // rngs.rs:109-113
-  Rep3PrimeFieldShare rand() { auto ab = random_fes(); return {ab.first, ab.second}; }          // arithmetic.rs:357-360
-  Fr masking_field_element() { auto ab = random_fes(); return fr_sub(ab.first, ab.second); }    // rngs.rs:103-106
-  std::vector<Fr> masking_field_elements_vec(size_t n) {                                         // rngs.rs:137-156
-    std::vector<Fr> out(n);
-    for (auto& x : out) x = masking_field_element();
-    return out;
+  ~NetAdapter() { cs_net_free(h); }
+  NetAdapter(const NetAdapter&) = delete;
+  static int send_cb(void* u, int to, const void* data, size_t bytes) {
+    try {
+      auto* b = static_cast<const uint8_t*>(data);
+      static_cast<NetAdapter*>(u)->net.send((size_t)to, std::vector<uint8_t>(b, b + bytes));
+      return 0;
+    } catch (...) { return -1; }
   }
-  G1 masking_ec_element(const G1& generator) {                                                   // rngs.rs:177-186
-    auto ab = random_fes();
-    return generator * ab.first + (-(generator * ab.second));
+  static int recv_cb(void* u, int from, void* data, size_t bytes) {
+    try {
+      auto v = static_cast<NetAdapter*>(u)->net.recv((size_t)from);
+      if (v.size() != bytes) return -2;
+      std::memcpy(data, v.data(), bytes);
+      return 0;
+    } catch (...) { return -1; }
   }
 };
 
-// ---- R1CSToQAP ------------------------------------------------------------------------------------
-struct CircomReduction {                                 // groth16/reduction.rs:73-193
-  // plain driver: h as field elements
-  static std::vector<Fr> witness_map_from_matrices(Context& ctx, ProvingKey& pk, const std::vector<Fr>& public_inputs,
-                                                   const std::vector<Fr>& private_witness) {
-    std::vector<Fr> h(pk.domain_size());
-    check(cs_groth16_witness_map(ctx.h, pk.h, CS_PLAIN, 0, public_inputs[0].data(),
-                                 private_witness.empty() ? nullptr : private_witness[0].data(), nullptr, nullptr, h[0].data()));
-    return h;
-  }
-  // Rep3 driver: half shares of h; consumes two mask vectors from the party's state, in the order
-  // reduction.rs:160 and :182 do
-  static std::vector<Fr> witness_map_from_matrices(Context& ctx, ProvingKey& pk, Rep3State& state,
-                                                   const std::vector<Fr>& public_inputs,
-                                                   const std::vector<Rep3PrimeFieldShare>& private_witness) {
-    const size_t n = pk.domain_size();
-    auto m1 = state.masking_field_elements_vec(n), m2 = state.masking_field_elements_vec(n);
-    std::vector<Fr> h(n);
-    check(cs_groth16_witness_map(ctx.h, pk.h, CS_REP3, (int)state.id.v, public_inputs[0].data(),
-                                 private_witness.empty() ? nullptr : private_witness[0].a.data(), m1[0].data(), m2[0].data(),
-                                 h[0].data()));
-    return h;
+// Rep3State (rep3.rs:43-75): Rep3Rand's two ChaCha12 streams live inside the library.  new(): seed1 from the OS
+// entropy pool (ChaCha12Rng::from_entropy), seed2 = net.reshare(seed1) -- exactly setup_prf.
+struct Rep3State {
+  cs_rep3_state* h = nullptr;
+  explicit Rep3State(NetAdapter& net) { check(cs_rep3_state_create(net.h, &h)); }
+  ~Rep3State() { cs_rep3_state_free(h); }
+  Rep3State(const Rep3State&) = delete;
+  Rep3PrimeFieldShare rand() {                                                                   // arithmetic.rs:357-360
+    Rep3PrimeFieldShare s;
+    uint64_t ab[8];
+    check(cs_rep3_state_rand(h, CS_BN254, ab));
+    std::memcpy(s.a.data(), ab, 32);
+    std::memcpy(s.b.data(), ab + 4, 32);
+    return s;
   }
 };
 
@@ -238,9 +242,7 @@ struct Groth16 {
   // PlainGroth16Driver::rand (mpc/plain.rs:23-26) unless injected
   static Proof plain_prove(Context& ctx, ProvingKey& pk, const SharedWitness<Fr>& w, const Fr* r = nullptr, const Fr* s = nullptr) {
     check_witness_lengths(pk, w);
-    std::random_device rd;
-    std::mt19937_64 g(((uint64_t)rd() << 32) ^ rd());
-    Fr rr = r ? *r : Rep3State::draw(g), ss = s ? *s : Rep3State::draw(g);
+    Fr rr = r ? *r : fr_rand(), ss = s ? *s : fr_rand();
     Proof p;
     check(cs_groth16_prove_plain(ctx.h, pk.h, w.public_inputs[0].data(), w.witness.empty() ? nullptr : w.witness[0].data(),
                                  rr.data(), ss.data(), p.a.data(), p.b.data(), p.c.data()));
@@ -249,36 +251,23 @@ struct Groth16 {
 };
 
 struct Rep3CoGroth16 {
-  // Rep3CoGroth16::prove::<N, CircomReduction>(net0, net1, &pkey, &matrices, witness)  (groth16.rs:360-379).
-  // The local phase (witness map on shares + the five MSMs, groth16.rs:151-294) is one call on this party's
-  // GPU; the rest is create_proof_with_assignment's tail (groth16.rs:296-337) on single points.
+  // Rep3CoGroth16::prove::<N, CircomReduction>(net0, net1, &pkey, &matrices, witness)  (groth16.rs:360-379):
+  // state0 = Rep3State::new(net0), state1 = state0.fork(0), then prove_inner -- the local phase on this party's GPU
+  // and create_proof_with_assignment's two network legs (groth16.rs:296-337), all inside cs_groth16_rep3_prove.
   static Proof prove(Context& ctx, mpc_net::Network& net0, mpc_net::Network& net1, ProvingKey& pk,
-                     const SharedWitness<Rep3PrimeFieldShare>& w, uint64_t seed, const G1& g1_generator,
-                     Rep3PrimeFieldShare* out_r = nullptr, Rep3PrimeFieldShare* out_s = nullptr) {
+                     const SharedWitness<Rep3PrimeFieldShare>& w, Rep3PrimeFieldShare* out_r = nullptr,
+                     Rep3PrimeFieldShare* out_s = nullptr) {
     check_witness_lengths(pk, w);
-    Rep3State state0(net0, seed);
-    const size_t n = pk.domain_size();
-    auto m1 = state0.masking_field_elements_vec(n), m2 = state0.masking_field_elements_vec(n);
-    Rep3PrimeFieldShare r = state0.rand(), s = state0.rand();            // groth16.rs:157
-    G1 g_a, g1_b, l_acc, h_acc;
-    G2 g2_b;
-    check(cs_groth16_rep3_local(ctx.h, pk.h, (int)state0.id.v, w.public_inputs[0].data(),
-                                w.witness.empty() ? nullptr : w.witness[0].a.data(), m1[0].data(), m2[0].data(), r.a.data(),
-                                s.a.data(), g_a.data(), g1_b.data(), g2_b.data(), l_acc.data(), h_acc.data()));
-    // rs = local_mul_vec([r], [s]) (groth16.rs:297; ops.rs:69-76)
-    Fr rs = fr_add(fr_add(fr_add(fr_mul(r.a, s.a), fr_mul(r.a, s.b)), fr_mul(r.b, s.a)), state0.masking_field_element());
-    G1 r_s_delta_g1 = pk.delta_g1 * rs;
-    // network round (groth16.rs:305-308): open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1
-    auto bc = broadcast(net0, g_a);
-    G1 g_a_opened = g_a + bc.first + bc.second;                           // pointshare.rs:152-155
-    G1 g1_b_prev = reshare(net1, g1_b);                                   // mpc/rep3.rs:158-160
-    G1 r_g1_b = g1_b * r.a + g1_b_prev * r.a + g1_b * r.b + state0.masking_ec_element(g1_generator);  // pointshare/ops.rs:95-102
-    G1 g_c = g_a_opened * s.a + r_g1_b + (-r_s_delta_g1) + l_acc + h_acc;  // groth16.rs:314-322
-    auto bc_c = broadcast(net0, g_c);                                     // groth16.rs:325-328
-    auto bc_b = broadcast(net1, g2_b);
-    if (out_r) *out_r = r;
-    if (out_s) *out_s = s;
-    return Proof{g_a_opened, g2_b + bc_b.first + bc_b.second, g_c + bc_c.first + bc_c.second};
+    NetAdapter n0(net0), n1(net1);
+    Rep3State state0(n0);
+    Proof p;
+    uint64_t rs[16];
+    check(cs_groth16_rep3_prove(ctx.h, pk.h, n0.h, n1.h, state0.h, w.public_inputs[0].data(),
+                                w.witness.empty() ? nullptr : w.witness[0].a.data(), nullptr, p.a.data(), p.b.data(),
+                                p.c.data(), rs));
+    if (out_r) { std::memcpy(out_r->a.data(), rs, 32); std::memcpy(out_r->b.data(), rs + 4, 32); }
+    if (out_s) { std::memcpy(out_s->a.data(), rs + 8, 32); std::memcpy(out_s->b.data(), rs + 12, 32); }
+    return p;
   }
 };
 

@@ -92,10 +92,8 @@ struct Round1Challenges {
     return c;
   }
   static Round1Challenges random() {
-    std::random_device rd;
-    std::mt19937_64 g(((uint64_t)rd() << 32) ^ rd());
     Round1Challenges c;
-    for (auto& x : c.b) x = co_groth16::Rep3State::draw(g);
+    for (auto& x : c.b) x = co_groth16::fr_rand();  // OS entropy, rejection-sampled
     return c;
   }
 };
@@ -138,8 +136,11 @@ struct Rep3CoPlonk {
     // correlated ChaCha streams: own seed, previous party's seed (rep3.rs:71-110)
     cs_rep3_prf prf;
     std::memset(&prf, 0, sizeof(prf));
-    std::mt19937_64 g(seed * 4 + id.v);
-    std::array<uint64_t, 4> own{g(), g(), g(), g()};
+    // seed1 from the OS entropy pool (ChaCha12Rng::from_entropy, rep3.rs:57); `seed` is kept in the signature for
+    // source compatibility with round-1 callers and is not used
+    (void)seed;
+    std::array<uint64_t, 4> own;
+    co_groth16::check(cs_os_random(reinterpret_cast<uint8_t*>(own.data()), 32));
     auto prev = co_groth16::reshare(net, own);
     std::memcpy(prf.seed1, own.data(), 32);
     std::memcpy(prf.seed2, prev.data(), 32);

@@ -47,7 +47,7 @@ int main(int argc, char** argv) {
   auto exp_a = rd.vec<uint64_t>(), exp_b = rd.vec<uint64_t>(), exp_c = rd.vec<uint64_t>();
   std::vector<Rep3PrimeFieldShare> shares[3] = {rd.vec<Rep3PrimeFieldShare>(), rd.vec<Rep3PrimeFieldShare>(), rd.vec<Rep3PrimeFieldShare>()};
   auto gen = rd.vec<uint64_t>();
-  G1 g1gen; std::memcpy(g1gen.data(), gen.data(), sizeof(G1));
+  (void)gen;
 
   // ---- Groth16::plain_prove with injected (r, s) == oracle proof bytes
   Context ctx(0);
@@ -83,7 +83,7 @@ int main(int argc, char** argv) {
         Context c(0);
         ProvingKey k(c, d);
         SharedWitness<Rep3PrimeFieldShare> sw{pub, shares[i]};
-        proofs[i] = Rep3CoGroth16::prove(c, *nets0[i], *nets1[i], k, sw, 1000 + i, g1gen, &rsh[i], &ssh[i]);
+        proofs[i] = Rep3CoGroth16::prove(c, *nets0[i], *nets1[i], k, sw, &rsh[i], &ssh[i]);
       } catch (const std::exception& e) { errs[i] = e.what(); }
     });
   for (auto& t : th) t.join();

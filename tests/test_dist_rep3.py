@@ -351,6 +351,10 @@ def _party_shamir(rank, port, emu_path, q):
         net = ShamirNetwork()
         prover = ShamirCoGroth16(ctx, pk)
         A, Bp, Cp = prover.prove(net, cv.fr(w[:ni]), cv.fr(mine), cv.g1([z["delta_g1"]])[0])
+        # privacy of the dealing: from every dealer this party holds ONE evaluation per sharing (its own row);
+        # two would determine the degree-1 polynomial and with it r(0), s(0)
+        view = net.last_received
+        assert len(view) == 3 and all(v.shape == (2, 4) for v in view)
         q.put((rank, cv.pt1(A), cv.pt2(Bp), cv.pt1(Cp), prover.last_randomness, net.bytes_sent))
         pk.free()
         ctx.close()

@@ -93,10 +93,101 @@ def test_ntt_fullsize_roundtrip_and_linearity(gpu_ctx):
     dom.free()
 
 
-def test_groth16_2p20_proof_verifies(gpu_ctx):
+@pytest.fixture(scope="module")
+def syn20(gpu_ctx):
+    """BASELINE configs[1]/[2]: the synthetic 2^20-constraint R1CS with a valid (known toxic waste) key."""
     from workloads.synth_groth16 import SynthGroth16
+    return SynthGroth16(gpu_ctx, 20)
+
+
+def test_groth16_2p20_proof_bytes_equal_oracle_c(gpu_ctx, syn20):
+    """Bit-exact at BASELINE size: the GPU proof at 2^20 constraints equals the proof of the CPU restatement
+    (oracle/c, OpenMP) for the same valid key, witness and (r, s) -- A, B, C byte for byte."""
+    from oracle.c import run as oc
     cv = Conv("bn254")
-    syn = SynthGroth16(gpu_ctx, 20)
+    syn = syn20
+    pk = syn.make_key()
+    rng = random.Random(11)
+    r_m, s_m = cv.fr([rng.randrange(cv.r)]), cv.fr([rng.randrange(cv.r)])
+    A, Bp, Cp = pk.prove_plain(syn.public_inputs, syn.private_witness, r_m, s_m)
+    desc, keep = oc.key_desc(syn.matrices, syn.points)
+    a, b, c = oc.prove_plain(desc, syn.public_inputs, syn.private_witness, r_m, s_m)
+    assert (A == a).all() and (Bp == b).all() and (Cp == c).all(), "GPU proof bytes differ from oracle/c at 2^20"
+    # the witness map alone, all 2^20 half shares
+    h_gpu = pk.witness_map(syn.public_inputs, syn.private_witness)
+    h_cpu = oc.witness_map(desc, 0, 0, syn.public_inputs, syn.private_witness)
+    assert (h_gpu == h_cpu).all()
+    pk.free()
+    del keep
+
+
+def test_groth16_rep3_2p20_opens_to_oracle_c_proof(gpu_ctx, syn20):
+    """The metric's own configuration (co-Groth16, 3-party Rep3, 2^20 constraints), three parties as threads on this
+    GPU through the library's protocol (cs_groth16_rep3_prove over mailbox nets): every party returns the same
+    proof, and it equals oracle/c's plain proof for r = sum r_i.a, s = sum s_i.a -- bit-exact at full size."""
+    import threading
+    from co_snarks_b200.rep3 import random_field_limbs
+    from oracle.c import run as oc
+    cv = Conv("bn254")
+    syn = syn20
+    lib = gpu_ctx.lib
+    # replicated sharing of the witness (rep3.rs:281-293), vectorised: x = x0 + x1 + x2
+    share_rng = np.random.Generator(np.random.PCG64(5))
+    nw = syn.private_witness.shape[0]
+    x0, x1 = random_field_limbs(share_rng, nw), random_field_limbs(share_rng, nw)
+    d0, d1, dw = gpu_ctx.to_device(x0), gpu_ctx.to_device(x1), gpu_ctx.to_device(syn.private_witness)
+    # shares are Montgomery representations: treat the random limbs as such and subtract on the device
+    gpu_ctx._check(lib.cs_vec_sub(gpu_ctx.h, cv.id, dw, d0, dw, nw))
+    gpu_ctx._check(lib.cs_vec_sub(gpu_ctx.h, cv.id, dw, d1, dw, nw))
+    x2 = gpu_ctx.d2h(dw, (nw, 4))
+    for d in (d0, d1, dw):
+        gpu_ctx.free(d)
+    xs = (x0, x1, x2)
+    ctxs = [B.Context(0) for _ in range(3)]
+    pks = [B.Groth16Key(c, B.CS_BN254, syn.matrices, syn.points) for c in ctxs]
+    nets0 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    nets1 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    for i in range(3):
+        nets0[i].connect_local(nets0)
+        nets1[i].connect_local(nets1)
+    seeds = [B.os_random(lib, 32) for _ in range(3)]
+    states = [B.Rep3StateC.from_seeds(lib, i, seeds[i], seeds[(i + 2) % 3]) for i in range(3)]
+    out, errs = {}, []
+
+    def party(i):
+        try:
+            sh = np.ascontiguousarray(np.concatenate([xs[i], xs[(i + 2) % 3]], axis=1))
+            out[i] = pks[i].rep3_prove(nets0[i], nets1[i], states[i], syn.public_inputs, sh, want_rs=True)
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=party, args=(i,)) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    for i in (1, 2):
+        assert all((out[i][k] == out[0][k]).all() for k in range(3)), "parties disagree on the proof"
+    rs = [cv.fr_back(out[i][3]) for i in range(3)]
+    r_tot = sum(x[0] for x in rs) % cv.r
+    s_tot = sum(x[2] for x in rs) % cv.r
+    desc, keep = oc.key_desc(syn.matrices, syn.points)
+    a, b, c = oc.prove_plain(desc, syn.public_inputs, syn.private_witness, cv.fr([r_tot]), cv.fr([s_tot]))
+    assert (out[0][0] == a).all() and (out[0][1] == b).all() and (out[0][2] == c).all(), \
+        "opened Rep3 proof at 2^20 differs from oracle/c's plain proof for (sum r, sum s)"
+    assert all(0 < n.bytes_sent < 2048 for n in nets0 + nets1)
+    for pk in pks:
+        pk.free()
+    for n in nets0 + nets1:
+        n.free()
+    for c_ in ctxs:
+        c_.close()
+    del keep
+
+
+def test_groth16_2p20_proof_verifies(gpu_ctx, syn20):
+    cv = Conv("bn254")
+    syn = syn20
     pk = syn.make_key()
     rng = random.Random(3)
     r_, s_ = rng.randrange(cv.r), rng.randrange(cv.r)

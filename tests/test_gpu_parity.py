@@ -152,3 +152,10 @@ def test_plonk_zkey_ingest(gpu_ctx, tmp_path):
 
 def test_crs_file_ingest(gpu_ctx, tmp_path):
     K.check_crs_file_ingest(gpu_ctx, tmp_path)
+
+
+def test_groth16_bls12_381(gpu_ctx):
+    """Groth16 on the BLS12-381 instantiation (6-limb Fq, 255-bit Fr) on the GPU: witness map + five MSMs + assembly on
+    the reference's bls12_381/multiplier2 fixture; proof bytes == oracle, accepted by the BLS12-381 pairing check
+    under the snarkjs verification key (the acceptance criterion of co-groth16/src/lib.rs:93-119)."""
+    K.check_groth16_fixture(gpu_ctx, "multiplier2", rep3=False, curve="bls12_381")
