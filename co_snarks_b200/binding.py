@@ -159,6 +159,8 @@ SIGNATURES = {
     "cs_wtns_read": (C.c_int, [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "cs_groth16_pk_free": (None, [C.c_void_p]),
     "cs_groth16_domain_size": (C.c_size_t, [C.c_void_p]),
+    "cs_groth16_pk_curve": (C.c_int, [C.c_void_p]),
+    "cs_plonk_pk_curve": (C.c_int, [C.c_void_p]),
     "cs_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_witness_map_libsnark": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_groth16_prove_plain": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -508,14 +510,19 @@ class PlonkKey:
         del keep
 
     @classmethod
-    def from_zkey(cls, ctx, path, curve=CS_BN254):
-        """snarkjs Plonk .zkey -> device-resident key (cs_plonk_pk_from_zkey)."""
+    def from_zkey(cls, ctx, path, curve=None):
+        """snarkjs Plonk .zkey -> device-resident key (cs_plonk_pk_from_zkey); the curve is the one the zkey
+        declares, `curve` only asserts it."""
         self = cls.__new__(cls)
-        self.ctx, self.curve = ctx, curve
+        self.ctx = ctx
         h, npub, nwit = C.c_void_p(), C.c_size_t(), C.c_size_t()
         ctx._check(ctx.lib.cs_plonk_pk_from_zkey(ctx.h, str(path).encode(), C.byref(h), C.byref(npub), C.byref(nwit)))
         self.h, self.n_public, self.n_witness = h, npub.value, nwit.value
-        self.fq = limbs_of(curve, "fq")
+        self.curve = int(ctx.lib.cs_plonk_pk_curve(h))
+        if curve is not None and curve != self.curve:
+            ctx.lib.cs_plonk_pk_free(h)
+            raise CsError("%s is a curve-%d key, curve %d was requested" % (path, self.curve, curve))
+        self.fq = limbs_of(self.curve, "fq")
         return self
 
     def info(self):
@@ -648,17 +655,22 @@ class Groth16Key:
         del keep
 
     @classmethod
-    def from_zkey(cls, ctx, path, curve=CS_BN254, window_bits=0):
-        """Groth16ZKey::from_reader + upload in one step (cs_groth16_pk_from_zkey)."""
+    def from_zkey(cls, ctx, path, curve=None, window_bits=0):
+        """Groth16ZKey::from_reader + upload in one step (cs_groth16_pk_from_zkey).  The curve is the one the
+        zkey declares (its base-field modulus); passing `curve` only asserts it."""
         self = cls.__new__(cls)
-        self.ctx, self.curve = ctx, curve
+        self.ctx = ctx
         h = C.c_void_p()
         npub = C.c_size_t(0)
         ctx._check(ctx.lib.cs_groth16_pk_from_zkey(ctx.h, os.fsencode(path), window_bits, C.byref(h), C.byref(npub)))
         self.h = h
+        self.curve = int(ctx.lib.cs_groth16_pk_curve(h))
+        if curve is not None and curve != self.curve:
+            ctx.lib.cs_groth16_pk_free(h)
+            raise CsError("%s is a curve-%d key, curve %d was requested" % (path, self.curve, curve))
         self.ni = npub.value + 1
         self.nw = None
-        self.fq = limbs_of(curve, "fq")
+        self.fq = limbs_of(self.curve, "fq")
         return self
 
     def domain_size(self):

@@ -624,6 +624,7 @@ void cs_groth16_pk_free(cs_groth16_pk* pk) {
 }
 
 size_t cs_groth16_domain_size(const cs_groth16_pk* pk) { return pk ? pk->n : 0; }
+int cs_groth16_pk_curve(const cs_groth16_pk* pk) { return pk ? pk->curve : CS_ERR_ARG; }
 
 int cs_groth16_witness_map(cs_ctx* ctx, cs_groth16_pk* pk, cs_share_kind kind, int party, const uint64_t* h_pub,
                            const uint64_t* h_wit, const uint64_t* h_m1, const uint64_t* h_m2, uint64_t* h_out) {

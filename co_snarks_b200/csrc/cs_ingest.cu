@@ -41,7 +41,7 @@ int read_file(const char* path, const char* magic, Sections& s) {
     memcpy(&typ, s.data.data() + off, 4);
     memcpy(&len, s.data.data() + off + 4, 8);
     off += 12;
-    if (off + len > s.data.size()) return fail(CS_ERR_ARG, "%s: section %u exceeds the file", path, typ);
+    if (len > s.data.size() - off) return fail(CS_ERR_ARG, "%s: section %u exceeds the file", path, typ);
     if (!s.sec.count(typ)) s.sec[typ] = {off, (size_t)len};
     off += len;
   }
@@ -84,9 +84,16 @@ int cs_groth16_pk_from_zkey(cs_ctx* ctx, const char* path, int window_bits, cs_g
   const uint8_t* d = z.data.data();
   if (rd32(d + z.sec[1].first) != 1) return fail(CS_ERR_ARG, "%s: not a Groth16 zkey (protocol %u)", path, rd32(d + z.sec[1].first));
   const uint8_t* h = d + z.sec[2].first;
+  const size_t hlen = z.sec[2].second;
+  // sizes come from the file: validate each before it is used to form a pointer
+  if (hlen < 4) return fail(CS_ERR_ARG, "%s: header section too short", path);
   uint32_t n8q = rd32(h);
+  if (n8q != 32 && n8q != 48) return fail(CS_ERR_ARG, "%s: unsupported base field size %u", path, n8q);
+  if (hlen < 4 + (size_t)n8q + 4) return fail(CS_ERR_ARG, "%s: header section too short", path);
   const uint8_t* q = h + 4;
   uint32_t n8r = rd32(q + n8q);
+  if (n8r != 32) return fail(CS_ERR_ARG, "%s: unexpected scalar field size %u", path, n8r);
+  if (hlen < 4 + (size_t)n8q + 4 + n8r + 12) return fail(CS_ERR_ARG, "%s: header section too short", path);
   const uint8_t* p = q + n8q + 4 + n8r;
   int curve = detect_curve(q, n8q);
   if (curve < 0) return fail(CS_ERR_ARG, "%s: unsupported curve (base field of %u bytes)", path, n8q);
@@ -113,6 +120,7 @@ int cs_groth16_pk_from_zkey(cs_ctx* ctx, const char* path, int window_bits, cs_g
   }
   if (ncoef && max_row + 1 < n_public + 1) return fail(CS_ERR_ARG, "%s: fewer rows than public inputs", path);
   const size_t ni = (size_t)n_public + 1;
+  if (n_vars < ni) return fail(CS_ERR_ARG, "%s: nVars %u is smaller than nPublic + 1", path, n_vars);
   const size_t nc = ncoef ? (size_t)max_row + 1 - ni : 0;
   std::vector<uint32_t> rp[2], col[2];
   std::vector<uint64_t> cf[2];
@@ -190,9 +198,15 @@ int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size
   const uint8_t* d = z.data.data();
   if (rd32(d + z.sec[1].first) != 2) return fail(CS_ERR_ARG, "%s: not a Plonk zkey (protocol %u)", path, rd32(d + z.sec[1].first));
   const uint8_t* h = d + z.sec[2].first;
+  const size_t hlen = z.sec[2].second;
+  if (hlen < 4) return fail(CS_ERR_ARG, "%s: header section too short", path);
   const uint32_t n8q = rd32(h);
+  if (n8q != 32 && n8q != 48) return fail(CS_ERR_ARG, "%s: unsupported base field size %u", path, n8q);
+  if (hlen < 4 + (size_t)n8q + 4) return fail(CS_ERR_ARG, "%s: header section too short", path);
   const uint8_t* q = h + 4;
   const uint32_t n8r = rd32(q + n8q);
+  if (n8r != 32) return fail(CS_ERR_ARG, "%s: unexpected scalar field size %u", path, n8r);
+  if (hlen < 4 + (size_t)n8q + 4 + n8r + 20) return fail(CS_ERR_ARG, "%s: header section too short", path);
   const uint8_t* p = q + n8q + 4 + n8r;
   const int curve = detect_curve(q, n8q);
   if (curve < 0) return fail(CS_ERR_ARG, "%s: unsupported curve (base field of %u bytes)", path, n8q);
@@ -261,6 +275,8 @@ int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size
   k.lagrange_evals = lag.data();
   k.p_tau = aligned(d + z.sec[14].first, z.sec[14].second);
   k.n_p_tau = z.sec[14].second / g1;
+  if ((size_t)k.n_vars < (size_t)k.n_additions + k.n_public + 1)
+    return fail(CS_ERR_ARG, "%s: nVars %zu is smaller than nAdditions + nPublic + 1", path, (size_t)k.n_vars);
   if (out_n_public) *out_n_public = k.n_public;
   if (out_n_witness) *out_n_witness = (size_t)k.n_vars - k.n_additions - k.n_public - 1;
   return cs_plonk_pk_create(ctx, &k, out);
@@ -296,9 +312,20 @@ int cs_wtns_read(const char* path, cs_curve curve, uint64_t* out_mont, size_t ca
   CS_TRY(read_file(path, "wtns", w));
   if (!w.sec.count(1) || !w.sec.count(2)) return fail(CS_ERR_ARG, "%s: missing section", path);
   const uint8_t* h = w.data.data() + w.sec[1].first;
+  if (w.sec[1].second < 4) return fail(CS_ERR_ARG, "%s: header section too short", path);
   uint32_t n8 = rd32(h);
-  uint32_t nvars = rd32(h + 4 + n8);
   if (n8 != 32) return fail(CS_ERR_ARG, "%s: unexpected field size %u", path, n8);
+  if (w.sec[1].second < 4 + (size_t)n8 + 4) return fail(CS_ERR_ARG, "%s: header section too short", path);
+  uint32_t nvars = rd32(h + 4 + n8);
+  {  // the witness must live in the scalar field of the curve it is converted for
+    bool ok = true;
+    for (int i = 0; i < 8; i++) {
+      const uint32_t want = curve == CS_BN254 ? Bn254Fr::mod(i) : Bls381Fr::mod(i);
+      ok = ok && rd32(h + 4 + 4 * i) == want;
+    }
+    if (curve != CS_BN254 && curve != CS_BLS12_381) return fail(CS_ERR_ARG, "cs_wtns_read: unsupported curve id %d", (int)curve);
+    if (!ok) return fail(CS_ERR_ARG, "%s: the witness prime is not the scalar field of %s", path, curve == CS_BN254 ? "BN254" : "BLS12-381");
+  }
   if ((size_t)nvars * n8 > w.sec[2].second) return fail(CS_ERR_ARG, "%s: values section too short", path);
   *out_n = nvars;
   if (!out_mont) return 0;  // size query

@@ -865,6 +865,8 @@ void cs_plonk_pk_free(cs_plonk_pk* pk) {
   delete pk;
 }
 
+int cs_plonk_pk_curve(const cs_plonk_pk* pk) { return pk ? pk->curve : CS_ERR_ARG; }
+
 int cs_plonk_pk_info(const cs_plonk_pk* pk, size_t* n_public, size_t* n_witness, size_t* domain_size, uint64_t* vk_points) {
   if (!pk) return fail(CS_ERR_ARG, "cs_plonk_pk_info: NULL key");
   if (n_public) *n_public = pk->n_public;
@@ -978,6 +980,15 @@ int cs_plonk_rep3_round1(cs_plonk_rep3* s, const cs_rep3_prf* prf, const uint64_
 int cs_plonk_rep3_step(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out) {
   if (!s) return fail(CS_ERR_ARG, "cs_plonk_rep3_step: NULL session");
   CS_CUDA(cudaSetDevice(s->ctx->device));
+  // which steps read h_in / write h_out: a missing buffer is an argument error, not a crash
+  {
+    const bool needs_in = step == CS_PLONK_R3_ROUND2_A || step == CS_PLONK_R3_ROUND3_A || step == CS_PLONK_R3_ROUND4 ||
+                          step == CS_PLONK_R3_ROUND5;
+    const bool needs_out = step == CS_PLONK_R3_ROUND2_G || step == CS_PLONK_R3_ROUND3_B || step == CS_PLONK_R3_ROUND4 ||
+                           step == CS_PLONK_R3_ROUND5;
+    if (needs_in && !h_in) return fail(CS_ERR_ARG, "cs_plonk_rep3_step: step %d reads h_in, which is NULL", step);
+    if (needs_out && !h_out) return fail(CS_ERR_ARG, "cs_plonk_rep3_step: step %d writes h_out, which is NULL", step);
+  }
   switch (s->pk->curve) {
     case CS_BN254: return r3_step_t<Bn254Cfg>(s, step, h_in, h_out);
 #if defined(CS_ENABLE_BLS12_381)

@@ -72,58 +72,62 @@ class Rep3CoPlonk:
         pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
         if blinder_shares is None:  # Round1Challenges::random (round1.rs:82-92): eleven T::rand shares
             blinder_shares = np.stack([state.rand() for _ in range(11)])
-        pts = s.round1(state.prf_args(), pub, witness_shares, blinder_shares)
-        abc = yield ("sum_points", pts)
-        t = Transcript(lib, cv)
-        for P in np.asarray(vk_points, dtype=np.uint64).reshape(8, 2 * fq):
-            t.add_point(P)
-        for v in pub[1:]:
-            t.add_scalar(v)
-        for P in abc:
-            t.add_point(P)
-        beta = t.get_challenge()
-        t = Transcript(lib, cv)
-        t.add_scalar(beta)
-        gamma = t.get_challenge()
-        s.step(B.R3_ROUND2_A, np.stack([beta, gamma]))
-        yield ("reshare", ([0, 1], n))
-        s.step(B.R3_ROUND2_B)
-        yield ("reshare", ([2, 3], n))
-        s.step(B.R3_ROUND2_C)
-        yield ("sum_dev", 2 * n + 1)  # device-resident opening: sess.d_out summed over the parties into sess.d_in
-        s.step(B.R3_ROUND2_D)
-        yield ("reshare", ([4, 5], n))
-        s.step(B.R3_ROUND2_E)
-        yield ("reshare", ([6], n))
-        s.step(B.R3_ROUND2_F)
-        yield ("sum_dev", n)
-        zp = s.step(B.R3_ROUND2_G, None, (1, 2 * fq))
-        (Z,) = yield ("sum_points", zp)
-        t = Transcript(lib, cv)
-        t.add_scalar(beta)
-        t.add_scalar(gamma)
-        t.add_point(Z)
-        alpha = t.get_challenge()
-        s.step(B.R3_ROUND3_A, alpha.reshape(1, 4))
-        yield ("reshare", (list(range(12)), 4 * n))
-        tp = s.step(B.R3_ROUND3_B, None, (3, 2 * fq))
-        T = yield ("sum_points", tp)
-        t = Transcript(lib, cv)
-        t.add_scalar(alpha)
-        for P in T:
-            t.add_point(P)
-        xi = t.get_challenge()
-        ev = s.step(B.R3_ROUND4, xi.reshape(1, 4), (6, 4))
-        opened = yield ("sum_vec", ev[:4])
-        ea, eb, ec, ezw = opened
-        es1, es2 = ev[4], ev[5]
-        t = Transcript(lib, cv)
-        for v in (xi, ea, eb, ec, es1, es2, ezw):
-            t.add_scalar(v)
-        v0 = t.get_challenge()
-        wp = s.step(B.R3_ROUND5, np.stack([xi, v0, ea, eb, ec, es1, es2, ezw]), (2, 2 * fq))
-        W = yield ("sum_points", wp)
-        state.advance(s.prf_words())
+        # The streams move past whatever this proof consumed even when it aborts half-way (e.g. "Cannot invert
+        # zero", a transport error, the caller dropping the generator): PRF output is never used twice.
+        try:
+            pts = s.round1(state.prf_args(), pub, witness_shares, blinder_shares)
+            abc = yield ("sum_points", pts)
+            t = Transcript(lib, cv)
+            for P in np.asarray(vk_points, dtype=np.uint64).reshape(8, 2 * fq):
+                t.add_point(P)
+            for v in pub[1:]:
+                t.add_scalar(v)
+            for P in abc:
+                t.add_point(P)
+            beta = t.get_challenge()
+            t = Transcript(lib, cv)
+            t.add_scalar(beta)
+            gamma = t.get_challenge()
+            s.step(B.R3_ROUND2_A, np.stack([beta, gamma]))
+            yield ("reshare", ([0, 1], n))
+            s.step(B.R3_ROUND2_B)
+            yield ("reshare", ([2, 3], n))
+            s.step(B.R3_ROUND2_C)
+            yield ("sum_dev", 2 * n + 1)  # device-resident opening: sess.d_out summed over the parties into sess.d_in
+            s.step(B.R3_ROUND2_D)
+            yield ("reshare", ([4, 5], n))
+            s.step(B.R3_ROUND2_E)
+            yield ("reshare", ([6], n))
+            s.step(B.R3_ROUND2_F)
+            yield ("sum_dev", n)
+            zp = s.step(B.R3_ROUND2_G, None, (1, 2 * fq))
+            (Z,) = yield ("sum_points", zp)
+            t = Transcript(lib, cv)
+            t.add_scalar(beta)
+            t.add_scalar(gamma)
+            t.add_point(Z)
+            alpha = t.get_challenge()
+            s.step(B.R3_ROUND3_A, alpha.reshape(1, 4))
+            yield ("reshare", (list(range(12)), 4 * n))
+            tp = s.step(B.R3_ROUND3_B, None, (3, 2 * fq))
+            T = yield ("sum_points", tp)
+            t = Transcript(lib, cv)
+            t.add_scalar(alpha)
+            for P in T:
+                t.add_point(P)
+            xi = t.get_challenge()
+            ev = s.step(B.R3_ROUND4, xi.reshape(1, 4), (6, 4))
+            opened = yield ("sum_vec", ev[:4])
+            ea, eb, ec, ezw = opened
+            es1, es2 = ev[4], ev[5]
+            t = Transcript(lib, cv)
+            for v in (xi, ea, eb, ec, es1, es2, ezw):
+                t.add_scalar(v)
+            v0 = t.get_challenge()
+            wp = s.step(B.R3_ROUND5, np.stack([xi, v0, ea, eb, ec, es1, es2, ezw]), (2, 2 * fq))
+            W = yield ("sum_points", wp)
+        finally:
+            state.advance(s.prf_words())
         points = np.concatenate([abc, Z.reshape(1, -1), T, W])  # A B C Z T1 T2 T3 Wxi Wxiw
         evals = np.stack([ea, eb, ec, es1, es2, ezw])
         return points, evals

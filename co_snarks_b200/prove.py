@@ -16,22 +16,30 @@ import numpy as np
 
 from . import binding as B
 
-BN254_R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
-BN254_Q = 21888242871839275222246405745257275088696311157297823662689037894645226208583
+# scalar-field moduli and snarkjs curve names, by cs_curve id (the key tells which one applies)
+R_MOD = {B.CS_BN254: 21888242871839275222246405745257275088548364400416034343698204186575808495617,
+         B.CS_BLS12_381: 52435875175126190479447740508185965837690552500527637822603658699938581184513}
+CURVE_NAME = {B.CS_BN254: "bn128", B.CS_BLS12_381: "bls12381"}
 
 
-def _canon(lib, arr, field):
+def _canon(lib, arr, field, curve=B.CS_BN254):
+    nl = B.limbs_of(curve, field)
     out = np.zeros_like(arr)
     fn = lib.cs_fq_from_mont if field == "fq" else lib.cs_fr_from_mont
-    fn(B.CS_BN254, B._ptr(np.ascontiguousarray(arr)), B._ptr(out), arr.size // 4)
-    return B.limbs_to_ints(out.reshape(-1, 4))
+    fn(curve, B._ptr(np.ascontiguousarray(arr)), B._ptr(out), arr.size // nl)
+    return B.limbs_to_ints(out.reshape(-1, nl))
 
 
-def proof_json(lib, A, Bp, C):
-    a, b, c = _canon(lib, A, "fq"), _canon(lib, Bp, "fq"), _canon(lib, C, "fq")
+def _rand_fr(curve, k):
+    r = R_MOD[curve]
+    return B.ints_to_limbs(B.to_mont_ints([secrets.randbelow(r) for _ in range(k)], r, 4), 4)
+
+
+def proof_json(lib, A, Bp, C, curve=B.CS_BN254):
+    a, b, c = _canon(lib, A, "fq", curve), _canon(lib, Bp, "fq", curve), _canon(lib, C, "fq", curve)
     return {"pi_a": [str(a[0]), str(a[1]), "1"],
             "pi_b": [[str(b[0]), str(b[1])], [str(b[2]), str(b[3])], ["1", "0"]],
-            "pi_c": [str(c[0]), str(c[1]), "1"], "protocol": "groth16", "curve": "bn128"}
+            "pi_c": [str(c[0]), str(c[1]), "1"], "protocol": "groth16", "curve": CURVE_NAME[curve]}
 
 
 def zkey_protocol(path):
@@ -48,18 +56,18 @@ def zkey_protocol(path):
     raise ValueError("%s: no protocol section" % path)
 
 
-def plonk_proof_json(lib, pts, evs):
+def plonk_proof_json(lib, pts, evs, curve=B.CS_BN254):
     names = ("A", "B", "C", "Z", "T1", "T2", "T3", "Wxi", "Wxiw")
     out = {}
     for k, P in zip(names, pts):
-        c = _canon(lib, P, "fq")
+        c = _canon(lib, P, "fq", curve)
         out[k] = ["0", "1", "0"] if not any(c) else [str(c[0]), str(c[1]), "1"]
-    e = _canon(lib, evs, "fr")
+    e = _canon(lib, evs, "fr", curve)
     proof = {k: out[k] for k in names[:7]}
     for k, v in zip(("eval_a", "eval_b", "eval_c", "eval_s1", "eval_s2", "eval_zw"), e):
         proof[k] = str(v)
     proof["Wxi"], proof["Wxiw"] = out["Wxi"], out["Wxiw"]
-    proof["protocol"], proof["curve"] = "plonk", "bn128"
+    proof["protocol"], proof["curve"] = "plonk", CURVE_NAME[curve]
     return proof
 
 
@@ -75,33 +83,35 @@ def main(argv=None):
     ctx = B.Context(args.device, lib_path=args.lib)
     t0 = time.time()
     if zkey_protocol(args.zkey) == 2:
-        pk = B.PlonkKey.from_zkey(ctx, args.zkey)
-        wit = B.read_wtns(ctx.lib, args.wtns)
+        pk = B.PlonkKey.from_zkey(ctx, args.zkey)  # the curve comes from the zkey
+        cv = pk.curve
+        wit = B.read_wtns(ctx.lib, args.wtns, cv)  # rejects a witness over another field
         t1 = time.time()
-        bl = B.ints_to_limbs(B.to_mont_ints([secrets.randbelow(BN254_R) for _ in range(11)], BN254_R, 4), 4)
+        bl = _rand_fr(cv, 11)
         ni = pk.n_public + 1
         pts, evs = pk.prove_plain(np.ascontiguousarray(wit[:ni]), np.ascontiguousarray(wit[ni:]), bl)
         t2 = time.time()
         with open(args.out, "w") as f:
-            json.dump(plonk_proof_json(ctx.lib, pts, evs), f)
+            json.dump(plonk_proof_json(ctx.lib, pts, evs, cv), f)
         if args.public_out:
             with open(args.public_out, "w") as f:
-                json.dump([str(x) for x in _canon(ctx.lib, wit[1:ni], "fr")], f)
+                json.dump([str(x) for x in _canon(ctx.lib, wit[1:ni], "fr", cv)], f)
         print("key+witness load %.1f ms, Generate proof took %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
         pk.free()
         ctx.close()
         return
-    pk = B.Groth16Key.from_zkey(ctx, args.zkey)
-    wit = B.read_wtns(ctx.lib, args.wtns)
+    pk = B.Groth16Key.from_zkey(ctx, args.zkey)  # the curve comes from the zkey
+    cv = pk.curve
+    wit = B.read_wtns(ctx.lib, args.wtns, cv)
     t1 = time.time()
-    rs = B.ints_to_limbs(B.to_mont_ints([secrets.randbelow(BN254_R), secrets.randbelow(BN254_R)], BN254_R, 4), 4)
+    rs = _rand_fr(cv, 2)
     A, Bp, C = pk.prove_plain(np.ascontiguousarray(wit[:pk.ni]), np.ascontiguousarray(wit[pk.ni:]), rs[0:1], rs[1:2])
     t2 = time.time()
     with open(args.out, "w") as f:
-        json.dump(proof_json(ctx.lib, A, Bp, C), f)
+        json.dump(proof_json(ctx.lib, A, Bp, C, cv), f)
     if args.public_out:
         with open(args.public_out, "w") as f:
-            json.dump([str(x) for x in _canon(ctx.lib, wit[1:pk.ni], "fr")], f)
+            json.dump([str(x) for x in _canon(ctx.lib, wit[1:pk.ni], "fr", cv)], f)
     print("key+witness load %.1f ms, Generate proof took %.1f ms" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
     pk.free()
     ctx.close()

@@ -194,6 +194,8 @@ typedef struct {
 int cs_groth16_pk_create(cs_ctx* ctx, const cs_groth16_key_desc* desc, cs_groth16_pk** out);
 void cs_groth16_pk_free(cs_groth16_pk* pk);
 size_t cs_groth16_domain_size(const cs_groth16_pk* pk);
+/* the curve the key was built for (cs_curve; read from the zkey's base-field modulus by cs_groth16_pk_from_zkey) */
+int cs_groth16_pk_curve(const cs_groth16_pk* pk);
 
 /* snarkjs file ingest (what co-circom does with taceo-circom-types before calling prove,
  * co-circom/co-circom/src/bin/co-circom.rs:1005-1016): a Groth16 .zkey goes straight to the device-resident
@@ -409,6 +411,7 @@ int cs_bases_from_crs_file(cs_ctx* ctx, const char* path, size_t offset, size_t 
  * out_n_witness = number of private witness values a proof takes (nVars - nAdditions - nPublic - 1). */
 int cs_plonk_pk_from_zkey(cs_ctx* ctx, const char* path, cs_plonk_pk** out, size_t* out_n_public, size_t* out_n_witness);
 void cs_plonk_pk_free(cs_plonk_pk* pk);
+int cs_plonk_pk_curve(const cs_plonk_pk* pk);
 /* what a driver needs to know about an uploaded key: counts and the eight verification-key commitments
  * (Qm Ql Qr Qo Qc S1 S2 S3, affine Montgomery) that open the transcript; any output pointer may be NULL */
 int cs_plonk_pk_info(const cs_plonk_pk* pk, size_t* n_public, size_t* n_witness, size_t* domain_size, uint64_t* vk_points);
