@@ -192,6 +192,19 @@ int bases_upload_t(cs_ctx* ctx, const uint64_t* h_points, size_t n, int window_b
             b->infmask.as<uint32_t>());
   CS_LAUNCH(k_msm_precompute<F>, ceil_div(n, 128), 128, 0, ctx->stream, b->table.as<Affine<F>>(), (uint32_t)n,
             b->sh.c, b->sh.W);
+  // BN254 G1, opt-in (CS_MSM_F52=1): bucket accumulation on the FP64 pipe (cs_msm52.cuh); its table holds the
+  // coordinates in the radix-2^260 Montgomery form.  Measured on B200 (profiles/r2_f52_accum0_ab.log): bit-exact,
+  // 3.06 ms against 2.86 ms for the integer-pipe kernel at 2^20 -- the integer kernel stays the default.
+  if (G == 0 && std::is_same<Cfg, Bn254Cfg>::value) {
+    static int f52_env = -1;
+    if (f52_env < 0) { const char* e = getenv("CS_MSM_F52"); f52_env = e ? atoi(e) : 0; }
+    if (f52_env) {
+      const size_t ncoords = total * 2;
+      CS_LAUNCH(k_msm_table_to_m260<Bn254Fq52 COMMA Bn254Fq>, ceil_div(ncoords, 128), 128, 0, ctx->stream,
+                b->table.as<uint32_t>(), ncoords);
+      b->m260 = true;
+    }
+  }
   CS_CUDA(cudaGetLastError());
   CS_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -203,7 +216,7 @@ int msm_enqueue_t(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, siz
   typedef typename GroupOf<Cfg, G>::F F;
   return msm_enqueue<F, typename Cfg::FrP>(ctx->msm_ws[slot], b->table.as<Affine<F>>(), b->infmask.as<uint32_t>(), (uint32_t)b->n, b->sh,
                                            (uint32_t)offset, d_scalars, sstride, (uint32_t)n, mont, st,
-                                           sort_slot >= 0 ? &ctx->msm_ws[sort_slot] : nullptr);
+                                           sort_slot >= 0 ? &ctx->msm_ws[sort_slot] : nullptr, b->m260);
 }
 
 // After the stream has drained: XYZZ (pinned) -> affine on the host.

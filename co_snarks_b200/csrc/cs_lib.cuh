@@ -7,6 +7,7 @@
 #include "cs_params.cuh"
 #include "cs_curve.cuh"
 #include "cs_msm.cuh"
+#include "cs_msm52.cuh"
 #include "cs_ntt.cuh"
 #include "cs_vec.cuh"
 #include "cs_prf.cuh"
@@ -63,6 +64,7 @@ struct cs_bases {
   cs::MsmShape sh{};
   cs::DevBuf table;    // W * n affine points
   cs::DevBuf infmask;  // 1 bit per base: point at infinity
+  bool m260 = false;   // table coordinates are in the radix-2^260 Montgomery form: accumulate on the FP64 pipe (cs_msm52.cuh)
 };
 
 struct cs_domain {

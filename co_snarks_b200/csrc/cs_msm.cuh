@@ -486,6 +486,12 @@ struct MsmWorkspace {
   }
 };
 
+// FP64-pipe accumulation (cs_msm52.cuh); defined for the fields that have 52-bit-limb constants
+template <class F>
+int msm_accum0_f52(const Affine<F>* table, const uint32_t* sorted, const uint32_t* count, const uint32_t* start,
+                   const uint32_t* sstart0, uint32_t nb1, uint32_t S, const uint32_t* order, const uint32_t* order_b,
+                   Xyzz<F>* part0, uint32_t max_s0, cudaStream_t st);
+
 // Enqueue one MSM on `st`.  d_scalars: device, n elements of Fr (8 x u32).  The XYZZ result lands in
 // ws.h_result (pinned) after the stream drains.
 // sort_from (optional): another workspace whose MSM was enqueued over the SAME scalars with the same table
@@ -496,7 +502,7 @@ template <class F, class FrP>
 int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmask, uint32_t nbases, MsmShape sh,
                 uint32_t offset,
                 const uint32_t* d_scalars, uint32_t sstride, uint32_t n, int mont, cudaStream_t st,
-                MsmWorkspace* sort_from = nullptr) {
+                MsmWorkspace* sort_from = nullptr, bool table_m260 = false) {
   const uint32_t nb1 = sh.B + 1;
   const size_t nent = (size_t)sh.W * n;
   if (nent >= (1ull << 31) || (size_t)sh.W * nbases >= (1ull << 31))
@@ -582,6 +588,10 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
     static int minb_env = -1;
     if (minb_env < 0) { const char* e = getenv("CS_ACCUM0_MINB"); minb_env = e ? atoi(e) : 0; }
     const int minb = minb_env ? minb_env : (sizeof(F) > 32 ? 3 : 4);
+    if (table_m260) {
+      CS_TRY((msm_accum0_f52<F>(table, so.sorted.as<uint32_t>(), count, start, sstart0, nb1, S, order, order_b,
+                                ws.part0.as<Xyzz<F>>(), (uint32_t)max_s0, st)));
+    } else {
 #define CS_ACC0(M)                                                                                              \
   CS_LAUNCH(k_msm_accum0<F COMMA M>, ceil_div(max_s0, 128), 128, 0, st, table, so.sorted.as<uint32_t>(), count, \
             start, sstart0, nb1, S, order, order_b, ws.part0.as<Xyzz<F>>())
@@ -593,6 +603,7 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
       default: CS_ACC0(4); break;
     }
 #undef CS_ACC0
+    }
   }
   CS_TRY(ws.mark(3, st));
   CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,

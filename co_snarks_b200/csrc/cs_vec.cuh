@@ -95,6 +95,65 @@ CS_GLOBAL void k_rep3_to_shamir(const uint32_t* __restrict__ x, const uint32_t* 
   }
 }
 
+// Batched witness-extension VM operations on Rep3 share vectors (circom-mpc-vm/src/mpc/batched_rep3.rs:124-188,
+// 322-337 -> rep3::arithmetic::{add, sub, add_public, sub_shared_by_public, sub_public_by_shared, mul_public,
+// promote_to_trivial_share}, arithmetic.rs:36-100,321-327).  x: n shares {a, b}; y: n shares or n public values.
+// The public operand enters party 0's `a` and party 1's `b` only (arithmetic.rs:41-48).
+enum Rep3BatchOp {
+  R3B_ADD = 0,            // shared + shared
+  R3B_SUB = 1,            // shared - shared
+  R3B_ADD_PUBLIC = 2,     // shared + public
+  R3B_SUB_PUBLIC = 3,     // shared - public            (sub_shared_by_public)
+  R3B_PUBLIC_SUB = 4,     // public - shared            (sub_public_by_shared)
+  R3B_MUL_PUBLIC = 5,     // shared * public
+  R3B_NEG = 6,            // -shared                     (y unused)
+  R3B_PROMOTE = 7,        // public -> trivial share     (x unused)
+  R3B_OPEN_FINISH = 8     // a + b + c, c = previous party's b (open_vec, arithmetic.rs:261-271): out = n public values
+};
+template <class FrP>
+CS_GLOBAL void k_rep3_batch(int op, int party, const uint32_t* __restrict__ x, const uint32_t* __restrict__ y,
+                            uint32_t* __restrict__ out, size_t n) {
+  constexpr int NW = FrP::N;
+  typedef Fp<FrP> F;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) {
+    F xa = F::zero(), xb = F::zero();
+    if (op != R3B_PROMOTE) { xa = ld_fr<FrP>(x + (2 * i) * NW); xb = ld_fr<FrP>(x + (2 * i + 1) * NW); }
+    F ra, rb;
+    if (op == R3B_ADD || op == R3B_SUB) {
+      F ya = ld_fr<FrP>(y + (2 * i) * NW), yb = ld_fr<FrP>(y + (2 * i + 1) * NW);
+      ra = op == R3B_ADD ? xa + ya : xa - ya;
+      rb = op == R3B_ADD ? xb + yb : xb - yb;
+    } else if (op == R3B_NEG) {
+      ra = xa.neg(); rb = xb.neg();
+    } else if (op == R3B_OPEN_FINISH) {
+      st_fr<FrP>(out + i * NW, xa + xb + ld_fr<FrP>(y + i * NW));
+      continue;
+    } else {
+      F p = ld_fr<FrP>(y + i * NW);
+      if (op == R3B_MUL_PUBLIC) {
+        ra = xa * p; rb = xb * p;
+      } else {
+        if (op == R3B_SUB_PUBLIC) p = p.neg();
+        if (op == R3B_PUBLIC_SUB) { xa = xa.neg(); xb = xb.neg(); }
+        ra = party == 0 ? xa + p : xa;
+        rb = party == 1 ? xb + p : xb;
+      }
+    }
+    st_fr<FrP>(out + (2 * i) * NW, ra);
+    st_fr<FrP>(out + (2 * i + 1) * NW, rb);
+  }
+}
+// open_vec, first half: b-components as a contiguous vector, optionally written straight into the NEXT party's
+// receive buffer (peer memory) -- reshare_many(&b) (arithmetic.rs:269)
+template <class FrP>
+CS_GLOBAL void k_rep3_take_b(const uint32_t* __restrict__ x, uint32_t* __restrict__ out, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t step = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += step) st_fr<FrP>(out + i * FrP::N, ld_fr<FrP>(x + (2 * i + 1) * FrP::N));
+}
+
 // out_i = sum_j w_j * in_j[i], j < k <= LINCOMB_MAX.  Shamir's king-based degree reduction
 // (mpc-core/src/protocols/shamir/network.rs:150-243): the "pair consumption" `inp += r_2t` / `share -= r_t`
 // are k = 2 calls with weights (1, +-1); the king's Lagrange-weighted accumulation over the 2t+1 received

@@ -290,6 +290,45 @@ int cs_ipc_export(cs_ctx* ctx, const void* d_ptr, uint8_t* out_handle64);
 int cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** out_peer_ptr);
 int cs_ipc_close(cs_ctx* ctx, void* peer_ptr);
 
+/* ---- batched witness-extension VM operations (circom-mpc-vm/src/mpc/batched_rep3.rs:124-188, 322-337) ----------
+ * BatchedCircomRep3VmWitnessExtension runs one circuit on a batch of inputs, so every VM opcode acts on a vector of
+ * `batch_size` values.  These are its arithmetic opcodes on device-resident vectors: shares = n x {a, b}, publics =
+ * n x Fr (Montgomery).  `op` selects the reference function:
+ *   CS_R3B_ADD / CS_R3B_SUB            arithmetic::add / sub                         (shared, shared)
+ *   CS_R3B_ADD_PUBLIC                  arithmetic::add_public                        (shared, public)
+ *   CS_R3B_SUB_PUBLIC                  arithmetic::sub_shared_by_public              (shared - public)
+ *   CS_R3B_PUBLIC_SUB                  arithmetic::sub_public_by_shared              (public - shared)
+ *   CS_R3B_MUL_PUBLIC                  arithmetic::mul_public
+ *   CS_R3B_NEG                         -shared                                        (d_y = NULL)
+ *   CS_R3B_PROMOTE                     arithmetic::promote_to_trivial_share          (d_x = NULL, d_y = publics)
+ * The secret x secret `mul` (batched_rep3.rs:185 -> arithmetic::mul_vec) is cs_rep3_mul_vec_reshare above: product,
+ * masks and the store into the next party's vector in one kernel.
+ * `open` (batched_rep3.rs:322-327 -> open_vec): cs_rep3_batch_open_send copies the b-components into d_next_recv
+ * (the NEXT party's receive buffer mapped with cs_ipc_open, or a local staging buffer for other transports);
+ * after the parties have met, cs_rep3_batch_open_finish adds a + b + received. */
+typedef enum {
+  CS_R3B_ADD = 0, CS_R3B_SUB = 1, CS_R3B_ADD_PUBLIC = 2, CS_R3B_SUB_PUBLIC = 3, CS_R3B_PUBLIC_SUB = 4,
+  CS_R3B_MUL_PUBLIC = 5, CS_R3B_NEG = 6, CS_R3B_PROMOTE = 7
+} cs_rep3_batch_op;
+int cs_rep3_batch(cs_ctx* ctx, cs_curve curve, cs_rep3_batch_op op, int party, const uint64_t* d_x,
+                  const uint64_t* d_y, uint64_t* d_out, size_t n);
+int cs_rep3_batch_open_send(cs_ctx* ctx, cs_curve curve, const uint64_t* d_shares, size_t n, uint64_t* d_next_recv);
+int cs_rep3_batch_open_finish(cs_ctx* ctx, cs_curve curve, const uint64_t* d_shares, const uint64_t* d_recv,
+                              uint64_t* d_out_public, size_t n);
+
+/* ---- UltraHonk commitments: CoUtils::commit / commit_and_send (co-noir/co-noir-common/src/lib.rs:57-101) ->
+ * T::msm_public_points(&crs.monomials[..poly.len()], poly) -> HonkCurve::fast_msm = msm_unchecked
+ * (honk_curve.rs:81-83; the reference chops to the shorter slice, :33-34).  The Oink prover commits the wire,
+ * lookup and permutation polynomials one after the other (co_oink_prover.rs:547-700: w_l, w_r, w_o,
+ * lookup_read_counts, lookup_read_tags, w_4, lookup_inverses, z_perm); here a round's polynomials are committed
+ * concurrently (one stream and MSM workspace each) against the resident CRS table (cs_bases_from_crs_file).
+ *   share_kind CS_PLAIN: polys[k] = lens[k] x Fr                -> out_points[k]            (plain / Shamir shares)
+ *              CS_REP3 : polys[k] = lens[k] x {a, b}            -> out_points[2k], [2k+1]   (Rep3PointShare a, b:
+ *                                                                   co-noir-common/src/mpc/rep3.rs:259-266)
+ * polys are device pointers; k <= 4 per call. */
+int cs_honk_commit_batch(cs_ctx* ctx, const cs_bases* crs, cs_share_kind kind, const uint64_t* const* d_polys,
+                         const size_t* lens, unsigned k, uint64_t* h_out_points);
+
 /* ---- party-to-party transport: mpc_net::Network (mpc-net/src/lib.rs:34-63: id / send / recv) -------------
  * A cs_net is one n-party mesh.  Two implementations:
  *  (1) callbacks -- the host language hands over its own transport (the Rust shim wraps `&N: Network`,

@@ -159,3 +159,20 @@ def test_groth16_bls12_381(gpu_ctx):
     the reference's bls12_381/multiplier2 fixture; proof bytes == oracle, accepted by the BLS12-381 pairing check
     under the snarkjs verification key (the acceptance criterion of co-groth16/src/lib.rs:93-119)."""
     K.check_groth16_fixture(gpu_ctx, "multiplier2", rep3=False, curve="bls12_381")
+
+
+def test_msm_fp64_pipe_accumulation_subprocess():
+    """The opt-in FP64-pipe bucket accumulation (cs_msm52.cuh, CS_MSM_F52=1: 5 x 52-bit limbs, DFMA split products,
+    lazy ranges, exact-slice fallback for P + P / P + (-P)) gives the same bits as the oracle on the MSM edge-case
+    suite.  Separate process: the switch is read once per process at the first base upload."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from co_snarks_b200 import binding as B; import kernel_checks as K;"
+            "ctx = B.Context(0); K.check_msm(ctx, 0, 700, window_bits=(0, 9)); K.check_msm(ctx, 0, 5000); print('ok')"
+            % (root, os.path.join(root, "tests")))
+    env = dict(os.environ, CS_MSM_F52="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
