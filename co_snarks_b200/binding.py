@@ -16,6 +16,7 @@ DEFAULT_LIB = os.path.join(_HERE, "libcosnarks_gpu.so")
 CS_BN254, CS_BLS12_381 = 0, 1
 CS_G1, CS_G2 = 0, 1
 CS_PLAIN, CS_REP3 = 0, 1
+R3B_ADD, R3B_SUB, R3B_ADD_PUBLIC, R3B_SUB_PUBLIC, R3B_PUBLIC_SUB, R3B_MUL_PUBLIC, R3B_NEG, R3B_PROMOTE = range(8)
 CS_PART_A, CS_PART_B1, CS_PART_B2, CS_PART_L, CS_PART_H, CS_PART_ALL = 1, 2, 4, 8, 16, 31
 
 u64p = C.POINTER(C.c_uint64)
@@ -71,6 +72,10 @@ class NetCallbacks(C.Structure):
 
 # name -> (restype, argtypes); every symbol include/cosnarks_gpu.h declares
 SIGNATURES = {
+    "cs_rep3_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_rep3_batch_open_send": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cs_rep3_batch_open_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cs_honk_commit_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint, C.c_void_p]),
     "cs_net_from_callbacks": (C.c_int, [C.c_int, C.c_int, C.POINTER(NetCallbacks), C.POINTER(C.c_void_p)]),
     "cs_net_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cs_net_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -385,6 +390,21 @@ class Context:
 
     def rep3_set_b(self, curve, d_recv, n, d_out):
         self._check(self.lib.cs_rep3_set_b(self.h, curve, C.c_void_p(d_recv), n, C.c_void_p(d_out)))
+
+    def rep3_batch(self, curve, op, party, d_x, d_y, d_out, n):
+        """Batched VM opcode on device share vectors (cs_rep3_batch; op = R3B_*)."""
+        self._check(self.lib.cs_rep3_batch(self.h, curve, op, party, _ptr(d_x), _ptr(d_y), _ptr(d_out), n))
+
+    def honk_commit_batch(self, crs, kind, d_polys, lens):
+        """CoUtils::commit for up to 4 polynomials at once -> [k (x2 for Rep3), point limbs] affine Montgomery."""
+        k = len(d_polys)
+        per = 2 if kind == CS_REP3 else 1
+        pl = limbs_of(crs.curve, "fq") * (2 if crs.group == CS_G1 else 4)
+        out = np.zeros((k * per, pl), dtype=np.uint64)
+        ptrs = (C.c_void_p * k)(*[C.c_void_p(p) for p in d_polys])
+        ln = (C.c_size_t * k)(*lens)
+        self._check(self.lib.cs_honk_commit_batch(self.h, crs.h, kind, ptrs, ln, k, _ptr(out)))
+        return out
 
     def ipc_export(self, d_ptr):
         h = np.zeros(64, dtype=np.uint8)

@@ -684,6 +684,88 @@ int cs_rep3_set_b(cs_ctx* ctx, cs_curve curve, const uint64_t* d_recv, size_t n,
   return 0;
 }
 
+int cs_rep3_batch(cs_ctx* ctx, cs_curve curve, cs_rep3_batch_op op, int party, const uint64_t* d_x, const uint64_t* d_y,
+                  uint64_t* d_out, size_t n) {
+  if (!ctx || (n && !d_out)) return fail(CS_ERR_ARG, "cs_rep3_batch: NULL argument");
+  if ((int)op < 0 || (int)op > CS_R3B_PROMOTE) return fail(CS_ERR_ARG, "cs_rep3_batch: unknown op %d", (int)op);
+  if (party < 0 || party > 2) return fail(CS_ERR_ARG, "cs_rep3_batch: party must be 0..2");
+  if (n && op != CS_R3B_PROMOTE && !d_x) return fail(CS_ERR_ARG, "cs_rep3_batch: d_x is NULL");
+  if (n && op != CS_R3B_NEG && !d_y) return fail(CS_ERR_ARG, "cs_rep3_batch: d_y is NULL");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_batch<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, (int)op, party, reinterpret_cast<const uint32_t*>(d_x),
+              reinterpret_cast<const uint32_t*>(d_y), reinterpret_cast<uint32_t*>(d_out), n);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_rep3_batch_open_send(cs_ctx* ctx, cs_curve curve, const uint64_t* d_shares, size_t n, uint64_t* d_next_recv) {
+  if (!ctx || (n && (!d_shares || !d_next_recv))) return fail(CS_ERR_ARG, "cs_rep3_batch_open_send: NULL argument");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_take_b<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, reinterpret_cast<const uint32_t*>(d_shares),
+              reinterpret_cast<uint32_t*>(d_next_recv), n);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_rep3_batch_open_finish(cs_ctx* ctx, cs_curve curve, const uint64_t* d_shares, const uint64_t* d_recv,
+                              uint64_t* d_out_public, size_t n) {
+  if (!ctx || (n && (!d_shares || !d_recv || !d_out_public))) return fail(CS_ERR_ARG, "cs_rep3_batch_open_finish: NULL argument");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  unsigned blocks = ceil_div(n, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_rep3_batch<typename Cfg::FrP>, blocks, 256, 0, ctx->stream, (int)R3B_OPEN_FINISH, 0,
+              reinterpret_cast<const uint32_t*>(d_shares), reinterpret_cast<const uint32_t*>(d_recv),
+              reinterpret_cast<uint32_t*>(d_out_public), n);
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// CoUtils::commit for a round of polynomials (co-noir-common/src/lib.rs:88-101 -> msm_public_points -> fast_msm)
+int cs_honk_commit_batch(cs_ctx* ctx, const cs_bases* crs, cs_share_kind kind, const uint64_t* const* d_polys,
+                         const size_t* lens, unsigned k, uint64_t* h_out) {
+  if (!ctx || !crs || !d_polys || !lens || !h_out) return fail(CS_ERR_ARG, "cs_honk_commit_batch: NULL argument");
+  if (kind != CS_PLAIN && kind != CS_REP3) return fail(CS_ERR_ARG, "cs_honk_commit_batch: bad share kind");
+  const unsigned per = kind == CS_REP3 ? 2 : 1;
+  if (k == 0 || k * per > (unsigned)CS_NSIDE) return fail(CS_ERR_ARG, "cs_honk_commit_batch: %u polynomials do not fit %d streams", k, CS_NSIDE);
+  const size_t plimbs = point_limbs64(crs->curve, crs->group);
+  for (unsigned j = 0; j < k; j++) {
+    if (lens[j] > crs->n) return fail(CS_ERR_ARG, "cs_honk_commit_batch: polynomial %u has %zu coefficients, the CRS holds %zu points", j, lens[j], crs->n);
+    if (lens[j] && !d_polys[j]) return fail(CS_ERR_ARG, "cs_honk_commit_batch: polynomial %u is NULL", j);
+  }
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_TRY(ctx_fork(ctx, (int)(k * per)));
+  for (unsigned j = 0; j < k; j++)
+    for (unsigned c = 0; c < per; c++) {
+      const unsigned slot = j * per + c;
+      if (lens[j] == 0) continue;
+      const uint32_t* sc = reinterpret_cast<const uint32_t*>(d_polys[j]) + c * 8;
+      CS_TRY(msm_enqueue_dyn(ctx, (int)slot, ctx->side[slot], crs, 0, sc, per, lens[j], 1));
+    }
+  CS_TRY(ctx_join(ctx, (int)(k * per)));
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (unsigned j = 0; j < k; j++)
+    for (unsigned c = 0; c < per; c++) {
+      const unsigned slot = j * per + c;
+      uint64_t* dst = h_out + (size_t)slot * plimbs;
+      if (lens[j] == 0) { memset(dst, 0, plimbs * 8); continue; }
+      CS_TRY(msm_finish_dyn(ctx, (int)slot, crs, dst, nullptr));
+    }
+  return 0;
+}
+
 // peer mapping of another process's device buffer (one process per GPU): cudaIpc handles are 64 opaque bytes
 int cs_ipc_export(cs_ctx* ctx, const void* d_ptr, uint8_t* out_handle64) {
   if (!ctx || !d_ptr || !out_handle64) return fail(CS_ERR_ARG, "cs_ipc_export: NULL argument");

@@ -935,3 +935,97 @@ def check_libsnark_reduction(ctx, m_vars=50, seed=14):
         tot = [(p + q) % r for p, q in zip(tot, got)]
     assert tot == h
     pk.free()
+
+
+def check_rep3_batch_ops(ctx, n=257, seed=31):
+    """The batched VM opcodes (circom-mpc-vm/src/mpc/batched_rep3.rs:124-188, 322-337) on all three parties'
+    share vectors: every op's result, opened, equals the plain operation on the secrets; the per-party placement of
+    public operands follows arithmetic.rs:41-48 and promote_to_trivial_share (arithmetic.rs:321-327) exactly."""
+    from oracle import groth16 as OG
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(seed)
+    xs = [rng.randrange(r) for _ in range(n)]
+    ys = [rng.randrange(r) for _ in range(n)]
+    pub = [rng.randrange(r) for _ in range(n)]
+    xsh, ysh = OG.share_rep3(xs, r, rng), OG.share_rep3(ys, r, rng)
+    flat = lambda sh: cv.fr([v for ab in sh for v in ab])
+    dx = [ctx.to_device(flat(xsh[i])) for i in range(3)]
+    dy = [ctx.to_device(flat(ysh[i])) for i in range(3)]
+    dp = ctx.to_device(cv.fr(pub))
+    do = [ctx.alloc(n * 64) for _ in range(3)]
+    cases = [(B.R3B_ADD, True, lambda x, y, p: (x + y) % r), (B.R3B_SUB, True, lambda x, y, p: (x - y) % r),
+             (B.R3B_ADD_PUBLIC, False, lambda x, y, p: (x + p) % r), (B.R3B_SUB_PUBLIC, False, lambda x, y, p: (x - p) % r),
+             (B.R3B_PUBLIC_SUB, False, lambda x, y, p: (p - x) % r), (B.R3B_MUL_PUBLIC, False, lambda x, y, p: x * p % r),
+             (B.R3B_NEG, None, lambda x, y, p: (-x) % r), (B.R3B_PROMOTE, "promote", lambda x, y, p: p)]
+    for op, second, expect in cases:
+        outs = []
+        for i in range(3):
+            d_y = dy[i] if second is True else (None if second is None else dp)
+            d_x = None if second == "promote" else dx[i]
+            ctx.rep3_batch(cv.id, op, i, d_x, d_y, do[i], n)
+            outs.append(cv.fr_back(ctx.d2h(do[i], (2 * n, 4))))
+        for k in range(n):
+            # replicated: party i's b is party i-1's a; the three a's open to the expected value
+            assert all(outs[i][2 * k + 1] == outs[(i + 2) % 3][2 * k] for i in range(3)), (op, k)
+            assert sum(outs[i][2 * k] for i in range(3)) % r == expect(xs[k], ys[k], pub[k]), (op, k)
+        if op == B.R3B_ADD_PUBLIC:  # the public value sits in party 0's a (= party 1's b) and nowhere else
+            assert outs[2][0] == xsh[2][0][0] and outs[2][1] == xsh[2][0][1]
+            assert outs[0][0] == (xsh[0][0][0] + pub[0]) % r and outs[0][1] == xsh[0][0][1]
+        if op == B.R3B_PROMOTE:
+            assert (outs[0][0], outs[0][1]) == (pub[0], 0) and (outs[1][0], outs[1][1]) == (0, pub[0]) and outs[2][:2] == [0, 0]
+    # open (open_vec): b-components travel to the next party, a + b + c
+    recv = [ctx.alloc(n * 32) for _ in range(3)]
+    lib = ctx.lib
+    for i in range(3):
+        ctx._check(lib.cs_rep3_batch_open_send(ctx.h, cv.id, dx[i], n, recv[(i + 1) % 3]))
+    ctx.synchronize()
+    for i in range(3):
+        ctx._check(lib.cs_rep3_batch_open_finish(ctx.h, cv.id, dx[i], recv[i], do[i], n))
+        assert cv.fr_back(ctx.d2h(do[i], (n, 4))) == xs
+    for d in dx + dy + do + recv + [dp]:
+        ctx.free(d)
+
+
+def check_honk_commit_batch(ctx, n=200, seed=41):
+    """CoUtils::commit over the Ignition CRS (co-noir-common/src/lib.rs:88-101 -> fast_msm, honk_curve.rs:81-83) for a
+    round of polynomials at once: plain commitments == oracle MSM; Rep3 commitments are the point share {a, b} of
+    co-noir-common/src/mpc/rep3.rs:259-266 and the three parties' a-points open to the plain commitment; shorter
+    polynomials use the leading CRS points only."""
+    from oracle import groth16 as OG
+    cv = Conv("bn254")
+    r = cv.r
+    g = load_golden("crs_bn254_g1_first1024")
+    pts = [gp1(P) for P in g["points"]][:n]
+    crs = ctx.bases_upload(cv.id, 0, cv.g1(pts))
+    rng = random.Random(seed)
+    G = og1(BN254)
+    lens = [n, n - 17, 5, 0]
+    polys = [[rng.randrange(r) for _ in range(l)] for l in lens]
+    d = [ctx.to_device(cv.fr(p)) if p else 0 for p in polys]
+    out = ctx.honk_commit_batch(crs, B.CS_PLAIN, d, lens)
+    exp = [G.msm(pts[:l], p) if l else None for p, l in zip(polys, lens)]
+    assert [cv.pt1(o) for o in out] == exp
+    # Rep3: two polynomials, every party commits to both components
+    sh = [OG.share_rep3(p, r, rng) for p in polys[:2]]
+    a_pts = [[None] * 2 for _ in range(3)]
+    for i in range(3):
+        ds = [ctx.to_device(cv.fr([v for ab in sh[k][i] for v in ab])) for k in range(2)]
+        o = ctx.honk_commit_batch(crs, B.CS_REP3, ds, lens[:2])
+        for k in range(2):
+            a_pts[i][k], b_pt = cv.pt1(o[2 * k]), cv.pt1(o[2 * k + 1])
+            assert a_pts[i][k] == G.msm(pts[:lens[k]], [ab[0] for ab in sh[k][i]])
+            assert b_pt == G.msm(pts[:lens[k]], [ab[1] for ab in sh[k][i]])
+        for x in ds:
+            ctx.free(x)
+    for k in range(2):
+        acc = None
+        for i in range(3):
+            acc = G.add(acc, a_pts[i][k])
+        assert acc == exp[k]
+    with pytest.raises(RuntimeError):
+        ctx.honk_commit_batch(crs, B.CS_PLAIN, [d[0]], [n + 1])  # longer than the CRS
+    for x in d:
+        if x:
+            ctx.free(x)
+    crs.free()

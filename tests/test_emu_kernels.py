@@ -152,3 +152,11 @@ def test_emu_groth16_bls12_381(emu_ctx):
     """Groth16 on BLS12-381 (6-limb Fq, 255-bit Fr): witness map and proof bytes == oracle on the reference's
     bls12_381/multiplier2 fixture, proof accepted by the BLS12-381 pairing check under the snarkjs key."""
     K.check_groth16_fixture(emu_ctx, "multiplier2", rep3=False, curve="bls12_381")
+
+
+def test_emu_rep3_batch_vm_ops(emu_ctx):
+    K.check_rep3_batch_ops(emu_ctx, n=33)
+
+
+def test_emu_honk_commit_batch(emu_ctx):
+    K.check_honk_commit_batch(emu_ctx, n=40)

@@ -176,3 +176,11 @@ def test_msm_fp64_pipe_accumulation_subprocess():
     env = dict(os.environ, CS_MSM_F52="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
+def test_rep3_batch_vm_ops(gpu_ctx):
+    K.check_rep3_batch_ops(gpu_ctx, n=3001)
+
+
+def test_honk_commit_batch(gpu_ctx):
+    K.check_honk_commit_batch(gpu_ctx, n=1000)
