@@ -76,6 +76,18 @@ SIGNATURES = {
     "cs_rep3_batch_open_send": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cs_rep3_batch_open_finish": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_honk_commit_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_uint, C.c_void_p]),
+    "cs_fr_inv": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p]),
+    "cs_shamir_state_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cs_shamir_state_fork": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "cs_shamir_state_pairs": (C.c_size_t, [C.c_void_p]),
+    "cs_shamir_state_rand": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_shamir_state_free": (None, [C.c_void_p]),
+    "cs_shamir_open_lagrange": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "cs_shamir_degree_reduce_many": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "cs_shamir_degree_reduce_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_shamir_open_half_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "cs_groth16_shamir_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6),
+    "cs_groth16_prove_with_shamir_bridge": (C.c_int, [C.c_void_p] * 10),
     "cs_net_from_callbacks": (C.c_int, [C.c_int, C.c_int, C.POINTER(NetCallbacks), C.POINTER(C.c_void_p)]),
     "cs_net_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cs_net_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -773,6 +785,28 @@ class Groth16Key:
         dw = C.c_void_p(d_witness_shares) if d_witness_shares else None
         self.ctx._check(self.ctx.lib.cs_groth16_rep3_prove_helper(self.ctx.h, self.h, party, pair.h, state.h,
                                                                   _ptr(public_inputs), _ptr(witness_shares), dw))
+
+    def shamir_prove(self, net0, net1, num_parties, threshold, public_inputs, witness_shares):
+        """ShamirCoGroth16::prove inside the library -> (A, B, C, [r_share, s_share])."""
+        a = np.zeros(2 * self.fq, dtype=np.uint64)
+        b = np.zeros(4 * self.fq, dtype=np.uint64)
+        c = np.zeros(2 * self.fq, dtype=np.uint64)
+        rs = np.zeros((2, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_groth16_shamir_prove(self.ctx.h, self.h, net0.h, net1.h, num_parties, threshold,
+                                                             _ptr(public_inputs), _ptr(witness_shares), _ptr(a), _ptr(b),
+                                                             _ptr(c), _ptr(rs)))
+        return a, b, c, rs
+
+    def prove_with_shamir_bridge(self, net0, net1, public_inputs, witness_rep3_shares):
+        """CoGroth16::prove_with_shamir_bridge: Rep3 witness shares in, Shamir(t = 1) prover."""
+        a = np.zeros(2 * self.fq, dtype=np.uint64)
+        b = np.zeros(4 * self.fq, dtype=np.uint64)
+        c = np.zeros(2 * self.fq, dtype=np.uint64)
+        rs = np.zeros((2, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_groth16_prove_with_shamir_bridge(self.ctx.h, self.h, net0.h, net1.h, _ptr(public_inputs),
+                                                                         _ptr(witness_rep3_shares), _ptr(a), _ptr(b), _ptr(c),
+                                                                         _ptr(rs)))
+        return a, b, c, rs
 
     def shamir_local(self, public_inputs, witness_shares, r_share, s_share):
         g1 = lambda: np.zeros(2 * self.fq, dtype=np.uint64)

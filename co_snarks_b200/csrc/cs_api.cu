@@ -51,27 +51,6 @@ static int ntt_smem_optin() {
 
 using namespace cs;
 
-#if defined(CS_ENABLE_BLS12_381)
-#define CS_CASE_BLS(...)   \
-  case CS_BLS12_381: {     \
-    typedef Bls381Cfg Cfg; \
-    __VA_ARGS__;           \
-  } break;
-#else
-#define CS_CASE_BLS(...)
-#endif
-
-#define CS_DISPATCH_CURVE(curve, ...)                                        \
-  switch ((int)(curve)) {                                                    \
-    case CS_BN254: {                                                         \
-      typedef Bn254Cfg Cfg;                                                  \
-      __VA_ARGS__;                                                           \
-    } break;                                                                 \
-      CS_CASE_BLS(__VA_ARGS__)                                               \
-    default:                                                                 \
-      return fail(CS_ERR_ARG, "unsupported curve id %d", (int)(curve));      \
-  }
-
 extern "C" {
 
 const char* cs_last_error(void) { return last_error().c_str(); }
@@ -1005,6 +984,18 @@ int cs_fr_mul(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, ui
     memcpy(a.l, a_mont, sizeof(a.l));
     memcpy(b.l, b_mont, sizeof(b.l));
     HF r = a * b;
+    memcpy(out_mont, r.l, sizeof(r.l));
+  });
+  return 0;
+}
+int cs_fr_inv(cs_curve curve, const uint64_t* a_mont, uint64_t* out_mont) {
+  if (!a_mont || !out_mont) return fail(CS_ERR_ARG, "cs_fr_inv: NULL argument");
+  CS_DISPATCH_CURVE(curve, {
+    typedef host::HFp<typename Cfg::FrP> HF;
+    HF a;
+    memcpy(a.l, a_mont, sizeof(a.l));
+    if (a.is_zero()) return fail(CS_ERR_ARG, "Cannot invert zero");
+    HF r = a.inverse();
     memcpy(out_mont, r.l, sizeof(r.l));
   });
   return 0;

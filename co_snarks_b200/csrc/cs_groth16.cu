@@ -488,6 +488,54 @@ int rep3_prove_t(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_
   return 0;
 }
 
+// ShamirCoGroth16::prove (groth16.rs:439-463): preprocessing of three pairs over net0, state1 = state0.fork(1),
+// then prove_inner / create_proof_with_assignment with ShamirGroth16Driver (mpc/shamir.rs).
+template <class Cfg>
+int shamir_prove_t(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, int n_parties, int threshold,
+                   const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit, uint64_t* out_a, uint64_t* out_b,
+                   uint64_t* out_c, uint64_t* out_rs) {
+  typedef HostGroup<Cfg, 0> H1;
+  typedef host::HFp<typename Cfg::FrP> HR;
+  constexpr size_t G1L = 2 * H1::HF::N, G2L = 4 * H1::HF::N;
+  // we need 3 corr rand pairs: 2 for the two rand calls, 1 for scalar_mul (groth16.rs:448-452)
+  cs_shamir_state* s0 = nullptr;
+  CS_TRY(cs_shamir_state_create(net0, (cs_curve)pk->curve, n_parties, threshold, 3, &s0));
+  struct Guard { cs_shamir_state* a = nullptr; cs_shamir_state* b = nullptr; ~Guard() { cs_shamir_state_free(a); cs_shamir_state_free(b); } } guard;
+  guard.a = s0;
+  cs_shamir_state* s1 = nullptr;
+  CS_TRY(cs_shamir_state_fork(s0, 1, &s1));
+  guard.b = s1;
+  uint64_t r[HR::N], sv[HR::N];
+  CS_TRY(cs_shamir_state_rand(s0, net0, r));   // groth16.rs:157
+  CS_TRY(cs_shamir_state_rand(s0, net0, sv));
+  if (out_rs) { memcpy(out_rs, r, sizeof(r)); memcpy(out_rs + HR::N, sv, sizeof(sv)); }
+  HR rr, ss;
+  memcpy(rr.l, r, sizeof(r));
+  memcpy(ss.l, sv, sizeof(sv));
+  HR rs = rr * ss;  // local_mul_vec([r], [s]): a degree-2t share (shamir/arithmetic.rs:73-80)
+  uint64_t g_a[G1L], g1_b[G1L], g2_b[G2L], l_acc[G1L], h_acc[G1L], rsd[G1L];
+  // the Shamir driver's local computation is the plain driver's on degree-t shares: every party adds the public terms
+  CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, d_wit, nullptr, nullptr, r, sv, g_a, g1_b, g2_b, l_acc, h_acc,
+                           CS_PART_ALL, nullptr, rs.l, rsd)));
+  // round 1 (groth16.rs:305-308): open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1 with state1
+  uint64_t a_open[G1L], g1_b_red[G1L];
+  CS_TRY(cs_shamir_open_half_point(s0, net0, CS_G1, g_a, a_open));
+  CS_TRY(cs_shamir_degree_reduce_point(s1, net1, CS_G1, pk->alpha_g1.data(), g1_b, g1_b_red));  // mpc/shamir.rs:146-148
+  typename H1::X r_g1_b = H1::mul(H1::load(g1_b_red), r);                                      // scalar_mul_local
+  typename H1::X g_c = H1::mul(H1::load(a_open), sv);
+  g_c = host::hadd(g_c, r_g1_b);
+  g_c = host::hadd(g_c, host::hneg(H1::load(rsd)));
+  g_c = host::hadd(g_c, H1::load(l_acc));
+  g_c = host::hadd(g_c, H1::load(h_acc));
+  uint64_t gc[G1L];
+  H1::store(gc, g_c);
+  // round 2 (groth16.rs:325-328)
+  CS_TRY(cs_shamir_open_half_point(s0, net0, CS_G1, gc, out_c));
+  CS_TRY(cs_shamir_open_half_point(s1, net1, CS_G2, g2_b, out_b));
+  memcpy(out_a, a_open, sizeof(a_open));
+  return 0;
+}
+
 int rep3_prove_dispatch(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_net* pair, int role, int party,
                         cs_rep3_state* state, const uint64_t* h_pub, const uint64_t* h_wit, const uint64_t* d_wit,
                         uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs) {
@@ -762,6 +810,67 @@ int cs_groth16_rep3_local_prf(cs_ctx* ctx, cs_groth16_pk* pk, int party, unsigne
 #endif
     default: return fail(CS_ERR_ARG, "unsupported curve");
   }
+}
+
+int cs_groth16_shamir_prove(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, int num_parties, int threshold,
+                            const uint64_t* h_pub, const uint64_t* h_wit, uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                            uint64_t* out_rs) {
+  if (!ctx || !pk || !net0 || !net1 || !h_pub || (pk->nw && !h_wit) || !out_a || !out_b || !out_c)
+    return fail(CS_ERR_ARG, "cs_groth16_shamir_prove: NULL argument");
+  if (net0->n != num_parties || net1->n != num_parties || net0->id != net1->id)
+    return fail(CS_ERR_ARG, "cs_groth16_shamir_prove: net0/net1 must be %d-party meshes of the same party", num_parties);
+  switch (pk->curve) {
+    case CS_BN254: return shamir_prove_t<Bn254Cfg>(ctx, pk, net0, net1, num_parties, threshold, h_pub, h_wit, nullptr, out_a, out_b, out_c, out_rs);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: return shamir_prove_t<Bls381Cfg>(ctx, pk, net0, net1, num_parties, threshold, h_pub, h_wit, nullptr, out_a, out_b, out_c, out_rs);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
+int cs_groth16_prove_with_shamir_bridge(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, const uint64_t* h_pub,
+                                        const uint64_t* h_wit_rep3, uint64_t* out_a, uint64_t* out_b, uint64_t* out_c,
+                                        uint64_t* out_rs) {
+  if (!ctx || !pk || !net0 || !net1 || !h_pub || (pk->nw && !h_wit_rep3) || !out_a || !out_b || !out_c)
+    return fail(CS_ERR_ARG, "cs_groth16_prove_with_shamir_bridge: NULL argument");
+  if (net0->n != 3 || net0->id < 0 || net0->id > 2) return fail(CS_ERR_ARG, "not a valid party id");  // groth16.rs:403-404
+  CS_CUDA(cudaSetDevice(ctx->device));
+  // get_translation_points (bridges/rep3_to_shamir.rs:14-29): f(X) = 1 - X / z evaluated at id + 1
+  const uint64_t id = (uint64_t)net0->id;
+  const uint64_t z1 = id == 0 ? 3 : id, z2 = id == 2 ? 1 : id + 2, e = id + 1;
+  uint64_t ca[4], cb[4];
+  auto coeff = [&](uint64_t z, uint64_t* out) -> int {
+    uint64_t zc[4] = {z, 0, 0, 0}, ec[4] = {e, 0, 0, 0}, onec[4] = {1, 0, 0, 0}, zm[4], em[4], onem[4], q[4];
+    CS_TRY(cs_fr_to_mont((cs_curve)pk->curve, zc, zm, 1));
+    CS_TRY(cs_fr_to_mont((cs_curve)pk->curve, ec, em, 1));
+    CS_TRY(cs_fr_to_mont((cs_curve)pk->curve, onec, onem, 1));
+    CS_TRY(cs_fr_inv((cs_curve)pk->curve, zm, q));
+    CS_TRY(cs_fr_mul((cs_curve)pk->curve, q, em, q));
+    return cs_fr_sub((cs_curve)pk->curve, onem, q, out);
+  };
+  CS_TRY(coeff(z1, ca));
+  CS_TRY(coeff(z2, cb));
+  // translate_primefield_repshare_vec on the device: share_i = a_i x + b_i y (k_rep3_to_shamir)
+  DevBuf d_in, d_out;
+  CS_TRY(d_in.reserve(pk->nw * 64 + 64));
+  CS_TRY(d_out.reserve(pk->nw * 32 + 32));
+  int rc = 0;
+  if (pk->nw) {
+    CS_CUDA(cudaMemcpyAsync(d_in.p, h_wit_rep3, pk->nw * 64, cudaMemcpyHostToDevice, ctx->stream));
+    rc = cs_rep3_to_shamir(ctx, (cs_curve)pk->curve, d_in.as<uint64_t>(), ca, cb, d_out.as<uint64_t>(), pk->nw);
+  }
+  if (!rc) {
+    switch (pk->curve) {
+      case CS_BN254: rc = shamir_prove_t<Bn254Cfg>(ctx, pk, net0, net1, 3, 1, h_pub, nullptr, d_out.as<uint64_t>(), out_a, out_b, out_c, out_rs); break;
+#if defined(CS_ENABLE_BLS12_381)
+      case CS_BLS12_381: rc = shamir_prove_t<Bls381Cfg>(ctx, pk, net0, net1, 3, 1, h_pub, nullptr, d_out.as<uint64_t>(), out_a, out_b, out_c, out_rs); break;
+#endif
+      default: rc = fail(CS_ERR_ARG, "unsupported curve");
+    }
+  }
+  d_in.release();
+  d_out.release();
+  return rc;
 }
 
 }  // extern "C"

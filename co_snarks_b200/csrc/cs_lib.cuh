@@ -75,6 +75,28 @@ struct cs_domain {
   std::vector<uint64_t> group_gen;  // Montgomery
 };
 
+#if defined(CS_ENABLE_BLS12_381)
+#define CS_CASE_BLS(...)   \
+  case CS_BLS12_381: {     \
+    typedef Bls381Cfg Cfg; \
+    __VA_ARGS__;           \
+  } break;
+#else
+#define CS_CASE_BLS(...)
+#endif
+
+#define CS_DISPATCH_CURVE(curve, ...)                                        \
+  switch ((int)(curve)) {                                                    \
+    case CS_BN254: {                                                         \
+      typedef Bn254Cfg Cfg;                                                  \
+      __VA_ARGS__;                                                           \
+    } break;                                                                 \
+      CS_CASE_BLS(__VA_ARGS__)                                               \
+    default:                                                                 \
+      return cs::fail(CS_ERR_ARG, "unsupported curve id %d", (int)(curve));      \
+  }
+
+
 namespace cs {
 std::atomic<uint64_t>& launch_counter();
 int ctx_fork(cs_ctx* ctx, int nside);

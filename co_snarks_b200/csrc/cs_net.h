@@ -14,7 +14,7 @@
 namespace cs {
 
 constexpr int NET_MAX_PARTIES = 8;
-constexpr uint32_t NET_CHUNK = 1024;  // payload bytes per mailbox slot
+constexpr uint32_t NET_CHUNK = 65536;  // payload bytes per mailbox slot (point-sized messages use a few hundred; vectors stream in 64 KB chunks)
 constexpr uint32_t NET_SLOTS = 8;     // slots per (receiver, sender) channel
 
 // one slot: payload, then the header that makes it valid (written by a second, later copy)

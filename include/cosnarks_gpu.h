@@ -407,6 +407,46 @@ int cs_groth16_rep3_prove_helper(cs_ctx* ctx, cs_groth16_pk* pk, int party, cs_n
                                  const uint64_t* h_public_inputs, const uint64_t* h_witness_shares,
                                  const uint64_t* d_witness_shares);
 
+/* ---- Shamir(n, t): ShamirPreprocessing / ShamirState (mpc-core/src/protocols/shamir.rs:26-186), the DN07 double
+ * sharings (shamir/rngs.rs:334-470), king-based degree reduction (shamir/network.rs:150-301) and the openings
+ * (shamir/pointshare.rs:102-111) over an n-party cs_net.  num_parties >= 2 threshold + 1 (shamir.rs:41-43).
+ * `amount` pairs are preprocessed at creation (rounded up to batches of t + 1); get_pair refills on demand. */
+typedef struct cs_shamir_state cs_shamir_state;
+int cs_shamir_state_create(cs_net* net, cs_curve curve, int num_parties, int threshold, size_t amount, cs_shamir_state** out);
+int cs_shamir_state_fork(cs_shamir_state* st, size_t amount, cs_shamir_state** out);
+size_t cs_shamir_state_pairs(const cs_shamir_state* st);
+/* ShamirState::rand: a degree-t share of a value no party knows (the r_t half of a pair) */
+int cs_shamir_state_rand(cs_shamir_state* st, cs_net* net, uint64_t* out_share);
+/* the party's opening weights: open_lagrange_t (t + 1 entries) or open_lagrange_2t (2t + 1), for the parties
+ * id, id-1, id-2, ... (mod n) in that order */
+int cs_shamir_open_lagrange(const cs_shamir_state* st, int degree_2t, uint64_t* out, size_t capacity_elems, size_t* out_n);
+/* degree_reduce_many on a device vector of degree-2t values (the result of a local share product): consumes one pair
+ * per element; inp += r_2t, parties 1..2t send to the king (party 0), the king accumulates with the Lagrange weights
+ * (one k_vec_lincomb launch), shares the result as a known polynomial with t zero shares and sends acc * P(id + 1)
+ * to parties 0..n-t-1; share -= r_t.  Vector arithmetic on the GPU, traffic through cs_net. */
+int cs_shamir_degree_reduce_many(cs_ctx* ctx, cs_shamir_state* st, cs_net* net, const uint64_t* d_in, size_t len, uint64_t* d_out);
+/* degree_reduce_point: the same for one point share; `base_affine` is the public point the pair is lifted with
+ * (the reference uses the group generator) */
+int cs_shamir_degree_reduce_point(cs_shamir_state* st, cs_net* net, cs_group group, const uint64_t* base_affine,
+                                  const uint64_t* in_affine, uint64_t* out_affine);
+/* open_half_point: broadcast_next over 2t + 1 parties + reconstruct_point with open_lagrange_2t */
+int cs_shamir_open_half_point(cs_shamir_state* st, cs_net* net, cs_group group, const uint64_t* in_affine, uint64_t* out_affine);
+
+/* ShamirCoGroth16::prove (co-groth16/src/groth16.rs:439-463 -> prove_inner -> create_proof_with_assignment with
+ * ShamirGroth16Driver, mpc/shamir.rs): three pairs are preprocessed over net0 (two rand calls, one for scalar_mul's
+ * degree_reduce_point), state1 = state0.fork(1); local phase on the GPU (cs_groth16_shamir_local), then
+ * open_half_point(g_a) | scalar_mul(g1_b, r) = degree_reduce_point + local product, then the openings of g_c and
+ * g2_b as degree-2t sharings.  out_rs (optional, 2 x Fr): this party's shares of r and s. */
+int cs_groth16_shamir_prove(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, int num_parties, int threshold,
+                            const uint64_t* h_public_inputs, const uint64_t* h_witness_shares, uint64_t* out_a,
+                            uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs);
+/* CoGroth16::prove_with_shamir_bridge (groth16.rs:394-417): a Rep3-shared witness is translated locally to
+ * Shamir(t = 1, n = 3) shares (bridges/rep3_to_shamir.rs:31-63; k_rep3_to_shamir on the device) and proved with the
+ * Shamir driver. */
+int cs_groth16_prove_with_shamir_bridge(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1,
+                                        const uint64_t* h_public_inputs, const uint64_t* h_witness_rep3_shares,
+                                        uint64_t* out_a, uint64_t* out_b, uint64_t* out_c, uint64_t* out_rs);
+
 /* ShamirGroth16Driver's local phase (co-groth16/src/mpc/shamir.rs:29-119): identical arithmetic to the plain
  * driver on degree-t shares -- every party adds the public terms/points; outputs are degree-2t point shares
  * that the host protocol opens (shamir/pointshare.rs:86-113). */
@@ -522,6 +562,7 @@ int cs_fq_to_mont(cs_curve curve, const uint64_t* in_canonical, uint64_t* out_mo
 int cs_fq_from_mont(cs_curve curve, const uint64_t* in_mont, uint64_t* out_canonical, size_t n);
 /* single-element Fr arithmetic in Montgomery form (r*s of groth16.rs:297, share algebra of the host protocol) */
 int cs_fr_mul(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
+int cs_fr_inv(cs_curve curve, const uint64_t* a_mont, uint64_t* out_mont);
 int cs_fr_add(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
 int cs_fr_sub(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
 int cs_groth16_roots_of_unity(cs_curve curve, unsigned pow, uint64_t* out_group_gen_mont,
