@@ -415,6 +415,7 @@ typedef struct cs_shamir_state cs_shamir_state;
 int cs_shamir_state_create(cs_net* net, cs_curve curve, int num_parties, int threshold, size_t amount, cs_shamir_state** out);
 int cs_shamir_state_fork(cs_shamir_state* st, size_t amount, cs_shamir_state** out);
 size_t cs_shamir_state_pairs(const cs_shamir_state* st);
+void cs_shamir_state_free(cs_shamir_state* st);
 /* ShamirState::rand: a degree-t share of a value no party knows (the r_t half of a pair) */
 int cs_shamir_state_rand(cs_shamir_state* st, cs_net* net, uint64_t* out_share);
 /* the party's opening weights: open_lagrange_t (t + 1 entries) or open_lagrange_2t (2t + 1), for the parties
