@@ -88,6 +88,11 @@ SIGNATURES = {
     "cs_shamir_open_half_point": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cs_groth16_shamir_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6),
     "cs_groth16_prove_with_shamir_bridge": (C.c_int, [C.c_void_p] * 10),
+    "cs_share_rep3_device": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_fr_rand_device": (C.c_int, [C.c_void_p, C.c_int, C.c_char_p, C.c_uint64, C.c_void_p, C.c_size_t]),
+    "cs_rep3_witness_read": (C.c_int, [C.c_char_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t),
+                                       C.POINTER(C.c_size_t), C.POINTER(C.c_int)]),
+    "cs_rep3_replicate_additive": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "cs_net_from_callbacks": (C.c_int, [C.c_int, C.c_int, C.POINTER(NetCallbacks), C.POINTER(C.c_void_p)]),
     "cs_net_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
     "cs_net_peer_handle": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -957,6 +962,21 @@ def os_random(lib, nbytes):
     if lib.cs_os_random(_ptr(out), nbytes):
         raise CsError(lib.cs_last_error().decode())
     return out.tobytes()
+
+
+def read_rep3_witness(lib, path, curve=CS_BN254):
+    """CompressedRep3SharedWitness share file (co-circom split-witness output) -> (public [np, 4], shares, kind):
+    kind CS_REP3: shares [nw, 8] (a || b, Montgomery); kind CS_PLAIN: additive half shares [nw, 4]."""
+    npub, nwit, kind = C.c_size_t(0), C.c_size_t(0), C.c_int(0)
+    if lib.cs_rep3_witness_read(os.fsencode(path), curve, None, 0, None, 0, C.byref(npub), C.byref(nwit), C.byref(kind)):
+        raise CsError(lib.cs_last_error().decode())
+    per = 2 if kind.value == CS_REP3 else 1
+    pub = np.zeros((npub.value, 4), dtype=np.uint64)
+    sh = np.zeros((nwit.value, 4 * per), dtype=np.uint64)
+    if lib.cs_rep3_witness_read(os.fsencode(path), curve, _ptr(pub), npub.value, _ptr(sh), nwit.value * per,
+                                C.byref(npub), C.byref(nwit), C.byref(kind)):
+        raise CsError(lib.cs_last_error().decode())
+    return pub, sh, kind.value
 
 
 def read_wtns(lib, path, curve=CS_BN254):

@@ -448,12 +448,18 @@ int ntt_run(cs_ctx* ctx, const cs_domain* d, uint32_t* d_data, unsigned batch, b
             const uint32_t* d_post, cudaStream_t st) {
   if (batch != 1 && batch != 2) return fail(CS_ERR_ARG, "ntt: batch must be 1 or 2");
   if (d->log_n == 0) return 0;
+  static int v2_env = -1;  // CS_NTT_V2=0 keeps the round-1 kernel (A/B comparison)
+  if (v2_env < 0) { const char* e = getenv("CS_NTT_V2"); v2_env = e ? atoi(e) : 1; }
   CS_DISPATCH_CURVE(d->curve, {
     typedef typename Cfg::FrP FrP;
-    if (inverse_in_to_out)
-      return ntt_enqueue<FrP>(d_data, d->tw_inv.as<uint32_t>(), d->log_n, batch, false, d_post,
-                              d_post ? nullptr : d->inv_n.as<uint32_t>(), st);
-    return ntt_enqueue<FrP>(d_data, d->tw_fwd.as<uint32_t>(), d->log_n, batch, true, d_post, nullptr, st);
+    const uint32_t* twp = inverse_in_to_out ? d->tw_inv.as<uint32_t>() : d->tw_fwd.as<uint32_t>();
+    const uint32_t* scale = (inverse_in_to_out && !d_post) ? d->inv_n.as<uint32_t>() : nullptr;
+    if (v2_env) {  // TMA-staged tiles + register radix-8 (cs_ntt8.cuh) from 2^12 on
+      bool used = false;
+      CS_TRY((ntt_enqueue8<FrP>(d_data, twp, d->log_n, batch, !inverse_in_to_out, d_post, scale, st, &used)));
+      if (used) return 0;
+    }
+    return ntt_enqueue<FrP>(d_data, twp, d->log_n, batch, !inverse_in_to_out, d_post, scale, st);
   });
   return 0;
 }
@@ -658,6 +664,40 @@ int cs_rep3_set_b(cs_ctx* ctx, cs_curve curve, const uint64_t* d_recv, size_t n,
   CS_DISPATCH_CURVE(curve, {
     CS_LAUNCH(k_rep3_set_b<typename Cfg::FrP>, ceil_div(n, 256), 256, 0, ctx->stream,
               reinterpret_cast<const uint32_t*>(d_recv), n, reinterpret_cast<uint32_t*>(d_out));
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_share_rep3_device(cs_ctx* ctx, cs_curve curve, const uint64_t* d_witness, size_t n, const uint8_t* h_seed32,
+                         uint64_t* d_share0, uint64_t* d_share1, uint64_t* d_share2) {
+  if (!ctx || (n && (!d_witness || !d_share0 || !d_share1 || !d_share2))) return fail(CS_ERR_ARG, "cs_share_rep3_device: NULL argument");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  uint8_t seed[32];
+  if (h_seed32) memcpy(seed, h_seed32, 32); else CS_TRY(cs_os_random(seed, 32));
+  PrfKey1 key;
+  for (int i = 0; i < 8; i++) key.k[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_share_rep3<typename Cfg::FrP>, ceil_div(n, 128), 128, 0, ctx->stream, key, 12u, Cfg::FR_BITS,
+              reinterpret_cast<const uint32_t*>(d_witness), n, reinterpret_cast<uint32_t*>(d_share0),
+              reinterpret_cast<uint32_t*>(d_share1), reinterpret_cast<uint32_t*>(d_share2));
+  });
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int cs_fr_rand_device(cs_ctx* ctx, cs_curve curve, const uint8_t* h_seed32, uint64_t stream_base, uint64_t* d_out, size_t n) {
+  if (!ctx || (n && !d_out)) return fail(CS_ERR_ARG, "cs_fr_rand_device: NULL argument");
+  if (n == 0) return 0;
+  CS_CUDA(cudaSetDevice(ctx->device));
+  uint8_t seed[32];
+  if (h_seed32) memcpy(seed, h_seed32, 32); else CS_TRY(cs_os_random(seed, 32));
+  PrfKey1 key;
+  for (int i = 0; i < 8; i++) key.k[i] = (uint32_t)seed[4 * i] | ((uint32_t)seed[4 * i + 1] << 8) | ((uint32_t)seed[4 * i + 2] << 16) | ((uint32_t)seed[4 * i + 3] << 24);
+  CS_DISPATCH_CURVE(curve, {
+    CS_LAUNCH(k_fr_rand<typename Cfg::FrP>, ceil_div(n, 128), 128, 0, ctx->stream, key, stream_base, 12u, Cfg::FR_BITS, n,
+              reinterpret_cast<uint32_t*>(d_out));
   });
   CS_CUDA(cudaGetLastError());
   return 0;

@@ -13,6 +13,7 @@
 #include <fstream>
 #include <map>
 #include "cs_lib.cuh"
+#include "cs_net.h"
 
 using namespace cs;
 
@@ -334,6 +335,173 @@ int cs_wtns_read(const char* path, cs_curve curve, uint64_t* out_mont, size_t ca
   std::vector<uint64_t> tmp((size_t)nvars * 4);
   memcpy(tmp.data(), w.data.data() + w.sec[2].first, (size_t)nvars * 32);
   return cs_fr_to_mont(curve, tmp.data(), out_mont, nvars);
+}
+
+}  // extern "C"
+
+// ---- CompressedRep3SharedWitness (bincode 1 over the serde derives; see include/cosnarks_gpu.h) ------------------
+namespace {
+
+struct Cursor {
+  const uint8_t* p;
+  size_t left;
+  bool ok = true;
+  bool take(void* dst, size_t k) {
+    if (k > left) { ok = false; return false; }
+    if (dst) memcpy(dst, p, k);
+    p += k; left -= k;
+    return true;
+  }
+  uint64_t u64() { uint64_t v = 0; take(&v, 8); return v; }
+  uint32_t u32() { uint32_t v = 0; take(&v, 4); return v; }
+};
+
+// bytes(ark-compressed Vec<T>): u64 byte length, then u64 element count, then count * elem_bytes
+bool read_ark_vec(Cursor& c, size_t elem_bytes, std::vector<uint8_t>& out, size_t& count) {
+  const uint64_t blen = c.u64();
+  if (!c.ok || blen > c.left || blen < 8) return c.ok = false;
+  Cursor in{c.p, (size_t)blen};
+  count = (size_t)in.u64();
+  if (count > (blen - 8) / elem_bytes || count * elem_bytes != blen - 8) return c.ok = false;
+  out.assign(in.p, in.p + count * elem_bytes);
+  c.take(nullptr, (size_t)blen);
+  return true;
+}
+
+// SeededType<Vec<F>, ChaCha12Rng>: 0 Shares(bytes(Vec<F>)) | 1 Seed([u8; 32], usize) -> canonical or Montgomery limbs
+template <class FrP>
+bool read_seeded(Cursor& c, unsigned bits, std::vector<uint64_t>& mont) {
+  typedef host::HFp<FrP> HR;
+  const uint32_t variant = c.u32();
+  if (!c.ok) return false;
+  if (variant == 0) {
+    std::vector<uint8_t> raw;
+    size_t n = 0;
+    if (!read_ark_vec(c, 32, raw, n)) return false;
+    mont.resize(n * 4);
+    for (size_t i = 0; i < n; i++) {
+      HR v;
+      memcpy(v.l, &raw[32 * i], 32);
+      if (HR::geq_mod(v.l)) return c.ok = false;  // ark rejects non-canonical encodings
+      HR m = v.to_mont();
+      memcpy(&mont[4 * i], m.l, 32);
+    }
+    return true;
+  }
+  if (variant != 1) return c.ok = false;
+  uint8_t seed[32];
+  if (!c.take(seed, 32)) return false;
+  const uint64_t len = c.u64();
+  if (!c.ok || len > (1ull << 32)) return c.ok = false;
+  HostChaCha rng;
+  rng.init(seed, 0);
+  mont.resize((size_t)len * 4);
+  for (size_t i = 0; i < len; i++) rng.template fr_rand<FrP>(&mont[4 * i], bits);  // expand_vec: len x F::rand (rep3.rs:181-196)
+  return true;
+}
+
+template <class FrP>
+int rep3_witness_read_t(const std::vector<uint8_t>& file, const char* path, unsigned bits, uint64_t* out_public, size_t pub_cap,
+                        uint64_t* out_shares, size_t sh_cap, size_t* n_pub, size_t* n_wit, cs_share_kind* kind) {
+  typedef host::HFp<FrP> HR;
+  Cursor c{file.data(), file.size()};
+  std::vector<uint8_t> raw;
+  size_t np = 0;
+  if (!read_ark_vec(c, 32, raw, np)) return fail(CS_ERR_ARG, "%s: malformed public inputs", path);
+  const uint32_t variant = c.u32();
+  if (!c.ok || variant > 3) return fail(CS_ERR_ARG, "%s: unknown share variant", path);
+  std::vector<uint64_t> a, b;
+  size_t nw = 0;
+  bool replicated = variant < 2;
+  if (variant == 0) {
+    std::vector<uint8_t> sh;
+    if (!read_ark_vec(c, 64, sh, nw)) return fail(CS_ERR_ARG, "%s: malformed replicated shares", path);
+    a.resize(nw * 8);  // interleaved a || b directly
+    for (size_t i = 0; i < 2 * nw; i++) {
+      HR v;
+      memcpy(v.l, &sh[32 * i], 32);
+      if (HR::geq_mod(v.l)) return fail(CS_ERR_ARG, "%s: non-canonical field element", path);
+      HR m = v.to_mont();
+      memcpy(&a[4 * i], m.l, 32);
+    }
+  } else if (variant == 1) {
+    if (!read_seeded<FrP>(c, bits, a) || !read_seeded<FrP>(c, bits, b)) return fail(CS_ERR_ARG, "%s: malformed seeded shares", path);
+    if (a.size() != b.size()) return fail(CS_ERR_ARG, "Lengths of shares do not match");  // rep3.rs:266-268
+    nw = a.size() / 4;
+    std::vector<uint64_t> il(nw * 8);
+    for (size_t i = 0; i < nw; i++) { memcpy(&il[8 * i], &a[4 * i], 32); memcpy(&il[8 * i + 4], &b[4 * i], 32); }
+    a.swap(il);
+  } else if (variant == 2) {
+    std::vector<uint8_t> sh;
+    if (!read_ark_vec(c, 32, sh, nw)) return fail(CS_ERR_ARG, "%s: malformed additive shares", path);
+    a.resize(nw * 4);
+    for (size_t i = 0; i < nw; i++) {
+      HR v;
+      memcpy(v.l, &sh[32 * i], 32);
+      if (HR::geq_mod(v.l)) return fail(CS_ERR_ARG, "%s: non-canonical field element", path);
+      HR m = v.to_mont();
+      memcpy(&a[4 * i], m.l, 32);
+    }
+  } else {
+    if (!read_seeded<FrP>(c, bits, a)) return fail(CS_ERR_ARG, "%s: malformed seeded additive shares", path);
+    nw = a.size() / 4;
+  }
+  if (c.left != 0) return fail(CS_ERR_ARG, "%s: %zu trailing bytes", path, c.left);
+  *n_pub = np;
+  *n_wit = nw;
+  if (kind) *kind = replicated ? CS_REP3 : CS_PLAIN;
+  if (!out_public && !out_shares) return 0;  // size query
+  const size_t per = replicated ? 2 : 1;
+  if (!out_public || !out_shares || pub_cap < np || sh_cap < nw * per) return fail(CS_ERR_ARG, "cs_rep3_witness_read: output buffers too small");
+  for (size_t i = 0; i < np; i++) {
+    HR v;
+    memcpy(v.l, &raw[32 * i], 32);
+    if (HR::geq_mod(v.l)) return fail(CS_ERR_ARG, "%s: non-canonical field element", path);
+    HR m = v.to_mont();
+    memcpy(&out_public[4 * i], m.l, 32);
+  }
+  memcpy(out_shares, a.data(), nw * per * 32);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cs_rep3_witness_read(const char* path, cs_curve curve, uint64_t* out_public, size_t public_capacity, uint64_t* out_shares,
+                         size_t shares_capacity_elems, size_t* out_n_public, size_t* out_n_witness, cs_share_kind* out_kind) {
+  if (!path || !out_n_public || !out_n_witness) return fail(CS_ERR_ARG, "cs_rep3_witness_read: NULL argument");
+  std::ifstream f(path, std::ios::binary | std::ios::ate);
+  if (!f) return fail(CS_ERR_ARG, "cannot open %s", path);
+  const std::streamsize sz = f.tellg();
+  f.seekg(0);
+  std::vector<uint8_t> data((size_t)sz);
+  if (sz && !f.read((char*)data.data(), sz)) return fail(CS_ERR_ARG, "cannot read %s", path);
+  switch ((int)curve) {
+    case CS_BN254:
+      return rep3_witness_read_t<Bn254Fr>(data, path, 254, out_public, public_capacity, out_shares, shares_capacity_elems,
+                                          out_n_public, out_n_witness, out_kind);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381:
+      return rep3_witness_read_t<Bls381Fr>(data, path, 255, out_public, public_capacity, out_shares, shares_capacity_elems,
+                                           out_n_public, out_n_witness, out_kind);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve");
+  }
+}
+
+int cs_rep3_replicate_additive(cs_net* net, const uint64_t* h_additive, size_t n, uint64_t* h_out_shares) {
+  if (!net || (n && (!h_additive || !h_out_shares))) return fail(CS_ERR_ARG, "cs_rep3_replicate_additive: NULL argument");
+  if (net->n != 3) return fail(CS_ERR_ARG, "cs_rep3_replicate_additive: Rep3 needs a 3-party net");
+  std::vector<uint64_t> prev(n * 4);
+  Rep3Net rn(net);
+  CS_TRY(rn.send_next(h_additive, n * 32));
+  CS_TRY(rn.recv_prev(prev.data(), n * 32));
+  for (size_t i = 0; i < n; i++) {
+    memcpy(&h_out_shares[8 * i], &h_additive[4 * i], 32);
+    memcpy(&h_out_shares[8 * i + 4], &prev[4 * i], 32);
+  }
+  return 0;
 }
 
 }  // extern "C"

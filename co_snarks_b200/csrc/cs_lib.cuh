@@ -9,6 +9,7 @@
 #include "cs_msm.cuh"
 #include "cs_msm52.cuh"
 #include "cs_ntt.cuh"
+#include "cs_ntt8.cuh"
 #include "cs_vec.cuh"
 #include "cs_prf.cuh"
 #include "cs_host_field.h"

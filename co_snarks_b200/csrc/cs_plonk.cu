@@ -657,7 +657,7 @@ int r3_step_t(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out)
     }
     case CS_PLONK_R3_ROUND2_C: {  // out: g (n) | q (n + 1), additive
       s->rbase = s->ctr;
-      s->ctr += 3 * (uint64_t)n + 2;
+      s->ctr += 2 * (3 * (uint64_t)n + 2);  // 3n + 2 random shares s, r, s' of 64 bytes each (two element slots)
       CS_LAUNCH(k_r3_round2_c<FrP>, ceil_div(n + 1, 128), 128, 0, st, r3_slot(s, 3), n, s->prf, s->rbase, s->ctr, addv,
                 addv + (size_t)n * NW);
       s->ctr += 2 * (uint64_t)n + 1;

@@ -64,8 +64,12 @@ template <class FrP> CS_D Fp<FrP> sh_lmul(const Sh<FrP>& x, const Sh<FrP>& y) { 
 template <class FrP> CS_D Fp<FrP> prf_mask(const PrfArgs& P, uint64_t idx) {
   return prf_field_element<FrP>(P.keys.k, P.pos1 + 8 * idx, P.rounds) - prf_field_element<FrP>(P.keys.k + 8, P.pos2 + 8 * idx, P.rounds);
 }
-template <class FrP> CS_D Sh<FrP> prf_share(const PrfArgs& P, uint64_t idx) {  // arithmetic::rand: (rng1, rng2)
-  return Sh<FrP>{prf_field_element<FrP>(P.keys.k, P.pos1 + 8 * idx, P.rounds), prf_field_element<FrP>(P.keys.k + 8, P.pos2 + 8 * idx, P.rounds)};
+// arithmetic::rand: (F(rng1), F(rng2)).  Random share number `j` of the region that starts at element index `rbase`
+// takes TWO element slots (64 bytes) of each stream: a 64-byte draw is uniform up to 2^-256 (the reference uses
+// F::rand's rejection sampling, arithmetic.rs:357-360).
+template <class FrP> CS_D Sh<FrP> prf_share(const PrfArgs& P, uint64_t rbase, uint64_t j) {
+  const uint64_t w = 8 * (rbase + 2 * j);
+  return Sh<FrP>{prf_field_element_wide<FrP>(P.keys.k, P.pos1 + w, P.rounds), prf_field_element_wide<FrP>(P.keys.k + 8, P.pos2 + w, P.rounds)};
 }
 
 struct R3Round2In {
@@ -118,10 +122,10 @@ CS_GLOBAL void k_r3_round2_c(const uint32_t* den, uint32_t n, PrfArgs P, uint64_
                               uint32_t* out_g, uint32_t* out_q) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  Sh<FrP> r = prf_share<FrP>(P, rbase + n + i), sp = prf_share<FrP>(P, rbase + 2 * n + 1 + i);
+  Sh<FrP> r = prf_share<FrP>(P, rbase, n + i), sp = prf_share<FrP>(P, rbase, 2 * n + 1 + i);
   st_fr<FrP>(out_q + (size_t)i * FrP::N, sh_lmul<FrP>(r, sp) + prf_mask<FrP>(P, mbase + n + i));
   if (i < n) {
-    Sh<FrP> s = prf_share<FrP>(P, rbase + i);
+    Sh<FrP> s = prf_share<FrP>(P, rbase, i);
     st_fr<FrP>(out_g + (size_t)i * FrP::N, sh_lmul<FrP>(ld_sh<FrP>(den, i), s) + prf_mask<FrP>(P, mbase + i));
   }
 }
@@ -132,17 +136,17 @@ CS_GLOBAL void k_r3_round2_d(const uint32_t* num, const uint32_t* ginv, const ui
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   constexpr int NW = FrP::N;
-  Sh<FrP> deninv = sh_mulp<FrP>(prf_share<FrP>(P, rbase + i), ld_fr<FrP>(ginv + (size_t)i * NW));
+  Sh<FrP> deninv = sh_mulp<FrP>(prf_share<FrP>(P, rbase, i), ld_fr<FrP>(ginv + (size_t)i * NW));
   st_reshare<FrP>(ox, px, i, sh_lmul<FrP>(ld_sh<FrP>(num, i), deninv) + prf_mask<FrP>(P, mbase + i));
-  Sh<FrP> rinv0 = sh_mulp<FrP>(prf_share<FrP>(P, rbase + 2 * n + 1), ld_fr<FrP>(qinv));
-  st_reshare<FrP>(ou, pu, i, sh_lmul<FrP>(rinv0, prf_share<FrP>(P, rbase + n + i + 1)) + prf_mask<FrP>(P, mbase + n + i));
+  Sh<FrP> rinv0 = sh_mulp<FrP>(prf_share<FrP>(P, rbase, 2 * n + 1), ld_fr<FrP>(qinv));
+  st_reshare<FrP>(ou, pu, i, sh_lmul<FrP>(rinv0, prf_share<FrP>(P, rbase, n + i + 1)) + prf_mask<FrP>(P, mbase + n + i));
 }
 // m_i = r_i x_i
 template <class FrP>
 CS_GLOBAL void k_r3_round2_e(const uint32_t* x, uint32_t n, PrfArgs P, uint64_t rbase, uint64_t mbase, uint32_t* om, uint32_t* pm) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  st_reshare<FrP>(om, pm, i, sh_lmul<FrP>(prf_share<FrP>(P, rbase + n + i), ld_sh<FrP>(x, i)) + prf_mask<FrP>(P, mbase + i));
+  st_reshare<FrP>(om, pm, i, sh_lmul<FrP>(prf_share<FrP>(P, rbase, n + i), ld_sh<FrP>(x, i)) + prf_mask<FrP>(P, mbase + i));
 }
 // y_i = m_i / r_{i+1} = m_i (s'_{i+1} / Q_{i+1}), additive, to be opened
 template <class FrP>
@@ -150,7 +154,7 @@ CS_GLOBAL void k_r3_round2_f(const uint32_t* m, const uint32_t* qinv, uint32_t n
                               uint32_t* out_y) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  Sh<FrP> rinv = sh_mulp<FrP>(prf_share<FrP>(P, rbase + 2 * n + 1 + i + 1), ld_fr<FrP>(qinv + (size_t)(i + 1) * FrP::N));
+  Sh<FrP> rinv = sh_mulp<FrP>(prf_share<FrP>(P, rbase, 2 * n + 1 + i + 1), ld_fr<FrP>(qinv + (size_t)(i + 1) * FrP::N));
   st_fr<FrP>(out_y + (size_t)i * FrP::N, sh_lmul<FrP>(ld_sh<FrP>(m, i), rinv) + prf_mask<FrP>(P, mbase + i));
 }
 // prod_{j<=i} x_j = Y_0..Y_i * u_{i+1}  (Y public running products);  buffer_z is that rotated right by one

@@ -43,6 +43,7 @@ typedef struct cs_ctx cs_ctx;
 typedef struct cs_bases cs_bases;
 typedef struct cs_domain cs_domain;
 typedef struct cs_groth16_pk cs_groth16_pk;
+typedef struct cs_net cs_net; /* party-to-party transport, see "party-to-party transport" below */
 
 /* ---- library / context ------------------------------------------------------------------------ */
 const char* cs_last_error(void);
@@ -290,6 +291,35 @@ int cs_ipc_export(cs_ctx* ctx, const void* d_ptr, uint8_t* out_handle64);
 int cs_ipc_open(cs_ctx* ctx, const uint8_t* handle64, void** out_peer_ptr);
 int cs_ipc_close(cs_ctx* ctx, void* peer_ptr);
 
+/* ---- sharing on the device -----------------------------------------------------------
+ * cs_share_rep3_device: rep3::share_field_elements (mpc-core/src/protocols/rep3.rs:281-293; what split-witness /
+ * CompressedRep3SharedWitness::share_rep3 with Compression::None produce, co-circom-types/src/lib.rs:279-382) for a
+ * device-resident witness: a, b uniform by rejection sampling (F::rand), c = val - a - b; d_share0/1/2 receive the
+ * three parties' n x {a, b} vectors (they may live on other GPUs: any pointer this GPU can store to).  seed32 = the
+ * ChaCha12 key of the dealer's rng (NULL: OS entropy); element i draws from the sub-streams 2i and 2i + 1.
+ * cs_fr_rand_device: n uniform elements (F::rand), element i from sub-stream stream_base + i. */
+int cs_share_rep3_device(cs_ctx* ctx, cs_curve curve, const uint64_t* d_witness, size_t n, const uint8_t* h_seed32,
+                         uint64_t* d_share0, uint64_t* d_share1, uint64_t* d_share2);
+int cs_fr_rand_device(cs_ctx* ctx, cs_curve curve, const uint8_t* h_seed32, uint64_t stream_base, uint64_t* d_out, size_t n);
+
+/* ---- share files: CompressedRep3SharedWitness (co-circom-types/src/lib.rs:162-219; written by `co-circom
+ * split-witness`, read by generate-proof with bincode::deserialize_from, co-circom.rs:1014-1016) -----------------
+ * bincode 1 (fixed-width little-endian integers) over serde derives: public_inputs = bytes(ark-compressed Vec<F>),
+ * then the Rep3ShareVecType variant (u32): 0 Replicated(bytes(Vec<{a, b}>)), 1 SeededReplicated{a, b: SeededType},
+ * 2 Additive(bytes(Vec<F>)), 3 SeededAdditive(SeededType); SeededType = 0 Shares(bytes) | 1 Seed([u8; 32], u64 len),
+ * expanded as len x F::rand over ChaCha12Rng::from_seed (rep3.rs:181-196).  ark field elements are 32 canonical
+ * little-endian bytes.  Output: public inputs and shares in Montgomery form; *out_kind = CS_REP3 for replicated
+ * shares (n_witness x {a, b}) or CS_PLAIN for additive half shares (n_witness x Fr) that still need
+ * cs_rep3_replicate_additive (uncompress_shared_witness reshares once, co-circom/src/lib.rs:64-73).
+ * Pass out buffers = NULL to query the sizes.  No reference fixture of this format exists in the repository: the
+ * layout is restated from the serde derives ("parity unpinned" at the byte level; round-trip tested). */
+int cs_rep3_witness_read(const char* path, cs_curve curve, uint64_t* out_public, size_t public_capacity,
+                         uint64_t* out_shares, size_t shares_capacity_elems, size_t* out_n_public, size_t* out_n_witness,
+                         cs_share_kind* out_kind);
+/* additive -> replicated: send my additive share vector to the next party, receive the previous party's:
+ * share_i = (mine_i, prev_i)  (Rep3NetworkExt::reshare_many) */
+int cs_rep3_replicate_additive(cs_net* net, const uint64_t* h_additive, size_t n, uint64_t* h_out_shares);
+
 /* ---- batched witness-extension VM operations (circom-mpc-vm/src/mpc/batched_rep3.rs:124-188, 322-337) ----------
  * BatchedCircomRep3VmWitnessExtension runs one circuit on a batch of inputs, so every VM opcode acts on a vector of
  * `batch_size` values.  These are its arithmetic opcodes on device-resident vectors: shares = n x {a, b}, publics =
@@ -340,7 +370,6 @@ int cs_honk_commit_batch(cs_ctx* ctx, const cs_bases* crs, cs_share_kind kind, c
  *      a slow receiver is never overrun.  Messages of any size (chunked); the Groth16 legs send 64..192 bytes.
  *      Bootstrap: create, exchange the 64-byte handles by any means (torch.distributed, files), connect.
  *      Parties living in ONE process (threads) connect with cs_net_peer_connect_local instead. */
-typedef struct cs_net cs_net;
 typedef struct {
   void* user;
   int (*send)(void* user, int to_party, const void* data, size_t bytes);

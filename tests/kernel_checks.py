@@ -1029,3 +1029,114 @@ def check_honk_commit_batch(ctx, n=200, seed=41):
         if x:
             ctx.free(x)
     crs.free()
+
+
+def check_share_rep3_device(ctx, n=1000):
+    """rep3::share_field_elements on the device (rep3.rs:281-293): the three parties' vectors are replicated shares
+    of the witness (a + b + c = value; party i's b is party i-1's a), uniform draws stay below r, a fixed seed is
+    reproducible and two seeds differ; cs_fr_rand_device: exact rejection sampling on per-element sub-streams."""
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(9)
+    vals = [rng.randrange(r) for _ in range(n)]
+    lib = ctx.lib
+    dw = ctx.to_device(cv.fr(vals))
+    ds = [ctx.alloc(n * 64) for _ in range(3)]
+    seed = bytes(range(32))
+    ctx._check(lib.cs_share_rep3_device(ctx.h, cv.id, dw, n, seed, ds[0], ds[1], ds[2]))
+    sh = [cv.fr_back(ctx.d2h(d, (2 * n, 4))) for d in ds]
+    for k in range(n):
+        assert sum(sh[i][2 * k] for i in range(3)) % r == vals[k]
+        assert all(sh[i][2 * k + 1] == sh[(i + 2) % 3][2 * k] for i in range(3))
+    first = sh[0][:8]
+    ctx._check(lib.cs_share_rep3_device(ctx.h, cv.id, dw, n, seed, ds[0], ds[1], ds[2]))
+    assert cv.fr_back(ctx.d2h(ds[0], (2 * n, 4)))[:8] == first
+    ctx._check(lib.cs_share_rep3_device(ctx.h, cv.id, dw, n, None, ds[0], ds[1], ds[2]))  # OS entropy
+    assert cv.fr_back(ctx.d2h(ds[0], (2 * n, 4)))[:8] != first
+    # the raw limbs of a uniform draw are a 254-bit value below r; the first draw of sub-stream 0 matches the host's
+    # ChaCha12 block function (cs_chacha_keystream with stream id 0 = the plain keystream)
+    dr = ctx.alloc(n * 32)
+    ctx._check(lib.cs_fr_rand_device(ctx.h, cv.id, seed, 0, dr, n))
+    raw = ctx.d2h(dr, (n, 4))
+    ints = B.limbs_to_ints(raw)
+    assert all(v < r for v in ints) and len(set(ints)) == n
+    ks = np.asarray(ctx.chacha_keystream(seed, 0, 12, 4), dtype=np.uint32).reshape(-1)
+    for half in range(8):
+        w = ks[8 * half:8 * half + 8]
+        limbs = [int(w[2 * i]) | (int(w[2 * i + 1]) << 32) for i in range(4)]
+        limbs[3] &= (1 << 62) - 1
+        v = sum(l << (64 * i) for i, l in enumerate(limbs))
+        if v < r:
+            assert ints[0] == v
+            break
+    for d in ds + [dw, dr]:
+        ctx.free(d)
+
+
+def write_rep3_share_file(path, public_ints, variant, payload, r):
+    """TEST-SIDE writer of the CompressedRep3SharedWitness bincode layout (see include/cosnarks_gpu.h):
+    variant 0: payload = [(a, b), ...]; 2: [x, ...]; 1: (seeded_a, seeded_b); 3: seeded, where seeded is either
+    ("shares", [x, ...]) or ("seed", seed32, length)."""
+    import struct
+
+    def ark_vec(elems, width):
+        body = struct.pack("<Q", len(elems)) + b"".join(int(e).to_bytes(32, "little") if width == 1 else
+                                                        b"".join(int(x).to_bytes(32, "little") for x in e) for e in elems)
+        return struct.pack("<Q", len(body)) + body
+
+    def seeded(sd):
+        if sd[0] == "shares":
+            return struct.pack("<I", 0) + ark_vec(sd[1], 1)
+        return struct.pack("<I", 1) + bytes(sd[1]) + struct.pack("<Q", sd[2])
+    out = ark_vec(public_ints, 1) + struct.pack("<I", variant)
+    if variant == 0:
+        out += ark_vec(payload, 2)
+    elif variant == 2:
+        out += ark_vec(payload, 1)
+    elif variant == 1:
+        out += seeded(payload[0]) + seeded(payload[1])
+    else:
+        out += seeded(payload)
+    with open(path, "wb") as f:
+        f.write(out)
+
+
+def check_rep3_share_files(lib, tmp_path):
+    """cs_rep3_witness_read on all four Rep3ShareVecType variants (co-circom-types/src/lib.rs:162-219): replicated,
+    seeded replicated (one half given as a seed: expanded with F::rand over ChaCha12), additive, seeded additive;
+    malformed files give an error code."""
+    import os
+    cv = Conv("bn254")
+    r = cv.r
+    rng = random.Random(3)
+    pub = [1, rng.randrange(r)]
+    n = 50
+    rep = [(rng.randrange(r), rng.randrange(r)) for _ in range(n)]
+    p = os.path.join(str(tmp_path), "w.shared")
+    write_rep3_share_file(p, pub, 0, rep, r)
+    gp, gs, kind = B.read_rep3_witness(lib, p, cv.id)
+    assert kind == B.CS_REP3 and cv.fr_back(gp) == pub and cv.fr_back(gs) == [x for ab in rep for x in ab]
+    add = [rng.randrange(r) for _ in range(n)]
+    write_rep3_share_file(p, pub, 2, add, r)
+    gp, gs, kind = B.read_rep3_witness(lib, p, cv.id)
+    assert kind == B.CS_PLAIN and cv.fr_back(gs) == add
+    seed = bytes(range(7, 39))
+    write_rep3_share_file(p, pub, 3, ("seed", seed, n), r)
+    _, seeded_vals, kind = B.read_rep3_witness(lib, p, cv.id)
+    seeded_ints = B.limbs_to_ints(seeded_vals)  # F::rand output limbs are the Montgomery representation
+    assert kind == B.CS_PLAIN and len(seeded_ints) == n and all(v < r for v in seeded_ints) and len(set(seeded_ints)) == n
+    write_rep3_share_file(p, pub, 1, (("seed", seed, n), ("shares", add)), r)
+    _, gs, kind = B.read_rep3_witness(lib, p, cv.id)
+    assert kind == B.CS_REP3
+    assert (gs[:, :4] == seeded_vals).all() and cv.fr_back(gs[:, 4:]) == add
+    # error behaviour: length mismatch between the two halves, a non-canonical element, truncation
+    write_rep3_share_file(p, pub, 1, (("seed", seed, n - 1), ("shares", add)), r)
+    with pytest.raises(RuntimeError, match="Lengths of shares do not match"):
+        B.read_rep3_witness(lib, p, cv.id)
+    write_rep3_share_file(p, pub, 2, [r] + add[1:], r)
+    with pytest.raises(RuntimeError):
+        B.read_rep3_witness(lib, p, cv.id)
+    data = open(p, "rb").read()
+    open(p, "wb").write(data[:-5])
+    with pytest.raises(RuntimeError):
+        B.read_rep3_witness(lib, p, cv.id)

@@ -160,3 +160,11 @@ def test_emu_rep3_batch_vm_ops(emu_ctx):
 
 def test_emu_honk_commit_batch(emu_ctx):
     K.check_honk_commit_batch(emu_ctx, n=40)
+
+
+def test_emu_share_rep3_device(emu_ctx):
+    K.check_share_rep3_device(emu_ctx, n=60)
+
+
+def test_rep3_share_files(emu_ctx, tmp_path):
+    K.check_rep3_share_files(emu_ctx.lib, tmp_path)

@@ -184,3 +184,7 @@ def test_rep3_batch_vm_ops(gpu_ctx):
 
 def test_honk_commit_batch(gpu_ctx):
     K.check_honk_commit_batch(gpu_ctx, n=1000)
+
+
+def test_share_rep3_device(gpu_ctx):
+    K.check_share_rep3_device(gpu_ctx, n=100000)
