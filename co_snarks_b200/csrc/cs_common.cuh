@@ -23,6 +23,23 @@
 
 #define COMMA ,
 
+// NVTX ranges named after the reference's `tracing` spans (co-groth16/src/groth16.rs:230-313,
+// groth16/reduction.rs:98-184), so an nsys / ncu --nvtx timeline of a proof reads like the reference's
+// trace output.  No-ops in the emulation build; near-free when no tool is attached.
+#if defined(CS_EMU)
+struct CsNvtxRange { explicit CsNvtxRange(const char*) {} };
+#else
+#include <nvtx3/nvToolsExt.h>
+struct CsNvtxRange {
+  explicit CsNvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~CsNvtxRange() { nvtxRangePop(); }
+  CsNvtxRange(const CsNvtxRange&) = delete;
+};
+#endif
+#define CS_NVTX_CAT2(a, b) a##b
+#define CS_NVTX_CAT(a, b) CS_NVTX_CAT2(a, b)
+#define CS_SPAN(name) CsNvtxRange CS_NVTX_CAT(cs_span_, __LINE__)(name)
+
 namespace cs {
 
 std::atomic<uint64_t>& launch_counter();

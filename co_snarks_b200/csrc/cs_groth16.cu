@@ -106,15 +106,20 @@ int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, cons
   CS_TRY(pk->d_b.reserve((size_t)n * batch * 32));
   CS_TRY(pk->d_c.reserve((size_t)n * 32));
   // a = A w (+ promoted public rows, reduction.rs:104-113), b = B w   (evaluate_constraint)
+  CS_SPAN("witness map from matrices");
+  {
+  CS_SPAN("evaluate constraints + coset table computation");
   CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->a_rowptr.as<uint32_t>(), pk->a_col.as<uint32_t>(),
             pk->a_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch, batch,
             pub_comp, (uint32_t)pk->nc, (uint32_t)pk->ni, n, pk->d_a.as<uint32_t>());
   CS_LAUNCH(k_spmv<FrP>, ceil_div(n, 128), 128, 0, st, pk->b_rowptr.as<uint32_t>(), pk->b_col.as<uint32_t>(),
             pk->b_coeff.as<uint32_t>(), pk->d_pub.as<uint32_t>(), (uint32_t)pk->ni, d_wit, batch, batch,
             pub_comp, (uint32_t)pk->nc, 0u, n, pk->d_b.as<uint32_t>());
+  }
   unsigned blocks = ceil_div(n, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
   // c = local_mul_vec(a, b)   (reduction.rs:160)
+  CS_SPAN("c: local_mul_vec / a, b, c: distribute powers (fft/ifft)");
   if (kind == CS_REP3)
     CS_LAUNCH(k_rep3_local_mul<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
               have_m1 ? pk->d_m1.as<uint32_t>() : (const uint32_t*)nullptr, (const uint32_t*)nullptr,
@@ -132,6 +137,7 @@ int witness_map_device(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, cons
   CS_TRY(ntt_run(ctx, pk->dom, pk->d_c.as<uint32_t>(), 1, true, post, st));
   CS_TRY(ntt_run(ctx, pk->dom, pk->d_c.as<uint32_t>(), 1, false, nullptr, st));
   // h = local_mul_vec(a', b') - c'   (reduction.rs:182-190), in place over c
+  CS_SPAN("ab: local_mul_vec + compute ab");
   if (kind == CS_REP3)
     CS_LAUNCH(k_rep3_local_mul<FrP>, blocks, 256, 0, st, pk->d_a.as<uint32_t>(), pk->d_b.as<uint32_t>(),
               have_m2 ? pk->d_m2.as<uint32_t>() : (const uint32_t*)nullptr, pk->d_c.as<uint32_t>(),
@@ -269,6 +275,7 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
   const uint32_t* wit = d_wit_in ? reinterpret_cast<const uint32_t*>(d_wit_in) : pk->d_wit.as<uint32_t>();
   if (have_aux) {
     // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
+    CS_SPAN("compute A, B/G1, B/G2 in create proof with assignment + msm l_query");
     if (do_a) CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
     if (do_b1) CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
     if (do_b2)
@@ -295,7 +302,10 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
       have_m1 = have_m2 = true;
     }
     CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, have_m1, have_m2, ctx->stream)));
-    CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
+    {
+      CS_SPAN("msm h_query");
+      CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
+    }
   }
   CS_TRY(ctx_join(ctx, 4));
 
@@ -331,6 +341,7 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
         b2_acc = host::hadd(b2_acc, H2::mul(H2::load(pk->b2_head.data() + k * g2l), h_pub + k * 4));
     }
   }
+  CS_SPAN("r*s without networking");
   if (rs_mont && out_rs_delta)  // (r s) * delta_1 (groth16.rs:297-298), also while the GPU is busy
     H1::store(out_rs_delta, H1::mul(H1::load(pk->delta_g1.data()), rs_mont));
   if (overlap) (*overlap)();  // caller's single-point work that does not depend on the MSM results
@@ -449,6 +460,7 @@ int rep3_prove_t(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_
     memcpy(h_acc, msg + G2L, G1L * 8);
   }
   Rep3Net n0(net0), n1(net1);
+  CS_SPAN("network round after calc coeff + finish - open two points and some adds");
   // ---- network round 1 (groth16.rs:305-308): open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1.
   // All sends first (they do not block), then the receives.
   CS_TRY(n0.send_next(g_a, G1L * 8));
