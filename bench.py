@@ -583,6 +583,27 @@ def run_rep3(args):
     dist.destroy_process_group()
 
 
+def run_plonk_rep3(args):
+    """BASELINE.json configs[3]: co-Plonk Rep3, BN254, synthetic circuit of domain 2^log_m, 3 parties on 3 GPUs.
+    torchrun --nproc-per-node 3 bench.py --mode plonk-rep3 --log-m 22.  One step = one collaborative proof
+    (first-layer products stored into the next party's GPU over NVLink peer memory, openings over NCCL)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import time_co_plonk as T
+    res = T.measure([args.log_m], reps=args.steps + 1)
+    if res is None:
+        return
+    r = res["2p%d" % args.log_m]
+    print(json.dumps({
+        "metric": "co-Plonk Rep3 proofs/sec (BN254, domain 2^%d)" % args.log_m, "value": r["proofs_per_s"], "unit": "proofs/s",
+        "n_gpus": 3, "steps": args.steps, "warmup": 1, "ms_per_step": r["ms_per_proof"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery, integer)",
+        "data": "synthetic snarkjs-style Plonk circuit with a valid key; proof accepted by the oracle's verifier: %s" % r["verified"],
+        "config": {"workload": "co-Plonk Rep3, BN254, synthetic circuit domain size 2^%d, 3 parties on 3xB200 "
+                               "(BASELINE.json configs[3])" % args.log_m, "setup_s": r["setup_s"]},
+        "e2e": {"value": r["proofs_per_s"], "unit": "proofs/s", "note": "host share buffers in, opened proof out, wall clock, max over ranks"},
+        "net_bytes_per_party_per_proof": r["bytes_sent_per_party"]}))
+
+
 def int_pipe_ceiling():
     """Measured ceiling of 256-bit Montgomery products on the integer pipe (tools/imad_peak, built by
     __graft_entry__.build()); falls back to the committed measurement of this pool's B200."""
@@ -627,7 +648,7 @@ def main():
     ap.add_argument("--log-m", type=int, default=20, help="log2 of the number of R1CS variables / domain size")
     ap.add_argument("--cpu-log-m", type=int, default=20, help="log2 size of the CPU baseline sample")
     ap.add_argument("--window-bits", type=int, default=0)
-    ap.add_argument("--mode", default="plain", choices=["plain", "rep3"])
+    ap.add_argument("--mode", default="plain", choices=["plain", "rep3", "plonk-rep3"])
     ap.add_argument("--gpus-per-party", type=int, default=1)
     ap.add_argument("--fast-setup", action="store_true", help="random (invalid) key: skips the host-side QAP setup")
     ap.add_argument("--no-verify", action="store_true")
@@ -639,6 +660,8 @@ def main():
         run_reference(args)
     elif args.mode == "rep3":
         run_rep3(args)
+    elif args.mode == "plonk-rep3":
+        run_plonk_rep3(args)
     else:
         run_ours(args)
 

@@ -20,60 +20,68 @@ from co_snarks_b200.rep3 import Rep3Network, Rep3State, random_field_limbs
 from workloads.synth_plonk import SynthPlonk
 
 R = 21888242871839275222246405745257275088548364400416034343698204186575808495617
-rank = int(os.environ["RANK"])
-local = int(os.environ.get("LOCAL_RANK", rank))
-torch.cuda.set_device(local)
-dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-assert dist.get_world_size() == 3
-ctx = B.Context(local)
-net = Rep3Network(device="cuda")
-sizes = [int(a) for a in sys.argv[1:]] or [16, 18]
-out = {"world": 3}
-for lg in sizes:
-    t_setup = time.time()
-    syn = SynthPlonk(ctx, lg)  # same seeds on every rank -> same circuit and key
-    pk = syn.make_key()
-    setup_s = time.time() - t_setup
-    npub = syn.n_public
-    # replicated sharing of the private witness from a common seed (every rank derives all three shares)
-    g = np.random.Generator(np.random.PCG64(7))
-    wit = syn.private_witness  # Montgomery limbs [m, 4]
-    m = wit.shape[0]
-    s0, s1 = random_field_limbs(g, m), random_field_limbs(g, m)
-    ints = lambda a: np.array(B.limbs_to_ints(a), dtype=object)
-    x, a0, a1 = ints(wit), ints(s0), ints(s1)
-    sh = [a0, a1, (x - a0 - a1) % R]
-    mine = np.stack([B.ints_to_limbs(list(sh[rank]), 4), B.ints_to_limbs(list(sh[(rank + 2) % 3]), 4)], axis=1)
-    state = Rep3State(net, seed=5000 + lg)
-    prover = Rep3CoPlonk(ctx, pk, rank)
-    comm = DistRep3Comm(prover, net, peer=True)
-    ms = []
-    reps = int(os.environ.get('CS_CO_PLONK_REPS', '4'))
-    for i in range(reps):
-        torch.cuda.synchronize()
-        dist.barrier()
-        t0 = time.perf_counter()
-        pts, evs = comm.run(prover.prove(state, syn.public_inputs, mine, syn.key["vk_points"], syn.n))
-        t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms.append(float(t.item()))
-    ok = None
-    if rank == 0:
-        from helpers import Conv, plonk_proof_from_device
-        from oracle import plonk as OP
-        from oracle.fields import BN254
-        from oracle.pairing_bn254 import pairing_product_is_one
-        proof = plonk_proof_from_device(Conv("bn254"), pts, evs)
-        ok = bool(OP.verify(BN254, syn.vk_ints(), proof, syn.full_witness[1:npub + 1], pairing_product_is_one))
-    t = sum(ms[1:]) / len(ms[1:])
-    out["2p%d" % lg] = {"ms_per_proof": round(t, 2), "proofs_per_s": round(1e3 / t, 2), "verified": ok,
-                        "bytes_sent_per_party": net.bytes_sent // reps, "setup_s": round(setup_s, 1)}
-    net.bytes_sent = 0
-    comm.close()
-    prover.free()
-    pk.free()
-if rank == 0:
-    print(json.dumps(out))
-dist.barrier()
-ctx.close()
-dist.destroy_process_group()
+
+
+def measure(sizes, reps=None):
+    """-> {"world": 3, "2p<lg>": {...}} on rank 0 (None elsewhere); needs torchrun with 3 ranks."""
+    rank = int(os.environ["RANK"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert dist.get_world_size() == 3
+    ctx = B.Context(local)
+    net = Rep3Network(device="cuda")
+    out = {"world": 3}
+    for lg in sizes:
+        t_setup = time.time()
+        syn = SynthPlonk(ctx, lg)  # same seeds on every rank -> same circuit and key
+        pk = syn.make_key()
+        setup_s = time.time() - t_setup
+        npub = syn.n_public
+        # replicated sharing of the private witness from a common seed (every rank derives all three shares)
+        g = np.random.Generator(np.random.PCG64(7))
+        wit = syn.private_witness  # Montgomery limbs [m, 4]
+        m = wit.shape[0]
+        s0, s1 = random_field_limbs(g, m), random_field_limbs(g, m)
+        ints = lambda a: np.array(B.limbs_to_ints(a), dtype=object)
+        x, a0, a1 = ints(wit), ints(s0), ints(s1)
+        sh = [a0, a1, (x - a0 - a1) % R]
+        mine = np.stack([B.ints_to_limbs(list(sh[rank]), 4), B.ints_to_limbs(list(sh[(rank + 2) % 3]), 4)], axis=1)
+        state = Rep3State(net, seed=5000 + lg)
+        prover = Rep3CoPlonk(ctx, pk, rank)
+        comm = DistRep3Comm(prover, net, peer=True)
+        ms = []
+        reps = reps or int(os.environ.get('CS_CO_PLONK_REPS', '4'))
+        for i in range(reps):
+            torch.cuda.synchronize()
+            dist.barrier()
+            t0 = time.perf_counter()
+            pts, evs = comm.run(prover.prove(state, syn.public_inputs, mine, syn.key["vk_points"], syn.n))
+            t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms.append(float(t.item()))
+        ok = None
+        if rank == 0:
+            from helpers import Conv, plonk_proof_from_device
+            from oracle import plonk as OP
+            from oracle.fields import BN254
+            from oracle.pairing_bn254 import pairing_product_is_one
+            proof = plonk_proof_from_device(Conv("bn254"), pts, evs)
+            ok = bool(OP.verify(BN254, syn.vk_ints(), proof, syn.full_witness[1:npub + 1], pairing_product_is_one))
+        t = sum(ms[1:]) / len(ms[1:])
+        out["2p%d" % lg] = {"ms_per_proof": round(t, 2), "proofs_per_s": round(1e3 / t, 2), "verified": ok,
+                            "bytes_sent_per_party": net.bytes_sent // reps, "setup_s": round(setup_s, 1)}
+        net.bytes_sent = 0
+        comm.close()
+        prover.free()
+        pk.free()
+    dist.barrier()
+    ctx.close()
+    dist.destroy_process_group()
+    return out if rank == 0 else None
+
+
+if __name__ == "__main__":
+    res = measure([int(a) for a in sys.argv[1:]] or [16, 18])
+    if res is not None:
+        print(json.dumps(res))
