@@ -259,7 +259,8 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
                 const uint64_t* d_wit_in, const uint64_t* h_m1, const uint64_t* h_m2, const uint64_t* r_hs, const uint64_t* s_hs,
                 uint64_t* out_a, uint64_t* out_b1, uint64_t* out_b2, uint64_t* out_l, uint64_t* out_h,
                 unsigned parts = CS_PART_ALL, const cs_rep3_prf* prf = nullptr, const uint64_t* rs_mont = nullptr,
-                uint64_t* out_rs_delta = nullptr, const std::function<void()>* overlap = nullptr) {
+                uint64_t* out_rs_delta = nullptr, const std::function<void()>* overlap = nullptr,
+                const std::function<int(const uint64_t*, const uint64_t*)>* mid = nullptr) {
   typedef HostGroup<Cfg, 0> H1;
   typedef HostGroup<Cfg, 1> H2;
   const unsigned batch = kind == CS_REP3 ? 2 : 1;
@@ -345,21 +346,37 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
   if (rs_mont && out_rs_delta)  // (r s) * delta_1 (groth16.rs:297-298), also while the GPU is busy
     H1::store(out_rs_delta, H1::mul(H1::load(pk->delta_g1.data()), rs_mont));
   if (overlap) (*overlap)();  // caller's single-point work that does not depend on the MSM results
-  CS_CUDA(cudaStreamSynchronize(ctx->stream));
   uint64_t tmp[24];
   int inf = 0;
+  // A and B1 run on side streams that started before the witness map and finish well before H: the caller's work
+  // that needs only those two (the first network round, s*A and r*B1) is done while the GPU still computes L, B2, H
+  bool ab_done = false;
+  if (mid && have_aux && do_a && do_b1) {
+    CS_CUDA(cudaEventSynchronize(ctx->ev_side[0]));
+    CS_CUDA(cudaEventSynchronize(ctx->ev_side[1]));
+    CS_TRY(msm_finish_dyn(ctx, 0, pk->a_query, tmp, &inf)); a_acc = host::hadd(a_acc, H1::load(tmp));
+    CS_TRY(msm_finish_dyn(ctx, 1, pk->b_g1, tmp, &inf)); b1_acc = host::hadd(b1_acc, H1::load(tmp));
+    H1::store(out_a, a_acc);
+    H1::store(out_b1, b1_acc);
+    CS_TRY((*mid)(out_a, out_b1));
+    ab_done = true;
+  }
+  CS_CUDA(cudaStreamSynchronize(ctx->stream));
   memset(out_l, 0, g1l * 8);
   memset(out_h, 0, g1l * 8);
   if (have_aux) {
-    if (do_a) { CS_TRY(msm_finish_dyn(ctx, 0, pk->a_query, tmp, &inf)); a_acc = host::hadd(a_acc, H1::load(tmp)); }
-    if (do_b1) { CS_TRY(msm_finish_dyn(ctx, 1, pk->b_g1, tmp, &inf)); b1_acc = host::hadd(b1_acc, H1::load(tmp)); }
+    if (do_a && !ab_done) { CS_TRY(msm_finish_dyn(ctx, 0, pk->a_query, tmp, &inf)); a_acc = host::hadd(a_acc, H1::load(tmp)); }
+    if (do_b1 && !ab_done) { CS_TRY(msm_finish_dyn(ctx, 1, pk->b_g1, tmp, &inf)); b1_acc = host::hadd(b1_acc, H1::load(tmp)); }
     if (do_b2) { CS_TRY(msm_finish_dyn(ctx, 2, pk->b_g2, tmp, &inf)); b2_acc = host::hadd(b2_acc, H2::load(tmp)); }
     if (do_l) CS_TRY(msm_finish_dyn(ctx, 3, pk->l_query, out_l, &inf));
   }
   if (do_h) CS_TRY(msm_finish_dyn(ctx, 4, pk->h_query, out_h, &inf));
-  H1::store(out_a, a_acc);
-  H1::store(out_b1, b1_acc);
+  if (!ab_done) {
+    H1::store(out_a, a_acc);
+    H1::store(out_b1, b1_acc);
+  }
   H2::store(out_b2, b2_acc);
+  if (mid && !ab_done) CS_TRY((*mid)(out_a, out_b1));  // no early window (empty witness): same call, after the fact
   return 0;
 }
 
@@ -374,12 +391,15 @@ int prove_plain_t(cs_ctx* ctx, cs_groth16_pk* pk, const uint64_t* h_pub, const u
   memcpy(rr.l, r, sizeof(rr.l));
   memcpy(ss.l, s, sizeof(ss.l));
   HR rs = rr * ss;
+  // groth16.rs:296-322 with the plain driver: C = s*A + r*B1 - (r s)*delta1 + L + H; the two scalar
+  // multiplications run on the host as soon as A and B1 are there, while the GPU finishes L, B2 and H
+  typename H1::X c = H1::X::inf();
+  std::function<int(const uint64_t*, const uint64_t*)> mid = [&](const uint64_t* pa, const uint64_t* pb1) -> int {
+    c = host::hadd(H1::mul(H1::load(pa), s), H1::mul(H1::load(pb1), r));
+    return 0;
+  };
   CS_TRY((local_phase<Cfg>(ctx, pk, CS_PLAIN, 0, h_pub, h_wit, d_wit, nullptr, nullptr, r, s, a, b1, out_b, l, h,
-                           CS_PART_ALL, nullptr, rs.l, rsd)));
-  // groth16.rs:296-322 with the plain driver: C = s*A + r*B1 - (r s)*delta1 + L + H
-  typename H1::X A = H1::load(a);
-  typename H1::X c = H1::mul(A, s);
-  c = host::hadd(c, H1::mul(H1::load(b1), r));
+                           CS_PART_ALL, nullptr, rs.l, rsd, nullptr, &mid)));
   c = host::hadd(c, host::hneg(H1::load(rsd)));
   c = host::hadd(c, H1::load(l));
   c = host::hadd(c, H1::load(h));
@@ -451,34 +471,39 @@ int rep3_prove_t(cs_ctx* ctx, cs_groth16_pk* pk, cs_net* net0, cs_net* net1, cs_
   };
   uint64_t g_a[G1L], g1_b[G1L], g2_b[G2L], l_acc[G1L], h_acc[G1L], rsd[G1L];
   const unsigned parts = role == 1 ? (CS_PART_A | CS_PART_B1 | CS_PART_L) : CS_PART_ALL;
+  Rep3Net n0(net0), n1(net1);
+  typename H1::X A_open = H1::X::inf(), g_c = H1::X::inf();
+  // ---- network round 1 (groth16.rs:305-308): open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1, run as soon
+  // as THIS party's A and B1 are there -- the GPU is still busy with L, B2 and H, so the round trip and the three
+  // scalar multiplications that follow it are off the critical path.  All sends first (they do not block).
+  std::function<int(const uint64_t*, const uint64_t*)> mid = [&](const uint64_t* pa, const uint64_t* pb1) -> int {
+    CS_SPAN("network round after calc coeff");
+    CS_TRY(n0.send_next(pa, G1L * 8));
+    CS_TRY(n0.send_prev(pa, G1L * 8));
+    CS_TRY(n1.send_next(pb1, G1L * 8));
+    // what can be done before the answers arrive: rhs.a * self.b
+    typename H1::X B1 = H1::load(pb1);
+    typename H1::X t = H1::mul(B1, r_sh + HR::N);
+    uint64_t ga_prev[G1L], ga_next[G1L], g1b_prev[G1L];
+    CS_TRY(n0.recv_prev(ga_prev, G1L * 8));
+    CS_TRY(n0.recv_next(ga_next, G1L * 8));
+    CS_TRY(n1.recv_prev(g1b_prev, G1L * 8));
+    A_open = host::hadd(host::hadd(H1::load(pa), H1::load(ga_prev)), H1::load(ga_next));
+    // scalar_mul_local: b * point + mask, (a, b) * (pa, pb) = pa b.a + pb b.a + pa b.b  (rep3 share product)
+    typename H1::X r_g1_b = host::hadd(host::hadd(H1::mul(host::hadd(B1, H1::load(g1b_prev)), r_sh), t), ec_mask);
+    g_c = host::hadd(H1::mul(A_open, s_sh), r_g1_b);  // groth16.rs:314-317
+    return 0;
+  };
   CS_TRY((local_phase<Cfg>(ctx, pk, CS_REP3, party, h_pub, h_wit, d_wit, nullptr, nullptr, r_sh, s_sh, g_a, g1_b, g2_b,
-                           l_acc, h_acc, parts, role == 1 ? nullptr : &prf, rs.l, rsd, &overlap)));
+                           l_acc, h_acc, parts, role == 1 ? nullptr : &prf, rs.l, rsd, &overlap, &mid)));
   if (role == 1) {
     uint64_t msg[G2L + G1L];
     CS_TRY(cs_net_recv(pair, 1, msg, sizeof(msg)));
     memcpy(g2_b, msg, G2L * 8);
     memcpy(h_acc, msg + G2L, G1L * 8);
   }
-  Rep3Net n0(net0), n1(net1);
-  CS_SPAN("network round after calc coeff + finish - open two points and some adds");
-  // ---- network round 1 (groth16.rs:305-308): open_half_point(g_a) on net0 | scalar_mul(g1_b, r) on net1.
-  // All sends first (they do not block), then the receives.
-  CS_TRY(n0.send_next(g_a, G1L * 8));
-  CS_TRY(n0.send_prev(g_a, G1L * 8));
-  CS_TRY(n1.send_next(g1_b, G1L * 8));
-  // what can be done before the answers arrive: rhs.a * self.b
-  typename H1::X B1 = H1::load(g1_b);
-  typename H1::X t = H1::mul(B1, r_sh + HR::N);
-  uint64_t ga_prev[G1L], ga_next[G1L], g1b_prev[G1L];
-  CS_TRY(n0.recv_prev(ga_prev, G1L * 8));
-  CS_TRY(n0.recv_next(ga_next, G1L * 8));
-  CS_TRY(n1.recv_prev(g1b_prev, G1L * 8));
-  typename H1::X A_open = host::hadd(host::hadd(H1::load(g_a), H1::load(ga_prev)), H1::load(ga_next));
-  // scalar_mul_local: b * point + mask, (a, b) * (pa, pb) = pa b.a + pb b.a + pa b.b  (rep3 share product)
-  typename H1::X r_g1_b = host::hadd(host::hadd(H1::mul(host::hadd(B1, H1::load(g1b_prev)), r_sh), t), ec_mask);
-  // ---- groth16.rs:314-322
-  typename H1::X g_c = H1::mul(A_open, s_sh);
-  g_c = host::hadd(g_c, r_g1_b);
+  CS_SPAN("finish - open two points and some adds");
+  // ---- groth16.rs:318-322
   g_c = host::hadd(g_c, host::hneg(H1::load(rsd)));
   g_c = host::hadd(g_c, H1::load(l_acc));
   g_c = host::hadd(g_c, H1::load(h_acc));
