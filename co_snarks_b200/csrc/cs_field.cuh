@@ -8,6 +8,12 @@
 // mul(): word-serial Montgomery product with the even/odd accumulator split, so every
 // 32x32->64 partial product is one IMAD.WIDE in a single carry chain (no carry-save fix-ups).
 // All results are fully reduced to [0, p), which the exact equality tests in the point formulas need.
+//
+// Attribution: the even/odd-accumulator word-serial product below (mul_n, cmad_n, madc_n_rshift,
+// mad_n_redc and the way mul_inline drives them) follows the structure and helper naming of
+// Supranational's sppark, ff/mont_t.cuh (Copyright Supranational LLC, Apache License 2.0,
+// https://github.com/supranational/sppark); see NOTICE at the repository root.  The product-scanning
+// squaring, the conversions and everything else in this file are this repository's own.
 #pragma once
 #include "cs_prims.cuh"
 
