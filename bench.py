@@ -405,6 +405,21 @@ def run_ours(args):
     launches = ctx.launch_count() - l0
     barrier()
 
+    timeline = None
+    if args.timeline and rank == 0:
+        ctx.msm_profile(True)
+        tls = []
+        for _ in range(3):
+            pk.prove_plain_device(pub, d_wit, r_m, s_m)
+            tls.append(ctx.msm_timeline_ms())
+        ctx.msm_profile(False)
+        names = ["A", "B1", "B2", "L", "H"]
+        timeline = {"order": "ms after the fork: start, digits done, sort done, accumulate done, fold done, reduce done",
+                    "stream_prio": os.environ.get("CS_STREAM_PRIO", "")}
+        for w, nm in enumerate(names):
+            timeline[nm] = [round(x, 3) for x in tls[-1][w]]
+        print("timeline", json.dumps(timeline), file=sys.stderr, flush=True)
+
     # ---- e2e: host buffers through the C ABI, wall clock between synchronisations
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -526,7 +541,8 @@ def run_ours(args):
                     "gmodmul_s": n * lg / 2 / (ntt_avg * 1e-3) / 1e9,
                     "int_pipe_frac": n * lg / 2 / (ntt_avg * 1e-3) / 1e9 / gmul_peak,
                     "note": "n/2 log n butterflies of one Montgomery product each: integer-pipe bound like the MSM"},
-            "cpu_baseline": cpu_baseline(args) if world == 1 else None,  # rank 0 at N = 1 only
+            "cpu_baseline": cpu_baseline(args) if (world == 1 and not args.no_cpu_baseline) else None,  # rank 0 at N = 1 only
+            **({"timeline_ms": timeline} if timeline else {}),
             "rep3": rep3 if rep3 is not None else ("skipped (--no-rep3)" if args.no_rep3 else "needs 1 or >= 3 GPUs"),
         }
         if rep3_split is not None:
@@ -671,6 +687,9 @@ def main():
     ap.add_argument("--fast-setup", action="store_true", help="random (invalid) key: skips the host-side QAP setup")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-rep3", action="store_true", help="skip the Rep3 block of the default run")
+    ap.add_argument("--timeline", action="store_true",
+                    help="after the timed region: one more proof with stage events, reported as timeline_ms (diagnostic)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="diagnostic runs: skip the CPU leg")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

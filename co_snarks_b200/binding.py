@@ -32,6 +32,13 @@ class Rep3Prf(C.Structure):
                 ("word_pos2", C.c_uint64), ("rounds", C.c_uint)]
 
 
+ARITH_POLY_NAMES = ("w_l", "w_r", "w_o", "w_4", "w_l_shift", "w_4_shift", "q_m", "q_l", "q_r", "q_o", "q_4", "q_c", "q_arith")
+
+
+class HonkArithPolys(C.Structure):  # cs_honk_arith_polys: device pointers
+    _fields_ = [(n, C.c_void_p) for n in ARITH_POLY_NAMES]
+
+
 class KeyDesc(C.Structure):
     _fields_ = [
         ("curve", C.c_int),
@@ -100,6 +107,7 @@ SIGNATURES = {
     "cs_net_peer_connect_local": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "cs_net_send": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "cs_net_recv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
+    "cs_net_sendrecv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t]),
     "cs_net_bytes_sent": (C.c_uint64, [C.c_void_p]),
     "cs_net_free": (None, [C.c_void_p]),
     "cs_rep3_state_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
@@ -133,6 +141,11 @@ SIGNATURES = {
     "cs_msm_rep3_shares": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "cs_msm_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "cs_msm_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cs_msm_timeline_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "cs_sumcheck_gate_separator": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p]),
+    "cs_sumcheck_fold": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, C.c_void_p]),
+    "cs_sumcheck_arith_round": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
     "cs_fixed_base_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "cs_domain_create": (C.c_int, [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.POINTER(C.c_void_p)]),
     "cs_domain_free": (None, [C.c_void_p]),
@@ -369,6 +382,12 @@ class Context:
         self._check(self.lib.cs_msm_stage_ms(self.h, arr))
         return [float(x) for x in arr]
 
+    def msm_timeline_ms(self):
+        """[5 workspaces][6 stage boundaries] in ms after the last fork (Groth16: A, B1, B2, L, H); -1 = no event."""
+        arr = (C.c_float * 30)()
+        self._check(self.lib.cs_msm_timeline_ms(self.h, arr))
+        return [[float(arr[w * 6 + i]) for i in range(6)] for w in range(5)]
+
     def fixed_base_mul(self, curve, group, base_mont, scalars, montgomery=True):
         scalars = np.ascontiguousarray(scalars, dtype=np.uint64)
         base_mont = np.ascontiguousarray(base_mont, dtype=np.uint64)
@@ -422,6 +441,27 @@ class Context:
         ln = (C.c_size_t * k)(*lens)
         self._check(self.lib.cs_honk_commit_batch(self.h, crs.h, kind, ptrs, ln, k, _ptr(out)))
         return out
+
+    # ---- UltraHonk sumcheck kernels (csrc/cs_sumcheck.cuh)
+    def sumcheck_gate_separator(self, curve, betas_mont, d_out):
+        b = np.ascontiguousarray(betas_mont, dtype=np.uint64).reshape(-1, 4)
+        self._check(self.lib.cs_sumcheck_gate_separator(self.h, curve, _ptr(b) if b.shape[0] else None, b.shape[0], _ptr(d_out)))
+
+    def sumcheck_fold(self, curve, d_in, d_out, shared, length, challenge_mont):
+        k = len(d_in)
+        pin = (C.c_void_p * k)(*[C.c_void_p(p) for p in d_in])
+        pout = (C.c_void_p * k)(*[C.c_void_p(p) for p in d_out])
+        u = np.ascontiguousarray(challenge_mont, dtype=np.uint64).reshape(4)
+        self._check(self.lib.cs_sumcheck_fold(self.h, curve, pin, pout, k, int(shared), length, _ptr(u)))
+
+    def sumcheck_arith_round(self, curve, kind, party, d_polys, round_size, d_beta_products, periodicity, prf=None):
+        """d_polys: name -> device pointer (ARITH_POLY_NAMES).  -> (r0 [6, 4], r1 [5, 4] plain or [5, 2, 4] Rep3)"""
+        st = HonkArithPolys(*[C.c_void_p(d_polys[n]) for n in ARITH_POLY_NAMES])
+        r0 = np.zeros((6, 4), dtype=np.uint64)
+        r1 = np.zeros((5, 2, 4) if kind == CS_REP3 else (5, 4), dtype=np.uint64)
+        self._check(self.lib.cs_sumcheck_arith_round(self.h, curve, kind, party, C.byref(st), round_size, _ptr(d_beta_products),
+                                                     periodicity, C.byref(prf) if prf is not None else None, _ptr(r0), _ptr(r1)))
+        return r0, r1
 
     def ipc_export(self, d_ptr):
         h = np.zeros(64, dtype=np.uint8)
@@ -894,6 +934,13 @@ class Net:
     def recv(self, frm, nbytes):
         buf = C.create_string_buffer(nbytes)
         self._check(self.lib.cs_net_recv(self.h, frm, buf, nbytes))
+        return buf.raw
+
+    def sendrecv(self, to, data, frm, nbytes):
+        """Both directions advance together: safe for exchanges larger than the mailbox credit window."""
+        b = bytes(data)
+        buf = C.create_string_buffer(nbytes)
+        self._check(self.lib.cs_net_sendrecv(self.h, to, b, len(b), frm, buf, nbytes))
         return buf.raw
 
     @property

@@ -24,6 +24,10 @@ std::atomic<uint64_t>& launch_counter() {
 }
 
 int ctx_fork(cs_ctx* ctx, int nside) {
+  if (ctx->msm_ws[0].profile) {
+    if (!ctx->ev_t0) CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_t0, 0));
+    CS_CUDA(cudaEventRecord(ctx->ev_t0, ctx->stream));
+  }
   CS_CUDA(cudaEventRecord(ctx->ev_fork, ctx->stream));
   for (int i = 0; i < nside; i++) CS_CUDA(cudaStreamWaitEvent(ctx->side[i], ctx->ev_fork, 0));
   return 0;
@@ -74,16 +78,27 @@ int cs_ctx_create(int device, void* stream, cs_ctx** out) {
   CS_CUDA(cudaSetDevice(device));
   cs_ctx* ctx = new cs_ctx();
   ctx->device = device;
+  // Stream priorities (CUDA: lower number = served first).  The short, latency-bound kernels (digit sort, folds,
+  // bucket reduction, NTT passes) run on higher-priority streams than the full-GPU MSM accumulation grids, so that
+  // they are not queued behind every accumulation launched before them.  CS_PRIO="side,acc,wm" overrides
+  // (default "-2,0,-3"); CS_MSM_SPLIT=0 keeps each MSM on a single stream.
+  int prio_side = -2, prio_acc = 0, prio_wm = -3;
+  if (const char* e = getenv("CS_PRIO")) sscanf(e, "%d,%d,%d", &prio_side, &prio_acc, &prio_wm);
+  const char* split_env = getenv("CS_MSM_SPLIT");
+  const bool split = !(split_env && atoi(split_env) == 0);
   if (stream) {
     ctx->stream = (cudaStream_t)stream;
   } else {
-    CS_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CS_CUDA(cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, prio_side));
     ctx->own_stream = true;
   }
   for (int i = 0; i < CS_NSIDE; i++) {
-    CS_CUDA(cudaStreamCreateWithFlags(&ctx->side[i], cudaStreamNonBlocking));
+    CS_CUDA(cudaStreamCreateWithPriority(&ctx->side[i], cudaStreamNonBlocking, prio_side));
+    if (split) CS_CUDA(cudaStreamCreateWithPriority(&ctx->acc[i], cudaStreamNonBlocking, prio_acc));
     CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_side[i], cudaEventDisableTiming));
   }
+  CS_CUDA(cudaStreamCreateWithPriority(&ctx->wm, cudaStreamNonBlocking, prio_wm));
+  CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_wm, cudaEventDisableTiming));
   CS_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
   CS_TRY(ntt_smem_optin<Bn254Fr>());
 #if defined(CS_ENABLE_BLS12_381)
@@ -100,9 +115,13 @@ void cs_ctx_destroy(cs_ctx* ctx) {
   for (int i = 0; i < CS_NSIDE; i++) {
     ctx->msm_ws[i].release();
     if (ctx->side[i]) cudaStreamDestroy(ctx->side[i]);
+    if (ctx->acc[i]) cudaStreamDestroy(ctx->acc[i]);
     if (ctx->ev_side[i]) cudaEventDestroy(ctx->ev_side[i]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->wm) cudaStreamDestroy(ctx->wm);
+  if (ctx->ev_wm) cudaEventDestroy(ctx->ev_wm);
+  if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   ctx->io.release();
   ctx->prf_keys.release();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -195,7 +214,7 @@ int msm_enqueue_t(cs_ctx* ctx, int slot, cudaStream_t st, const cs_bases* b, siz
   typedef typename GroupOf<Cfg, G>::F F;
   return msm_enqueue<F, typename Cfg::FrP>(ctx->msm_ws[slot], b->table.as<Affine<F>>(), b->infmask.as<uint32_t>(), (uint32_t)b->n, b->sh,
                                            (uint32_t)offset, d_scalars, sstride, (uint32_t)n, mont, st,
-                                           sort_slot >= 0 ? &ctx->msm_ws[sort_slot] : nullptr, b->m260);
+                                           sort_slot >= 0 ? &ctx->msm_ws[sort_slot] : nullptr, b->m260, ctx->acc[slot]);
 }
 
 // After the stream has drained: XYZZ (pinned) -> affine on the host.
@@ -338,6 +357,25 @@ int cs_msm_stage_ms(cs_ctx* ctx, float* out_ms) {
     CS_CUDA(cudaEventElapsedTime(&out_ms[i], ws.ev[i], ws.ev[i + 1]));
 #endif
   }
+  return 0;
+}
+
+int cs_msm_timeline_ms(cs_ctx* ctx, float* out_ms) {
+  if (!ctx || !out_ms) return fail(CS_ERR_ARG, "cs_msm_timeline_ms: NULL argument");
+  if (!ctx->msm_ws[0].profile || !ctx->ev_t0) return fail(CS_ERR_STATE, "cs_msm_timeline_ms: no profiled fork has run");
+  CS_CUDA(cudaSetDevice(ctx->device));
+  CS_CUDA(cudaDeviceSynchronize());
+  for (int w = 0; w < CS_NSIDE; w++)
+    for (int i = 0; i <= MSM_NSTAGE; i++) {
+      float v = -1.f;
+#if !defined(CS_EMU)
+      if (ctx->msm_ws[w].ev[i] && cudaEventElapsedTime(&v, ctx->ev_t0, ctx->msm_ws[w].ev[i]) != cudaSuccess) {
+        v = -1.f;
+        cudaGetLastError();
+      }
+#endif
+      out_ms[w * (MSM_NSTAGE + 1) + i] = v;
+    }
   return 0;
 }
 

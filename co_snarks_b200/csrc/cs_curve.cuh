@@ -173,6 +173,34 @@ CS_D void padd(Xyzz<F>& acc, const Xyzz<F>& q) {
   acc.zzz = acc.zzz * q.zzz * PPP;
 }
 
+// A point held by the lane `delta` above this one (warp shuffle, whole warp takes part); lanes whose source falls
+// outside the warp get their own value back, as __shfl_down_sync does.
+template <class P>
+CS_D Fp<P> shfl_down(const Fp<P>& a, unsigned delta) {
+  Fp<P> r;
+  CS_UNROLL
+  for (int i = 0; i < P::N; i++) r.l[i] = __shfl_down_sync(0xffffffffu, a.l[i], delta);
+  return r;
+}
+template <class P>
+CS_D Fp2<P> shfl_down(const Fp2<P>& a, unsigned delta) {
+  Fp2<P> r;
+  r.c0 = shfl_down(a.c0, delta);
+  r.c1 = shfl_down(a.c1, delta);
+  return r;
+}
+template <class F>
+CS_D Xyzz<F> shfl_down(const Xyzz<F>& p, unsigned delta) {
+  Xyzz<F> r;
+#if defined(CS_EMU)  // test emulation: one block-wide exchange for the whole point instead of one per 32-bit word
+  cs::emu::shfl_bytes(&p, &r, sizeof(r), 1, delta);
+  return r;
+#endif
+  r.x = shfl_down(p.x, delta); r.y = shfl_down(p.y, delta);
+  r.zz = shfl_down(p.zz, delta); r.zzz = shfl_down(p.zzz, delta);
+  return r;
+}
+
 // XYZZ -> affine (one inversion); off the per-proof path
 template <class F>
 CS_DN Affine<F> to_affine(const Xyzz<F>& p) {

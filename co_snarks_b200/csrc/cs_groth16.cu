@@ -270,20 +270,15 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
              do_l = parts & CS_PART_L, do_h = parts & CS_PART_H;
   CS_CUDA(cudaSetDevice(ctx->device));
   CS_TRY(upload_inputs(ctx, pk, kind, h_pub, h_wit, do_h ? h_m1 : nullptr, do_h ? h_m2 : nullptr));
-  // fork: A, B1, B2, L need only the witness; the witness map + H run on the main stream.
+  // fork: A, B1, B2, L need only the witness.  The witness map -> H chain is the longest dependency chain of the proof
+  // (6-10 NTTs, then a full MSM), so it is enqueued FIRST and on the highest-priority stream: its passes interleave
+  // with the other MSMs' accumulation grids instead of queueing behind all of them (profiles/r2_prio_ab.log: before,
+  // H started 14.8 ms into an 18.9 ms proof, after the four side MSMs had drained).
   CS_TRY(ctx_fork(ctx, 4));
+  cudaStream_t wm = ctx->wm;
+  CS_CUDA(cudaStreamWaitEvent(wm, ctx->ev_fork, 0));
   // witness either uploaded from the host just above, or already resident in HBM (d_wit_in)
   const uint32_t* wit = d_wit_in ? reinterpret_cast<const uint32_t*>(d_wit_in) : pk->d_wit.as<uint32_t>();
-  if (have_aux) {
-    // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
-    CS_SPAN("compute A, B/G1, B/G2 in create proof with assignment + msm l_query");
-    if (do_a) CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
-    if (do_b1) CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
-    if (do_b2)
-      CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1,
-                             (do_b1 && pk->share_b_sort) ? 1 : -1));
-    if (do_l) CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
-  }
   if (do_h) {
     bool have_m1 = h_m1 != nullptr, have_m2 = h_m2 != nullptr;
     if (prf && kind == CS_REP3) {
@@ -294,21 +289,33 @@ int local_phase(cs_ctx* ctx, cs_groth16_pk* pk, int kind, int party, const uint6
       CS_TRY(pk->d_m1.reserve(n * 32));
       CS_TRY(pk->d_m2.reserve(n * 32));
       CS_TRY(ctx->prf_keys.reserve(64));
-      CS_CUDA(cudaMemcpyAsync(ctx->prf_keys.p, prf->seed1, 32, cudaMemcpyHostToDevice, ctx->stream));
-      CS_CUDA(cudaMemcpyAsync((char*)ctx->prf_keys.p + 32, prf->seed2, 32, cudaMemcpyHostToDevice, ctx->stream));
-      CS_LAUNCH(k_rep3_masks<FrP>, ceil_div(n, 128), 128, 0, ctx->stream, ctx->prf_keys.as<uint32_t>(), prf->word_pos1,
+      CS_CUDA(cudaMemcpyAsync(ctx->prf_keys.p, prf->seed1, 32, cudaMemcpyHostToDevice, wm));
+      CS_CUDA(cudaMemcpyAsync((char*)ctx->prf_keys.p + 32, prf->seed2, 32, cudaMemcpyHostToDevice, wm));
+      CS_LAUNCH(k_rep3_masks<FrP>, ceil_div(n, 128), 128, 0, wm, ctx->prf_keys.as<uint32_t>(), prf->word_pos1,
                 prf->word_pos2, prf->rounds, n, pk->d_m1.as<uint32_t>());
-      CS_LAUNCH(k_rep3_masks<FrP>, ceil_div(n, 128), 128, 0, ctx->stream, ctx->prf_keys.as<uint32_t>(),
+      CS_LAUNCH(k_rep3_masks<FrP>, ceil_div(n, 128), 128, 0, wm, ctx->prf_keys.as<uint32_t>(),
                 prf->word_pos1 + 8 * n, prf->word_pos2 + 8 * n, prf->rounds, n, pk->d_m2.as<uint32_t>());
       have_m1 = have_m2 = true;
     }
-    CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, have_m1, have_m2, ctx->stream)));
+    CS_TRY((witness_map_device<Cfg>(ctx, pk, kind, party, wit, have_m1, have_m2, wm)));
     {
       CS_SPAN("msm h_query");
-      CS_TRY(msm_enqueue_dyn(ctx, 4, ctx->stream, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
+      CS_TRY(msm_enqueue_dyn(ctx, 4, wm, pk->h_query, 0, pk->d_c.as<uint32_t>(), 1, pk->n, 1));
     }
   }
+  if (have_aux) {
+    // query[1 + pub_len ..] = query[ni ..]  (groth16.rs:193)
+    CS_SPAN("compute A, B/G1, B/G2 in create proof with assignment + msm l_query");
+    if (do_a) CS_TRY(msm_enqueue_dyn(ctx, 0, ctx->side[0], pk->a_query, pk->ni, wit, batch, pk->nw, 1));
+    if (do_b1) CS_TRY(msm_enqueue_dyn(ctx, 1, ctx->side[1], pk->b_g1, pk->ni, wit, batch, pk->nw, 1));
+    if (do_b2)
+      CS_TRY(msm_enqueue_dyn(ctx, 2, ctx->side[2], pk->b_g2, pk->ni, wit, batch, pk->nw, 1,
+                             (do_b1 && pk->share_b_sort) ? 1 : -1));
+    if (do_l) CS_TRY(msm_enqueue_dyn(ctx, 3, ctx->side[3], pk->l_query, 0, wit, batch, pk->nw, 1));
+  }
   CS_TRY(ctx_join(ctx, 4));
+  CS_CUDA(cudaEventRecord(ctx->ev_wm, wm));
+  CS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_wm, 0));
 
   // ---- host work overlapped with the GPU: scalar_mul_public_point_hs + public parts (groth16.rs:232-276)
   const size_t g1l = 2 * H1::HF::N, g2l = 4 * H1::HF::N;

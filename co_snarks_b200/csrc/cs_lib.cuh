@@ -52,7 +52,11 @@ struct cs_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   cudaStream_t side[cs::CS_NSIDE] = {};
+  cudaStream_t acc[cs::CS_NSIDE] = {};   // lower priority: the MSM accumulation kernels (see msm_enqueue's st_acc)
+  cudaStream_t wm = nullptr;             // highest priority: witness map -> H MSM chain of the Groth16 prover
+  cudaEvent_t ev_wm = nullptr;
   cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_t0 = nullptr;  // timing event at the last fork, recorded only while MSM profiling is on (cs_msm_timeline_ms)
   cudaEvent_t ev_side[cs::CS_NSIDE] = {};
   cs::MsmWorkspace msm_ws[cs::CS_NSIDE];
   cs::DevBuf io;  // staging for host-buffer convenience calls

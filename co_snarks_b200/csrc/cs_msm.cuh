@@ -86,46 +86,86 @@ CS_GLOBAL void k_msm_infmask(const Affine<F>* __restrict__ table, uint32_t n, ui
   mask[wd] = m;
 }
 
-// --------------------------------------------------------------------------- scans (one block)
+// --------------------------------------------------------------------------- scans
 // From count[0..B]: start = exclusive scan of count; ns0[b] = ceil(count[b]/S), ns1 = ceil(ns0/S),
 // ns2 = ceil(ns1/S) (three fold levels keep the last, serial, per-bucket fold short even when most scalars
 // share one digit: 2^24 entries in ONE bucket leave 512 partials); sstart0 / sstart1 / sstart2 = exclusive scans.  Arrays have B + 2 entries (last = total).
-static CS_GLOBAL void k_msm_scan(const uint32_t* __restrict__ count, uint32_t nb1 /* B + 1 */, uint32_t MSM_SLICE,
-                          uint32_t* __restrict__ start, uint32_t* __restrict__ sstart0,
-                          uint32_t* __restrict__ sstart1, uint32_t* __restrict__ sstart2) {
-  __shared__ uint32_t sm[4][1024];
-  const uint32_t T = blockDim.x, t = threadIdx.x;
-  const uint32_t per = (nb1 + T - 1) / T;
-  const uint32_t lo = t * per, hi = (lo + per < nb1) ? lo + per : nb1;
-  uint32_t a = 0, b = 0, cc = 0, dd = 0;
-  for (uint32_t k = lo; k < hi; k++) {
-    uint32_t cnt = k ? count[k] : 0;  // bucket 0 (zero digits) is dropped
-    uint32_t n0 = (cnt + MSM_SLICE - 1) / MSM_SLICE;
-    uint32_t n1 = (n0 + MSM_SLICE - 1) / MSM_SLICE;
-    uint32_t n2 = (n1 + MSM_SLICE - 1) / MSM_SLICE;
-    a += cnt; b += n0; cc += n1; dd += n2;
+// Two launches over ceil((B + 1) / 1024) blocks: coalesced block-local scans (warp shuffles, then the warp totals by
+// the first warp) that leave each block's totals in aux[block][4], then the block offsets are added.
+constexpr unsigned MSM_SCAN_T = 1024;
+constexpr unsigned MSM_SCAN_MAX_BLOCKS = 1024;  // 2^20 buckets
+CS_D void msm_scan_terms(const uint32_t* __restrict__ count, uint32_t k, uint32_t nb1, uint32_t S, uint32_t* v) {
+  uint32_t cnt = (k && k < nb1) ? count[k] : 0;  // bucket 0 (zero digits) is dropped
+  uint32_t n0 = (cnt + S - 1) / S;
+  uint32_t n1 = (n0 + S - 1) / S;
+  v[0] = cnt; v[1] = n0; v[2] = n1; v[3] = (n1 + S - 1) / S;
+}
+static CS_GLOBAL void k_msm_scan1(const uint32_t* __restrict__ count, uint32_t nb1 /* B + 1 */, uint32_t S,
+                                  uint32_t* __restrict__ start, uint32_t* __restrict__ sstart0,
+                                  uint32_t* __restrict__ sstart1, uint32_t* __restrict__ sstart2, uint32_t* __restrict__ aux) {
+  __shared__ uint32_t sm[4][32];
+  const uint32_t t = threadIdx.x, lane = t & 31, wid = t >> 5, nwarp = blockDim.x >> 5;
+  const uint32_t k = blockIdx.x * blockDim.x + t;
+  uint32_t v[4], inc[4];
+  msm_scan_terms(count, k, nb1, S, v);
+  CS_UNROLL
+  for (int q = 0; q < 4; q++) {
+    uint32_t x = v[q];
+    CS_UNROLL
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    inc[q] = x;
+    if (lane == 31) sm[q][wid] = x;
   }
-  sm[0][t] = a; sm[1][t] = b; sm[2][t] = cc; sm[3][t] = dd;
   __syncthreads();
-  if (t < 4) {
-    uint32_t run = 0;
-    for (uint32_t k = 0; k < T; k++) {
-      uint32_t v = sm[t][k];
-      sm[t][k] = run;
-      run += v;
+  uint32_t w[4], x[4];
+  CS_UNROLL
+  for (int q = 0; q < 4; q++) {
+    w[q] = (wid == 0 && lane < nwarp) ? sm[q][lane] : 0;
+    x[q] = w[q];
+    CS_UNROLL
+    for (uint32_t d = 1; d < 32; d <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x[q], d);
+      if (lane >= d) x[q] += y;
     }
   }
   __syncthreads();
-  a = sm[0][t]; b = sm[1][t]; cc = sm[2][t]; dd = sm[3][t];
-  for (uint32_t k = lo; k < hi; k++) {
-    uint32_t cnt = k ? count[k] : 0;
-    uint32_t n0 = (cnt + MSM_SLICE - 1) / MSM_SLICE;
-    uint32_t n1 = (n0 + MSM_SLICE - 1) / MSM_SLICE;
-    uint32_t n2 = (n1 + MSM_SLICE - 1) / MSM_SLICE;
-    start[k] = a; sstart0[k] = b; sstart1[k] = cc; sstart2[k] = dd;
-    a += cnt; b += n0; cc += n1; dd += n2;
+  if (wid == 0 && lane < nwarp) {
+    CS_UNROLL
+    for (int q = 0; q < 4; q++) sm[q][lane] = x[q] - w[q];  // exclusive prefix of the warp totals
+    if (lane == nwarp - 1) {
+      CS_UNROLL
+      for (int q = 0; q < 4; q++) aux[blockIdx.x * 4 + q] = x[q];  // block total
+    }
   }
-  if (hi == nb1 && lo < hi) { start[nb1] = a; sstart0[nb1] = b; sstart1[nb1] = cc; sstart2[nb1] = dd; }
+  __syncthreads();
+  if (k < nb1) {
+    start[k] = sm[0][wid] + inc[0] - v[0];
+    sstart0[k] = sm[1][wid] + inc[1] - v[1];
+    sstart1[k] = sm[2][wid] + inc[2] - v[2];
+    sstart2[k] = sm[3][wid] + inc[3] - v[3];
+  }
+}
+static CS_GLOBAL void k_msm_scan2(const uint32_t* __restrict__ count, uint32_t nb1, uint32_t S,
+                                  uint32_t* __restrict__ start, uint32_t* __restrict__ sstart0,
+                                  uint32_t* __restrict__ sstart1, uint32_t* __restrict__ sstart2,
+                                  const uint32_t* __restrict__ aux) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nb1) return;
+  uint32_t off[4] = {0, 0, 0, 0};
+  for (uint32_t b = 0; b < blockIdx.x; b++) {
+    CS_UNROLL
+    for (int q = 0; q < 4; q++) off[q] += aux[b * 4 + q];
+  }
+  uint32_t a = start[k] + off[0], b0 = sstart0[k] + off[1], b1 = sstart1[k] + off[2], b2 = sstart2[k] + off[3];
+  start[k] = a; sstart0[k] = b0; sstart1[k] = b1; sstart2[k] = b2;
+  if (k == nb1 - 1) {
+    uint32_t v[4];
+    msm_scan_terms(count, k, nb1, S, v);
+    start[nb1] = a + v[0]; sstart0[nb1] = b0 + v[1]; sstart1[nb1] = b1 + v[2]; sstart2[nb1] = b2 + v[3];
+  }
 }
 
 // --------------------------------------------------------------------------- scatter
@@ -464,6 +504,7 @@ struct MsmWorkspace {
   cudaEvent_t ev[MSM_NSTAGE + 1] = {};
   cudaEvent_t sorted_ev = nullptr;  // recorded once the sorted entries / slice order of this MSM are final
   bool sorted_ev_made = false, sorted_once = false;
+  cudaEvent_t acc_in = nullptr, acc_out = nullptr;  // hand-off to / from the accumulation stream (msm_enqueue's st_acc)
   int mark(int i, cudaStream_t st) {
     if (!profile) return 0;
     if (!ev[i]) CS_CUDA(cudaEventCreateWithFlags(&ev[i], 0));
@@ -476,6 +517,9 @@ struct MsmWorkspace {
       ev[i] = nullptr;
     }
     if (sorted_ev_made) cudaEventDestroy(sorted_ev);
+    if (acc_in) cudaEventDestroy(acc_in);
+    if (acc_out) cudaEventDestroy(acc_out);
+    acc_in = acc_out = nullptr;
     sorted_ev = nullptr;
     sorted_ev_made = sorted_once = false;
     dig.release(); sorted.release(); meta.release(); part0.release(); part1.release(); part2.release();
@@ -498,11 +542,15 @@ int msm_accum0_f52(const Affine<F>* table, const uint32_t* sorted, const uint32_
 // geometry (nbases, offset, n, window) and the same infinity pattern -- Groth16's B1 / B2 pair.  Its sorted
 // entries and slice order are reused (they index table slots, not points), so this MSM starts at the
 // accumulation; `st` waits for that workspace's sort to finish.
+// st_acc (optional): a second, LOWER-priority stream for the accumulation kernel alone.  When several MSMs share the
+// GPU, the block scheduler serves equal-priority grids in launch order, so the short sort / fold / reduce kernels of
+// one MSM queue behind the full-GPU accumulation grids of all the others (measured: folds of an MSM finished at 3 ms
+// ran at 13 ms, profiles/r2_prio_ab.log); with the accumulation on a lower-priority stream they slip in between.
 template <class F, class FrP>
 int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmask, uint32_t nbases, MsmShape sh,
                 uint32_t offset,
                 const uint32_t* d_scalars, uint32_t sstride, uint32_t n, int mont, cudaStream_t st,
-                MsmWorkspace* sort_from = nullptr, bool table_m260 = false) {
+                MsmWorkspace* sort_from = nullptr, bool table_m260 = false, cudaStream_t st_acc = nullptr) {
   const uint32_t nb1 = sh.B + 1;
   const size_t nent = (size_t)sh.W * n;
   if (nent >= (1ull << 31) || (size_t)sh.W * nbases >= (1ull << 31))
@@ -512,8 +560,8 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   const size_t max_s1 = max_s0 / S + nb1;
   const size_t max_s2 = max_s1 / S + nb1;
   MsmWorkspace& so = sort_from ? *sort_from : ws;  // owner of the sort buffers
-  // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1] sstart2[nb1+1]
-  const size_t meta_words = 2 * (size_t)nb1 + 4 * ((size_t)nb1 + 1);
+  // meta: count[nb1] cursor[nb1] | start[nb1+1] sstart0[nb1+1] sstart1[nb1+1] sstart2[nb1+1] | aux[4 * scan blocks]
+  const size_t meta_words = 2 * (size_t)nb1 + 4 * ((size_t)nb1 + 1) + 4 * MSM_SCAN_MAX_BLOCKS;  // + the scan's block totals
   if (!sort_from) {
     CS_TRY(ws.dig.reserve(nent * 4));
     CS_TRY(ws.sorted.reserve(nent * 4));
@@ -563,7 +611,13 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
     CS_LAUNCH(k_msm_digits<FrP>, ceil_div(n, 256), 256, 0, st, d_scalars, sstride, n, mont, sh.c, sh.W, infmask, offset,
               ws.dig.as<uint32_t>(), count);
     CS_TRY(ws.mark(1, st));
-    CS_LAUNCH_SYNC(k_msm_scan, 1, 1024, 0, st, count, nb1, S, start, sstart0, sstart1, sstart2);
+    {
+      const uint32_t sb = ceil_div(nb1, MSM_SCAN_T);
+      if (sb > MSM_SCAN_MAX_BLOCKS) return fail(-3, "msm: %u buckets exceed the scan's limit", sh.B);
+      uint32_t* aux = sstart2 + nb1 + 1;
+      CS_LAUNCH_SYNC(k_msm_scan1, sb, MSM_SCAN_T, 0, st, count, nb1, S, start, sstart0, sstart1, sstart2, aux);
+      CS_LAUNCH(k_msm_scan2, sb, MSM_SCAN_T, 0, st, count, nb1, S, start, sstart0, sstart1, sstart2, aux);
+    }
     CS_LAUNCH(k_msm_scatter, dim3(ceil_div(n, 256), sh.W), 256, 0, st, ws.dig.as<uint32_t>(), n, nbases,
               offset, start, cursor, ws.sorted.as<uint32_t>());
     CS_LAUNCH_SYNC(k_msm_slice_hist, ob, MSM_ORDER_BLOCK, 0, st, count, sstart0, nb1, S, slice_len, slice_bkt, block_hist);
@@ -583,6 +637,16 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
     ws.sorted_once = true;
   }
   CS_TRY(ws.mark(2, st));
+  cudaStream_t st_main = st;
+  if (st_acc) {
+    if (!ws.acc_in) {
+      CS_CUDA(cudaEventCreateWithFlags(&ws.acc_in, cudaEventDisableTiming));
+      CS_CUDA(cudaEventCreateWithFlags(&ws.acc_out, cudaEventDisableTiming));
+    }
+    CS_CUDA(cudaEventRecord(ws.acc_in, st));
+    CS_CUDA(cudaStreamWaitEvent(st_acc, ws.acc_in, 0));
+    st = st_acc;
+  }
   {
     // resident blocks per SM (register cap) -- tuned on B200, overridable for experiments
     static int minb_env = -1;
@@ -604,6 +668,11 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
     }
 #undef CS_ACC0
     }
+  }
+  if (st_acc) {
+    CS_CUDA(cudaEventRecord(ws.acc_out, st_acc));
+    st = st_main;
+    CS_CUDA(cudaStreamWaitEvent(st, ws.acc_out, 0));
   }
   CS_TRY(ws.mark(3, st));
   CS_LAUNCH(k_msm_accum1<F>, ceil_div(max_s1, 128), 128, 0, st, ws.part0.as<Xyzz<F>>(), sstart0, sstart1,

@@ -39,67 +39,107 @@ constexpr cudaMemcpyKind kAny = cudaMemcpyHostToDevice;  // the emulation's memc
 constexpr cudaMemcpyKind kAny = cudaMemcpyDefault;
 #endif
 
-int peer_send(cs_net* net, int to, const uint8_t* data, size_t bytes) {
+// One chunk towards `to` if a credit is free: 1 = sent, 0 = would block, < 0 = error.
+int try_send_chunk(cs_net* net, int to, const uint8_t* data, size_t bytes, size_t& off) {
   NetChannel* dst = net->peer_box[to] + net->id;  // my channel inside the receiver's mailbox
-  size_t off = 0;
-  do {
-    const uint64_t c = net->send_seq[to];
-    // credit: at most NET_SLOTS chunks in flight towards `to`
-    if (c - net->acked[to] >= NET_SLOTS) {
-      Deadline dl;
-      for (;;) {
-        CS_CUDA(cudaMemcpyAsync(&net->h_ack[net->n + to], &net->d_box[to].ack, 8, cudaMemcpyDeviceToHost, net->st));
-        CS_CUDA(cudaStreamSynchronize(net->st));
-        net->acked[to] = net->h_ack[net->n + to];
-        if (c - net->acked[to] < NET_SLOTS) break;
-        if (dl.expired()) return fail(CS_ERR_STATE, "cs_net: party %d timed out waiting for credits from party %d", net->id, to);
-      }
-    }
-    const size_t len = bytes - off < NET_CHUNK ? bytes - off : NET_CHUNK;
-    NetSlot* s = &dst->slot[c % NET_SLOTS];
-    if (len) memcpy(net->h_send->payload, data + off, len);
-    net->h_send->seq = c + 1;
-    net->h_send->len = len;
-    // payload first, then the header that publishes it: two stream-ordered copies into the peer's HBM
-    if (len) CS_CUDA(cudaMemcpyAsync(s->payload, net->h_send->payload, len, kAny, net->st));
-    CS_CUDA(cudaMemcpyAsync(&s->seq, &net->h_send->seq, 16, kAny, net->st));
+  const uint64_t c = net->send_seq[to];
+  // credit: at most NET_SLOTS chunks in flight towards `to`
+  if (c - net->acked[to] >= NET_SLOTS) {
+    CS_CUDA(cudaMemcpyAsync(&net->h_ack[net->n + to], &net->d_box[to].ack, 8, cudaMemcpyDeviceToHost, net->st));
     CS_CUDA(cudaStreamSynchronize(net->st));
-    net->send_seq[to] = c + 1;
-    off += len;
-  } while (off < bytes);
+    net->acked[to] = net->h_ack[net->n + to];
+    if (c - net->acked[to] >= NET_SLOTS) return 0;
+  }
+  const size_t len = bytes - off < NET_CHUNK ? bytes - off : NET_CHUNK;
+  NetSlot* s = &dst->slot[c % NET_SLOTS];
+  if (len) memcpy(net->h_send->payload, data + off, len);
+  net->h_send->seq = c + 1;
+  net->h_send->len = len;
+  // payload first, then the header that publishes it: two stream-ordered copies into the peer's HBM
+  if (len) CS_CUDA(cudaMemcpyAsync(s->payload, net->h_send->payload, len, kAny, net->st));
+  CS_CUDA(cudaMemcpyAsync(&s->seq, &net->h_send->seq, 16, kAny, net->st));
+  CS_CUDA(cudaStreamSynchronize(net->st));
+  net->send_seq[to] = c + 1;
+  off += len;
+  return 1;
+}
+
+// The next chunk from `from` if it has arrived: 1 = received, 0 = nothing yet, < 0 = error.
+int try_recv_chunk(cs_net* net, int from, uint8_t* data, size_t bytes, size_t& off) {
+  NetChannel* ch = net->d_box + from;
+  const uint64_t c = net->recv_seq[from];
+  NetSlot* s = &ch->slot[c % NET_SLOTS];
+  const size_t want = bytes - off < NET_CHUNK ? bytes - off : NET_CHUNK;
+  // the header first: it is the last thing the sender wrote, so a valid header implies a complete payload;
+  // fetching both in one copy could pair a fresh header with stale payload bytes
+  CS_CUDA(cudaMemcpyAsync(&net->h_recv->seq, &s->seq, 16, cudaMemcpyDeviceToHost, net->st));
+  CS_CUDA(cudaStreamSynchronize(net->st));
+  if (net->h_recv->seq != c + 1) return 0;
+  if (net->h_recv->len != want)
+    return fail(CS_ERR_STATE, "cs_net: party %d expected %zu bytes from party %d, got %llu", net->id, want, from,
+                (unsigned long long)net->h_recv->len);
+  if (want) {
+    CS_CUDA(cudaMemcpyAsync(net->h_recv->payload, s->payload, want, cudaMemcpyDeviceToHost, net->st));
+    CS_CUDA(cudaStreamSynchronize(net->st));
+    memcpy(data + off, net->h_recv->payload, want);
+  }
+  net->recv_seq[from] = c + 1;
+  off += want;
+  // acknowledge into the sender's mailbox (its channel for me): frees one of its credits
+  net->h_ack[from] = c + 1;
+  CS_CUDA(cudaMemcpyAsync(&net->peer_box[from][net->id].ack, &net->h_ack[from], 8, kAny, net->st));
+  return 1;
+}
+
+int peer_send(cs_net* net, int to, const uint8_t* data, size_t bytes) {
+  size_t off = 0;
+  bool first = true;
+  Deadline dl;
+  while (first || off < bytes) {
+    int rc = try_send_chunk(net, to, data, bytes, off);
+    if (rc < 0) return rc;
+    if (rc) { first = false; dl = Deadline(); continue; }
+    if (dl.expired()) return fail(CS_ERR_STATE, "cs_net: party %d timed out waiting for credits from party %d", net->id, to);
+  }
   return 0;
 }
 
 int peer_recv(cs_net* net, int from, uint8_t* data, size_t bytes) {
-  NetChannel* ch = net->d_box + from;
   size_t off = 0;
-  do {
-    const uint64_t c = net->recv_seq[from];
-    NetSlot* s = &ch->slot[c % NET_SLOTS];
-    const size_t want = bytes - off < NET_CHUNK ? bytes - off : NET_CHUNK;
-    Deadline dl;
-    for (;;) {
-      // the header first: it is the last thing the sender wrote, so a valid header implies a complete payload;
-      // fetching both in one copy could pair a fresh header with stale payload bytes
-      CS_CUDA(cudaMemcpyAsync(&net->h_recv->seq, &s->seq, 16, cudaMemcpyDeviceToHost, net->st));
-      CS_CUDA(cudaStreamSynchronize(net->st));
-      if (net->h_recv->seq == c + 1) break;
-      if (dl.expired()) return fail(CS_ERR_STATE, "cs_net: party %d timed out waiting for a message from party %d", net->id, from);
+  bool first = true;
+  Deadline dl;
+  while (first || off < bytes) {
+    int rc = try_recv_chunk(net, from, data, bytes, off);
+    if (rc < 0) return rc;
+    if (rc) { first = false; dl = Deadline(); continue; }
+    if (dl.expired()) return fail(CS_ERR_STATE, "cs_net: party %d timed out waiting for a message from party %d", net->id, from);
+  }
+  return 0;
+}
+
+// Send to one party and receive from another with both directions making progress chunk by chunk: an all-to-all of
+// messages larger than the credit window (NET_SLOTS * NET_CHUNK) cannot dead-lock on everybody sending first.
+int peer_sendrecv(cs_net* net, int to, const uint8_t* sdata, size_t sbytes, int from, uint8_t* rdata, size_t rbytes) {
+  size_t soff = 0, roff = 0;
+  bool sfirst = true, rfirst = true;
+  Deadline dl;
+  while (sfirst || rfirst || soff < sbytes || roff < rbytes) {
+    bool progress = false;
+    if (sfirst || soff < sbytes) {
+      int rc = try_send_chunk(net, to, sdata, sbytes, soff);
+      if (rc < 0) return rc;
+      if (rc) { sfirst = false; progress = true; }
     }
-    if (net->h_recv->len != want)
-      return fail(CS_ERR_STATE, "cs_net: party %d expected %zu bytes from party %d, got %llu", net->id, want, from,
-                  (unsigned long long)net->h_recv->len);
-    if (want) {
-      CS_CUDA(cudaMemcpyAsync(net->h_recv->payload, s->payload, want, cudaMemcpyDeviceToHost, net->st));
-      CS_CUDA(cudaStreamSynchronize(net->st));
-      memcpy(data + off, net->h_recv->payload, want);
+    if (rfirst || roff < rbytes) {
+      int rc = try_recv_chunk(net, from, rdata, rbytes, roff);
+      if (rc < 0) return rc;
+      if (rc) { rfirst = false; progress = true; }
     }
-    net->recv_seq[from] = c + 1;
-    off += want;
-    // acknowledge into the sender's mailbox (its channel for me): frees one of its credits
-    net->h_ack[from] = c + 1;
-    CS_CUDA(cudaMemcpyAsync(&net->peer_box[from][net->id].ack, &net->h_ack[from], 8, kAny, net->st));
-  } while (off < bytes);
+    if (progress) dl = Deadline();
+    else if (dl.expired())
+      return fail(CS_ERR_STATE, "cs_net: party %d timed out in sendrecv (to %d: %zu of %zu, from %d: %zu of %zu bytes)", net->id, to,
+                  soff, sbytes, from, roff, rbytes);
+  }
   return 0;
 }
 
@@ -226,6 +266,20 @@ int cs_net_recv(cs_net* net, int from, void* data, size_t bytes) {
   if (!net->connected) return fail(CS_ERR_STATE, "cs_net_recv: mailbox net is not connected");
   CS_CUDA(cudaSetDevice(net->device));
   return peer_recv(net, from, (uint8_t*)data, bytes);
+}
+
+int cs_net_sendrecv(cs_net* net, int to, const void* sdata, size_t sbytes, int from, void* rdata, size_t rbytes) {
+  if (!net || (!sdata && sbytes) || (!rdata && rbytes)) return fail(CS_ERR_ARG, "cs_net_sendrecv: NULL argument");
+  if (to < 0 || to >= net->n || to == net->id) return fail(CS_ERR_ARG, "cs_net_sendrecv: bad destination %d", to);
+  if (from < 0 || from >= net->n || from == net->id) return fail(CS_ERR_ARG, "cs_net_sendrecv: bad source %d", from);
+  if (net->is_cb) {  // the callback transport queues its sends (mpc_net::Network::send does not wait for the receiver)
+    CS_TRY(cs_net_send(net, to, sdata, sbytes));
+    return cs_net_recv(net, from, rdata, rbytes);
+  }
+  if (!net->connected) return fail(CS_ERR_STATE, "cs_net_sendrecv: mailbox net is not connected");
+  net->bytes_sent += sbytes;
+  CS_CUDA(cudaSetDevice(net->device));
+  return peer_sendrecv(net, to, (const uint8_t*)sdata, sbytes, from, (uint8_t*)rdata, rbytes);
 }
 
 uint64_t cs_net_bytes_sent(const cs_net* net) { return net ? net->bytes_sent : 0; }

@@ -93,26 +93,25 @@ int buffer_pairs_t(cs_shamir_state* st, cs_net* net, size_t batches) {
   }
   // rcv[k][src]: the share dealer `src` gave me
   std::vector<std::vector<HR>> rcv_t(batches, std::vector<HR>(n)), rcv_2t(batches, std::vector<HR>(n));
-  std::vector<uint64_t> msg(batches * 2 * HR::N);
-  for (int j = 0; j < n; j++) {
+  // all-to-all in n - 1 rounds: round k sends my dealing to party id + k and takes party id - k's (cs_net_sendrecv moves
+  // both directions chunk by chunk, so dealings larger than the mailbox credit window cannot dead-lock)
+  std::vector<uint64_t> msg(batches * 2 * HR::N), rmsg(batches * 2 * HR::N);
+  {
+    const HR xi = O::from_u((uint64_t)id + 1);
+    for (size_t k = 0; k < batches; k++) { rcv_t[k][id] = O::eval_poly(f[k], xi); rcv_2t[k][id] = O::eval_poly(g[k], xi); }
+  }
+  for (int round = 1; round < n; round++) {
+    const int j = (id + round) % n, src = (id + n - round) % n;
     const HR xj = O::from_u((uint64_t)j + 1);
-    if (j == id) {
-      for (size_t k = 0; k < batches; k++) { rcv_t[k][id] = O::eval_poly(f[k], xj); rcv_2t[k][id] = O::eval_poly(g[k], xj); }
-      continue;
-    }
     for (size_t k = 0; k < batches; k++) {
       const HR a = O::eval_poly(f[k], xj), b = O::eval_poly(g[k], xj);
       memcpy(&msg[(2 * k) * HR::N], a.l, sizeof(a.l));
       memcpy(&msg[(2 * k + 1) * HR::N], b.l, sizeof(b.l));
     }
-    CS_TRY(cs_net_send(net, j, msg.data(), msg.size() * 8));
-  }
-  for (int j = 0; j < n; j++) {
-    if (j == id) continue;
-    CS_TRY(cs_net_recv(net, j, msg.data(), msg.size() * 8));
+    CS_TRY(cs_net_sendrecv(net, j, msg.data(), msg.size() * 8, src, rmsg.data(), rmsg.size() * 8));
     for (size_t k = 0; k < batches; k++) {
-      rcv_t[k][j] = O::load(&msg[(2 * k) * HR::N]);
-      rcv_2t[k][j] = O::load(&msg[(2 * k + 1) * HR::N]);
+      rcv_t[k][src] = O::load(&rmsg[(2 * k) * HR::N]);
+      rcv_2t[k][src] = O::load(&rmsg[(2 * k + 1) * HR::N]);
     }
   }
   // DN07 extraction with the (t + 1) x n Vandermonde matrix M[row][col] = (col + 1)^row  (rngs.rs:140-157, matmul)

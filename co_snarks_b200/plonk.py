@@ -253,11 +253,17 @@ class DistRep3Comm:
             parts = self._gather(ctx.d2h(sess.d_out, (m, 4)))
             ctx.h2d(sess.d_in, _sum_vec(ctx, curve, parts))
 
-    def run(self, gen):
+    def run(self, gen, trace=None):
+        """`trace` (a list) receives (request kind, ms until the party's GPU drained, ms in the exchange) per step."""
+        import time
         ctx, curve, sess = self.prover.ctx, self.prover.curve, self.prover.sess
+        t0 = time.perf_counter()
         req = next(gen)
         while True:
             kind, payload = req
+            if trace is not None:
+                ctx.synchronize()
+                t1 = time.perf_counter()
             if kind == "sum_points":
                 ans = _sum_points(ctx.lib, curve, self._gather(payload))
             elif kind == "sum_vec":
@@ -280,7 +286,14 @@ class DistRep3Comm:
                         ctx.synchronize()
                         ctx.free(d)
                 ans = None
+            if trace is not None:
+                t2 = time.perf_counter()
+                trace.append((kind, round((t1 - t0) * 1e3, 2), round((t2 - t1) * 1e3, 2)))
+                t0 = t2
             try:
                 req = gen.send(ans)
             except StopIteration as e:
+                if trace is not None:
+                    ctx.synchronize()
+                    trace.append(("end", round((time.perf_counter() - t0) * 1e3, 2), 0.0))
                 return e.value

@@ -96,6 +96,10 @@ int cs_msm_rep3_shares(cs_ctx* ctx, const cs_bases* bases, size_t offset, const 
  * {digits+histogram, scan+scatter, bucket accumulation (k_msm_accum0), partial folding, bucket reduction}. */
 int cs_msm_profile(cs_ctx* ctx, int enable);
 int cs_msm_stage_ms(cs_ctx* ctx, float* out_ms5);
+/* While profiling is on: where the stage boundaries of the five MSM workspaces (Groth16: A, B1, B2, L, H) fell in the
+ * last fork/join section, in ms after the fork -- out_ms[w * 6 + i], i = 0..5 (start, after digits, sort, accumulate,
+ * fold, reduce); -1 where no event exists.  Synchronises the device. */
+int cs_msm_timeline_ms(cs_ctx* ctx, float* out_ms);
 
 /* out[i] = scalars[i] * base (affine Montgomery), i < n.  No counterpart on the reference's prover path:
  * it is the fixed-base multiplication a Groth16/KZG setup performs, provided so that tests and bench.py
@@ -383,6 +387,10 @@ int cs_net_peer_connect(cs_net* net, const uint8_t* handles);
 int cs_net_peer_connect_local(cs_net* net, cs_net* const* peers /* n_parties entries, own may be NULL */);
 int cs_net_send(cs_net* net, int to_party, const void* data, size_t bytes);
 int cs_net_recv(cs_net* net, int from_party, void* data, size_t bytes);
+/* Send to `to` and receive from `from` in one call; on mailbox nets both directions advance chunk by chunk, so an
+ * all-to-all of messages larger than the credit window (8 x 64 KB per channel) cannot dead-lock with every party
+ * sending first.  Callback nets: send then recv (the transport queues sends, like mpc_net::Network::send). */
+int cs_net_sendrecv(cs_net* net, int to, const void* sdata, size_t sbytes, int from, void* rdata, size_t rbytes);
 uint64_t cs_net_bytes_sent(const cs_net* net);
 void cs_net_free(cs_net* net);
 
@@ -597,6 +605,46 @@ int cs_fr_add(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, ui
 int cs_fr_sub(cs_curve curve, const uint64_t* a_mont, const uint64_t* b_mont, uint64_t* out_mont);
 int cs_groth16_roots_of_unity(cs_curve curve, unsigned pow, uint64_t* out_group_gen_mont,
                               uint64_t* out_coset_shift_mont);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * UltraHonk sumcheck, prover side (co-noir/co-ultrahonk/src/co_decider/co_sumcheck/*; plain prover:
+ * co-noir/ultrahonk/src/decider/sumcheck/*).  Field elements are Montgomery Fr; a Rep3 share is {a, b}.
+ * ------------------------------------------------------------------------------------------------------------- */
+
+/* GateSeparatorPolynomial::new (ultrahonk/src/decider/types.rs:53-67): d_out[j] = prod over the set bits i of j of
+ * betas[i], j < 2^log_n (d_out: device, 2^log_n elements). */
+int cs_sumcheck_gate_separator(cs_ctx* ctx, cs_curve curve, const uint64_t* h_betas_mont, unsigned log_n, uint64_t* d_out);
+
+/* partially_evaluate_init / partially_evaluate_inplace (co_sumcheck_prover.rs:33-97) for a batch of polynomials of
+ * the same current length `len` (even): d_out[k][i] = d_in[k][2i] + (d_in[k][2i+1] - d_in[k][2i]) * u, i < len/2.
+ * d_in / d_out: host arrays of n_polys device pointers; shared = 0: public values, 1: Rep3 shares (both components).
+ * When len == 2 a zero is written behind the single result, as the reference keeps two entries (:75-77, :91-93), so
+ * output buffers hold at least two elements.  An output may not alias its input: callers ping-pong two buffers where
+ * the reference folds in place.  Runs on the context's stream, asynchronously. */
+int cs_sumcheck_fold(cs_ctx* ctx, cs_curve curve, const uint64_t* const* d_in, uint64_t* const* d_out, size_t n_polys,
+                     int shared, size_t len, const uint64_t* h_challenge_mont);
+
+/* The polynomials UltraArithmeticRelation::add_entities batches (relations/ultra_arithmetic_relation.rs:252-268):
+ * device pointers, `round_size` rows each.  Witness columns are Fr values (CS_PLAIN) or Rep3 shares (CS_REP3);
+ * selectors are public. */
+typedef struct {
+  const uint64_t *w_l, *w_r, *w_o, *w_4, *w_l_shift, *w_4_shift;
+  const uint64_t *q_m, *q_l, *q_r, *q_o, *q_4, *q_c, *q_arith;
+} cs_honk_arith_polys;
+
+/* One sumcheck round of the UltraArithmeticRelation over all edges (row pairs) of the round:
+ * SumcheckRound::compute_univariate_inner's loop (co_sumcheck_round.rs:261-305: extend_edges, scaling factor
+ * beta_products[(edge >> 1) * periodicity], accumulate) restricted to that relation.
+ *   h_r0: 6 evaluations of sub-relation 0 -- Fr values (plain) or this party's ADDITIVE share (Rep3: the half-shared
+ *         accumulator UltraArithmeticRelationAccHalfShared::r0); h_r1: 5 evaluations of sub-relation 1 -- Fr values
+ *         (plain, 5 x Fr) or Rep3 shares (5 x {a, b}).
+ *   prf (Rep3, optional): the party's two ChaCha12 streams; words [pos, pos + 48) of each become one zero share per
+ *         r0 evaluation (the reference masks every product inside local_mul_vec; only the sum reaches the protocol).
+ *         The caller advances both streams by 48 words.  NULL: no mask (tests).
+ * Edges whose q_arith is zero contribute zero, which is what the reference's can_skip filter leaves out. */
+int cs_sumcheck_arith_round(cs_ctx* ctx, cs_curve curve, cs_share_kind kind, int party, const cs_honk_arith_polys* d_polys,
+                            size_t round_size, const uint64_t* d_beta_products, size_t periodicity, const cs_rep3_prf* prf,
+                            uint64_t* h_r0, uint64_t* h_r1);
 
 #ifdef __cplusplus
 }

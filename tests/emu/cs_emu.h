@@ -56,6 +56,14 @@ void launch(dim3 grid, dim3 block, size_t smem, bool uses_sync, const std::funct
 
 static inline void __syncthreads() { cs::emu::syncthreads(); }
 static inline void __syncwarp() {}
+// warp shuffles (32-bit), emulated with a block-wide exchange: every thread of the block must make the call together,
+// i.e. the kernel is launched with CS_LAUNCH_SYNC and has no early return ahead of it
+namespace cs { namespace emu { uint32_t shfl_from(uint32_t v, int delta_kind, unsigned arg);
+void shfl_bytes(const void* in, void* out, size_t bytes, int kind, unsigned arg); } }
+static inline uint32_t __shfl_up_sync(unsigned, uint32_t v, unsigned d) { return cs::emu::shfl_from(v, 0, d); }
+static inline uint32_t __shfl_down_sync(unsigned, uint32_t v, unsigned d) { return cs::emu::shfl_from(v, 1, d); }
+static inline uint32_t __shfl_xor_sync(unsigned, uint32_t v, unsigned m) { return cs::emu::shfl_from(v, 2, m); }
+static inline uint32_t __shfl_sync(unsigned, uint32_t v, unsigned lane) { return cs::emu::shfl_from(v, 3, lane); }
 static inline void __threadfence() {}
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
 static inline int atomicAdd(int* p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
@@ -84,6 +92,7 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = nullptr; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* s, unsigned, int) { *s = nullptr; return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }

@@ -1,6 +1,7 @@
 """Parity checks shared by the GPU tests (-m gpu, through libcosnarks_gpu.so) and the CPU-emulation
 tests (tests/emu build of the same kernels).  Every check compares the C-ABI result with the oracle
 or with a committed golden vector; integer work => bit-exact equality."""
+import ctypes as C
 import random
 
 import pytest
@@ -1140,3 +1141,141 @@ def check_rep3_share_files(lib, tmp_path):
     open(p, "wb").write(data[:-5])
     with pytest.raises(RuntimeError):
         B.read_rep3_witness(lib, p, cv.id)
+
+
+def check_sumcheck(ctx, log_n=5, seed=51, curve="bn254"):
+    """UltraHonk sumcheck kernels (csrc/cs_sumcheck.cuh) against oracle/sumcheck.py, plain and 3-party Rep3, and through
+    a whole sumcheck of the arithmetic relation: S_0(0) + S_0(1) = sum over the hypercube, S_i(0) + S_i(1) =
+    S_{i-1}(u_{i-1}), and the last claim equals the relation on the fully folded polynomials."""
+    from oracle import chacha as OC
+    from oracle import groth16 as OG
+    from oracle import sumcheck as OS
+    cv = Conv(curve)
+    r = cv.r
+    rng = random.Random(seed)
+    n = 1 << log_n
+    names_w, names_q = OS.ARITH_WITNESS, OS.ARITH_SELECTORS
+    # ---- gate separator
+    betas = [rng.randrange(r) for _ in range(log_n)]
+    d_beta = ctx.alloc(n * 32)
+    ctx.sumcheck_gate_separator(cv.id, cv.fr(betas), d_beta)
+    beta_products = OS.gate_separator(betas, log_n, r)
+    assert cv.fr_back(ctx.d2h(d_beta, (n, 4))) == beta_products
+    d_one = ctx.alloc(32)
+    ctx.sumcheck_gate_separator(cv.id, cv.fr([]), d_one)  # log_n = 0: the single entry 1
+    assert cv.fr_back(ctx.d2h(d_one, (1, 4))) == [1]
+    ctx.free(d_one)
+    # ---- polynomials: q_arith takes every branch value (0 disables an edge entirely when both rows are 0)
+    polys = {nm: [rng.randrange(r) for _ in range(n)] for nm in names_w + names_q}
+    polys["q_arith"] = [rng.choice([0, 0, 1, 2, 3, 4, rng.randrange(r)]) for _ in range(n)]
+    polys["q_arith"][0:2] = [0, 0]
+    polys["q_arith"][6:8] = [0, 0]
+    shares = {nm: OG.share_rep3(polys[nm], r, rng) for nm in names_w}  # [party][row] -> (a, b)
+    flat = lambda sh: cv.fr([v for ab in sh for v in ab])
+    bufs = []
+
+    def dev(arr):
+        p = ctx.to_device(arr)
+        bufs.append(p)
+        return p
+    d_plain = {nm: dev(cv.fr(polys[nm])) for nm in names_w + names_q}
+    d_party = [dict({nm: dev(flat(shares[nm][i])) for nm in names_w}, **{nm: d_plain[nm] for nm in names_q}) for i in range(3)]
+
+    # ---- one round, plain and Rep3, against the oracle (periodicity 2 = first round)
+    r0, r1 = ctx.sumcheck_arith_round(cv.id, B.CS_PLAIN, 0, d_plain, n, d_beta, 2)
+    exp0, exp1 = OS.arith_round_plain(polys, n, beta_products, 2, r)
+    assert cv.fr_back(r0) == exp0 and cv.fr_back(r1) == exp1
+    seeds = [bytes((11 * p + i) & 0xff for i in range(32)) for p in range(3)]
+    pos = [5, 64, 19]
+    tot0, tot0m, tot1 = [0] * 6, [0] * 6, [0] * 5
+    views = []
+    for i in range(3):
+        view = dict({nm: shares[nm][i] for nm in names_w}, **{nm: polys[nm] for nm in names_q})
+        e0, e1 = OS.arith_round_rep3(view, i, n, beta_products, 2, r)
+        g0, g1 = ctx.sumcheck_arith_round(cv.id, B.CS_REP3, i, d_party[i], n, d_beta, 2)
+        g1 = cv.fr_back(g1)
+        assert cv.fr_back(g0) == e0, i
+        assert [(g1[2 * k], g1[2 * k + 1]) for k in range(5)] == e1, i
+        views.append(e1)
+        tot0 = [(a + b) % r for a, b in zip(tot0, e0)]
+        tot1 = [(a + b[0]) % r for a, b in zip(tot1, e1)]
+        # with the zero-share masks drawn from the party's two streams
+        prev = (i + 2) % 3
+        prf = B.Rep3Prf((C.c_uint8 * 32)(*seeds[i]), pos[i], (C.c_uint8 * 32)(*seeds[prev]), pos[prev], 12)
+        m0, _ = ctx.sumcheck_arith_round(cv.id, B.CS_REP3, i, d_party[i], n, d_beta, 2, prf)
+        m0 = cv.fr_back(m0)
+        masks = OC.masking_field_elements_vec(seeds[i], pos[i], seeds[prev], pos[prev], 6, r)
+        assert m0 == [(a + b) % r for a, b in zip(e0, masks)], i
+        tot0m = [(a + b) % r for a, b in zip(tot0m, m0)]
+    assert tot0 == exp0 and tot0m == exp0 and tot1 == exp1  # the parties' accumulators open to the plain ones
+    assert all(views[i][k][1] == views[(i + 2) % 3][k][0] for i in range(3) for k in range(5))  # r1 stays replicated
+
+    # ---- fold: public + shared batches against the oracle, down to one row (+ the zero the reference pushes)
+    u0 = rng.randrange(r)
+    for shared in (False, True):
+        nms = names_w if shared else names_q
+        cur = {nm: (shares[nm][1] if shared else polys[nm]) for nm in nms}
+        d_cur = {nm: (d_party[1][nm] if shared else d_plain[nm]) for nm in nms}
+        length, u = n, u0
+        comps = 2 if shared else 1
+        while length >= 2:
+            d_out = {nm: ctx.alloc(max(length // 2, 2) * 32 * comps) for nm in nms}
+            ctx.sumcheck_fold(cv.id, [d_cur[nm] for nm in nms], [d_out[nm] for nm in nms], shared, length, cv.fr([u])[0])
+            for nm in nms:
+                cur[nm] = OS.partially_evaluate(cur[nm][:length], u, r)
+                got = cv.fr_back(ctx.d2h(d_out[nm], (len(cur[nm]) * comps, 4)))
+                want = [v for ab in cur[nm] for v in ab] if shared else cur[nm]
+                assert got == want, (nm, length)
+            bufs.extend(d_out.values())
+            d_cur, length, u = d_out, length // 2, (u * 7 + 3) % r
+
+    # ---- the whole sumcheck of this relation on the plain polynomials
+    alpha = rng.randrange(r)
+    neg_half = (-pow(2, -1, r)) % r
+
+    def relation_row(x):  # q_arith * [...] + alpha * q_arith (q_arith - 1)(q_arith - 2)(...)   (the doc comment, :270-320)
+        qa = x["q_arith"]
+        f0 = (x["w_l"] * x["w_r"] % r * x["q_m"] % r * (qa - 3) % r * neg_half + x["q_l"] * x["w_l"] + x["q_r"] * x["w_r"]
+              + x["q_o"] * x["w_o"] + x["q_4"] * x["w_4"] + x["q_c"] + (qa - 1) * x["w_4_shift"]) % r * qa % r
+        f1 = (x["w_l"] + x["w_4"] - x["w_l_shift"] + x["q_m"]) % r * (qa - 2) % r * (qa - 1) % r * qa % r
+        return (f0 + alpha * f1) % r
+
+    def eval_univariate(evals, x):
+        return sum(v * _lagrange_basis(len(evals), i, x, r) for i, v in enumerate(evals)) % r
+    target = sum(relation_row({nm: polys[nm][j] for nm in polys}) * beta_products[j] for j in range(n)) % r
+    cur = dict(polys)
+    d_cur = dict(d_plain)
+    size, periodicity, partial, us = n, 2, 1, []
+    SIZE = 8  # BATCHED_RELATION_PARTIAL_LENGTH
+    for rnd in range(log_n):
+        g0, g1 = ctx.sumcheck_arith_round(cv.id, B.CS_PLAIN, 0, d_cur, size, d_beta, periodicity)
+        g0, g1 = cv.fr_back(g0), cv.fr_back(g1)
+        assert (g0, g1) == OS.arith_round_plain({nm: cur[nm][:size] for nm in cur}, size, beta_products, periodicity, r)
+        S = OS.batch_univariates(g0, g1, alpha, betas[rnd], partial, SIZE, r)
+        assert (S[0] + S[1]) % r == target, rnd
+        u = rng.randrange(r)
+        us.append(u)
+        target = eval_univariate(S, u)
+        partial = partial * (1 + u * (betas[rnd] - 1)) % r  # GateSeparatorPolynomial::partially_evaluate (types.rs:96-102)
+        periodicity *= 2
+        nms = list(cur)
+        d_out = {nm: ctx.alloc(max(size // 2, 2) * 32) for nm in nms}
+        ctx.sumcheck_fold(cv.id, [d_cur[nm] for nm in nms], [d_out[nm] for nm in nms], False, size, cv.fr([u])[0])
+        bufs.extend(d_out.values())
+        d_cur = d_out
+        cur = {nm: OS.partially_evaluate(cur[nm][:size], u, r) for nm in nms}
+        size //= 2
+    final = {nm: cv.fr_back(ctx.d2h(d_cur[nm], (1, 4)))[0] for nm in cur}
+    assert final == {nm: cur[nm][0] for nm in cur}
+    assert target == relation_row(final) * partial % r  # the claim the verifier checks against the opened evaluations
+    for p in bufs + [d_beta]:
+        ctx.free(p)
+
+
+def _lagrange_basis(n, i, x, r):
+    num, den = 1, 1
+    for j in range(n):
+        if j != i:
+            num = num * (x - j) % r
+            den = den * (i - j) % r
+    return num * pow(den, -1, r) % r

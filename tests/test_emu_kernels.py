@@ -168,3 +168,11 @@ def test_emu_share_rep3_device(emu_ctx):
 
 def test_rep3_share_files(emu_ctx, tmp_path):
     K.check_rep3_share_files(emu_ctx.lib, tmp_path)
+
+
+def test_emu_sumcheck(emu_ctx):
+    K.check_sumcheck(emu_ctx, log_n=4)
+
+
+def test_emu_sumcheck_bls12_381(emu_ctx):
+    K.check_sumcheck(emu_ctx, log_n=3, curve="bls12_381")

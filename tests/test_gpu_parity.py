@@ -188,3 +188,11 @@ def test_honk_commit_batch(gpu_ctx):
 
 def test_share_rep3_device(gpu_ctx):
     K.check_share_rep3_device(gpu_ctx, n=100000)
+
+
+def test_sumcheck_kernels(gpu_ctx):
+    K.check_sumcheck(gpu_ctx, log_n=9)
+
+
+def test_sumcheck_kernels_bls12_381(gpu_ctx):
+    K.check_sumcheck(gpu_ctx, log_n=5, curve="bls12_381")

@@ -169,6 +169,36 @@ def test_net_mailbox_large_message_emu():
         n.free()
 
 
+def test_net_mailbox_sendrecv_ring_emu():
+    """cs_net_sendrecv: three parties each send 700 KB to the next and take 700 KB from the previous AT THE SAME TIME;
+    that is more than the 8 x 64 KB credit window, so send-then-recv would dead-lock; also the empty message."""
+    from co_snarks_b200 import binding as B
+    mk = _emu_factory()
+    ctxs = [mk() for _ in range(3)]
+    nets = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    for n in nets:
+        n.connect_local(nets)
+    msgs = [np.random.default_rng(i).integers(0, 256, 700_000, dtype=np.uint8).tobytes() for i in range(3)]
+    got, errs = {}, []
+
+    def run(i):
+        try:
+            got[i] = nets[i].sendrecv((i + 1) % 3, msgs[i], (i + 2) % 3, len(msgs[i]))
+            assert nets[i].sendrecv((i + 2) % 3, b"", (i + 1) % 3, 0) == b""
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=run, args=(i,)) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=120)
+    assert not errs, errs
+    assert all(got[i] == msgs[(i + 2) % 3] for i in range(3))
+    assert all(n.bytes_sent == 700_000 for n in nets)
+    for n in nets:
+        n.free()
+
+
 def test_rep3_state_streams_emu():
     """cs_rep3_state: F::rand rejection sampling stays below r; fork derives child seeds from both streams;
     prf() exposes (seed, word position) and rand() advances them."""

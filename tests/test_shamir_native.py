@@ -181,6 +181,12 @@ def test_shamir_degree_reduce_many_n3_t1_emu():
     _degree_reduce_vectors(_emu_factory(), 3, 1, 20)
 
 
+def test_shamir_dealing_larger_than_the_credit_window_emu():
+    # 20000 pairs at t = 1 are 10000 dealings of 64 B per party pair = 640 KB > 8 x 64 KB of mailbox credit: every party
+    # deals to every other at the same time (cs_net_sendrecv), then degree-reduces a vector of 640 KB through the king
+    _degree_reduce_vectors(_emu_factory(), 3, 1, 20000)
+
+
 def test_shamir_co_groth16_native_emu():
     _shamir_groth16(_emu_factory(), "multiplier2")
 

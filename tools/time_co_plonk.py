@@ -56,7 +56,10 @@ def measure(sizes, reps=None):
             torch.cuda.synchronize()
             dist.barrier()
             t0 = time.perf_counter()
-            pts, evs = comm.run(prover.prove(state, syn.public_inputs, mine, syn.key["vk_points"], syn.n))
+            trace = [] if (os.environ.get("CS_CO_PLONK_TRACE") and i == reps - 1) else None
+            pts, evs = comm.run(prover.prove(state, syn.public_inputs, mine, syn.key["vk_points"], syn.n), trace)
+            if trace and rank == 0:
+                print("trace 2^%d (kind, compute ms, exchange ms): %s" % (lg, trace), file=sys.stderr, flush=True)
             t = torch.tensor([(time.perf_counter() - t0) * 1e3], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms.append(float(t.item()))
