@@ -24,6 +24,10 @@ import sys
 import tempfile
 import time
 
+# the prover uses more streams than the driver's default 8 hardware queues (see csrc/cs_api.cu); must be set before the
+# CUDA context exists
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 

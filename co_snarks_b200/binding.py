@@ -10,6 +10,8 @@ import os
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")  # see csrc/cs_api.cu: read when the CUDA context is created
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 DEFAULT_LIB = os.path.join(_HERE, "libcosnarks_gpu.so")
 

@@ -18,6 +18,15 @@ int fail(int code, const char* fmt, ...) {
   last_error() = buf;
   return code;
 }
+#if !defined(CS_EMU)
+// The prover keeps up to 12 streams busy at once (five MSMs x {sort/fold/reduce, accumulation}, witness map, caller's
+// stream).  The driver multiplexes streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8); streams that
+// share a queue serialise -- measured: the L MSM did not start until the H MSM, 14 ms of unrelated work, had drained
+// (profiles/r2_prio_ab2.log).  The variable is read when the CUDA context is created, so it is set when this library is
+// loaded, unless the application chose a value itself.
+__attribute__((constructor)) static void cs_more_hw_queues() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+#endif
+
 std::atomic<uint64_t>& launch_counter() {
   static std::atomic<uint64_t> c{0};
   return c;
@@ -81,8 +90,10 @@ int cs_ctx_create(int device, void* stream, cs_ctx** out) {
   // Stream priorities (CUDA: lower number = served first).  The short, latency-bound kernels (digit sort, folds,
   // bucket reduction, NTT passes) run on higher-priority streams than the full-GPU MSM accumulation grids, so that
   // they are not queued behind every accumulation launched before them.  CS_PRIO="side,acc,wm" overrides
-  // (default "-2,0,-3"); CS_MSM_SPLIT=0 keeps each MSM on a single stream.
-  int prio_side = -2, prio_acc = 0, prio_wm = -3;
+  // (default "-2,0,-2"); CS_MSM_SPLIT=0 keeps each MSM on a single stream.  With 32 hardware queues every layout
+  // tried lands within 0.1 ms of the others (17.9-18.0 ms, profiles/r2_sched_ab*.log): the proof is bound by the sum
+  // of its integer-pipe work, the layout only decides which MSM finishes first.
+  int prio_side = -2, prio_acc = 0, prio_wm = -2;
   if (const char* e = getenv("CS_PRIO")) sscanf(e, "%d,%d,%d", &prio_side, &prio_acc, &prio_wm);
   const char* split_env = getenv("CS_MSM_SPLIT");
   const bool split = !(split_env && atoi(split_env) == 0);
@@ -486,8 +497,12 @@ int ntt_run(cs_ctx* ctx, const cs_domain* d, uint32_t* d_data, unsigned batch, b
             const uint32_t* d_post, cudaStream_t st) {
   if (batch != 1 && batch != 2) return fail(CS_ERR_ARG, "ntt: batch must be 1 or 2");
   if (d->log_n == 0) return 0;
-  static int v2_env = -1;  // CS_NTT_V2=0 keeps the round-1 kernel (A/B comparison)
-  if (v2_env < 0) { const char* e = getenv("CS_NTT_V2"); v2_env = e ? atoi(e) : 1; }
+  // CS_NTT_V2=1 selects the TMA-staged radix-8 pass (cs_ntt8.cuh).  Measured on B200 (profiles/r2_ntt_v1_v2.md): it
+  // ties the round-1 kernel at 2^20 (0.266 vs 0.260 ms, batch 2: 0.4735 vs 0.4743), loses 2-3 % at 2^22 / 2^24 and 2.5x
+  // at 2^16 (tile set-up); both sit at 65 % fmaheavy, the instruction-mix bound of one product + add + sub per
+  // butterfly.  The bulk-copy staging therefore buys nothing here and the default stays the round-1 pass.
+  static int v2_env = -1;
+  if (v2_env < 0) { const char* e = getenv("CS_NTT_V2"); v2_env = e ? atoi(e) : 0; }
   CS_DISPATCH_CURVE(d->curve, {
     typedef typename Cfg::FrP FrP;
     const uint32_t* twp = inverse_in_to_out ? d->tw_inv.as<uint32_t>() : d->tw_fwd.as<uint32_t>();

@@ -651,7 +651,7 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
     // resident blocks per SM (register cap) -- tuned on B200, overridable for experiments
     static int minb_env = -1;
     if (minb_env < 0) { const char* e = getenv("CS_ACCUM0_MINB"); minb_env = e ? atoi(e) : 0; }
-    const int minb = minb_env ? minb_env : (sizeof(F) > 32 ? 3 : 4);
+    const int minb = minb_env ? minb_env : 4;  // B200, dense 2^20: G1 2.87 ms at 4 (2.95 at 5); G2 8.52 at 4, 8.72 at 3, 9.19 at 2, 8.78 at 5
     if (table_m260) {
       CS_TRY((msm_accum0_f52<F>(table, so.sorted.as<uint32_t>(), count, start, sstart0, nb1, S, order, order_b,
                                 ws.part0.as<Xyzz<F>>(), (uint32_t)max_s0, st)));

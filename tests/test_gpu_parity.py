@@ -178,6 +178,24 @@ def test_msm_fp64_pipe_accumulation_subprocess():
     assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
 
 
+def test_ntt_tma_radix8_pass_subprocess():
+    """The opt-in TMA-staged radix-8 NTT pass (cs_ntt8.cuh, CS_NTT_V2=1: cp.async.bulk tile loads with mbarrier,
+    multi-column tiles, register radix-8/4 rounds) gives the oracle's transforms at every size it takes over (2^12 up),
+    batch 1 and 2, forward / inverse, and through the Plonk fft/ifft entry points.  Separate process: the switch is
+    read once per process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r);"
+            "from co_snarks_b200 import binding as B; import kernel_checks as K;"
+            "ctx = B.Context(0); K.check_ntt(ctx, (12, 13, 14, 15)); K.check_plonk_primitives(ctx, lg=13); print('ok')"
+            % (root, os.path.join(root, "tests")))
+    env = dict(os.environ, CS_NTT_V2="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_rep3_batch_vm_ops(gpu_ctx):
     K.check_rep3_batch_ops(gpu_ctx, n=3001)
 
