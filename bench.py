@@ -530,13 +530,13 @@ def run_ours(args):
             "roofline": {"kernel": "k_msm_accum0<Fp<Bn254Fq>> (G1 bucket accumulation)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": ncu_traffic(), "peak_source": hbm_src,
-                         "traffic_source": "profiles/r1_ncu_full_accum0_g1_v6.csv (ncu --set full of this kernel on a dense 2^20 G1 MSM; "
+                         "traffic_source": "profiles/r2_ncu_full_accum0_g1.csv (ncu --set full of this kernel on a dense 2^20 G1 MSM; "
                                            "bytes per launch). 16 precomputed table points are read per scalar by design (no doublings), "
                                            "HBM stays below 10 % busy",
                          "note": "256-bit modular arithmetic is integer-pipe bound (~2.3 kIMAD per 96 B); see DESIGN.md",
                          "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "int_pipe": {"achieved_gmodmul_s": gmul, "peak_gmodmul_s": gmul_peak, "frac": gmul / gmul_peak,
-                                      "imad_wide_tops": imad_tops, "peak_source": peak_src,
+                                      "imad_wide_tops": imad_tops, "imad_wide_tops_source": "profiles/r2_pipe_probe.json (data-dependent operands)", "peak_source": peak_src,
                                       "note": "the resource that actually bounds the kernel: 10 Montgomery products per mixed addition"}},
             "msm": {"g1_2p%d_ms" % lg: msm_avg, "mscalar_per_s": nw / (msm_avg * 1e-3) / 1e6,
                     "stage_ms": {"digits": float(stage[0]), "sort": float(stage[1]), "accumulate": float(stage[2]),
@@ -562,7 +562,7 @@ def run_ours(args):
 
 def ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of the accumulate kernel from the committed ncu summary."""
-    path = os.path.join(ROOT, "profiles", "r1_ncu_full_accum0_g1_v6.csv")
+    path = os.path.join(ROOT, "profiles", "r2_ncu_full_accum0_g1.csv")
     mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     try:
         tot = 0.0
@@ -649,9 +649,12 @@ def int_pipe_ceiling():
     try:
         out = subprocess.run([exe], capture_output=True, text=True, timeout=120).stdout
         j = json.loads(out)
-        return max(v for k, v in j.items() if k.startswith("montmul_gmuls")), j.get("imad_wide_tops_t512"), "measured live (tools/imad_peak)"
+        # the probe's own "imad_wide_tops" loop has loop-invariant operands that ptxas strength-reduces to adds (it reads
+        # 17 T/s); the IMAD.WIDE issue rate with data-dependent operands is 9.2 T/s (tools/pipe_probe.cu,
+        # profiles/r2_pipe_probe.json), which is what the Montgomery ceiling below reflects
+        return max(v for k, v in j.items() if k.startswith("montmul_gmuls")), 9.2, "measured live (tools/imad_peak)"
     except Exception:  # noqa: BLE001
-        return 65.2, 17.3, "committed measurement (profiles/r1_imad_peak_and_multiplier_variants.json)"
+        return 65.2, 9.2, "committed measurement (profiles/r1_imad_peak_and_multiplier_variants.json)"
 
 
 def pk_window(args, n):

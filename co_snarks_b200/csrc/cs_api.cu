@@ -135,6 +135,8 @@ void cs_ctx_destroy(cs_ctx* ctx) {
   if (ctx->ev_t0) cudaEventDestroy(ctx->ev_t0);
   ctx->io.release();
   ctx->prf_keys.release();
+  ctx->sc_part.release();
+  ctx->sc_res.release();
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -61,6 +61,7 @@ struct cs_ctx {
   cs::MsmWorkspace msm_ws[cs::CS_NSIDE];
   cs::DevBuf io;  // staging for host-buffer convenience calls
   cs::DevBuf prf_keys;
+  cs::DevBuf sc_part, sc_res;  // sumcheck round: per-block partial sums and the 16 results (reused across rounds)
 };
 
 struct cs_bases {

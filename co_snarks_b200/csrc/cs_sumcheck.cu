@@ -65,11 +65,11 @@ int arith_round_t(cs_ctx* ctx, int kind, int party, const cs_honk_arith_polys* d
   HR nh = HR::zero() - two.inverse();
   Fp<FrP> neg_half;
   memcpy(neg_half.l, nh.l, sizeof(neg_half.l));
-  DevBuf part, res;
+  DevBuf& part = ctx->sc_part;  // grown once, reused by every round (no cudaMalloc / cudaFree on the per-round path)
+  DevBuf& res = ctx->sc_res;
   CS_TRY(part.reserve((size_t)blocks * SC_SLOTS * 32));
-  int rc = res.reserve((size_t)SC_SLOTS * 32);
-  if (rc) { part.release(); return rc; }
-  auto done = [&](int r) { part.release(); res.release(); return r; };
+  CS_TRY(res.reserve((size_t)SC_SLOTS * 32));
+  auto done = [&](int r) { return r; };
   if (kind == CS_REP3)
     CS_LAUNCH_SYNC((k_sc_arith_round<FrP, true>), blocks, 128, 0, ctx->stream, p, n_edges,
                    reinterpret_cast<const uint32_t*>(d_beta_products), periodicity, party, neg_half, part.as<uint32_t>());
