@@ -200,6 +200,32 @@ def rep3_threads_one_gpu(args, ctx, pk, syn):
     return out
 
 
+def plonk_rep3_block(args, rank, local_rank):
+    """Rep3 co-Plonk (BASELINE configs[3]: domain 2^22, 3 parties on 3 GPUs) on ranks 0-2 of the running job: products
+    stored into the next party's GPU over NVLink by the kernels, the party driver inside the library (cs_plonk_rep3_prove),
+    proof checked by the oracle's verifier on rank 0.  Every rank calls this (new_group is collective)."""
+    import torch.distributed as dist
+    group = dist.new_group([0, 1, 2])
+    if rank > 2:
+        return None
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import time_co_plonk as T
+    lg = args.plonk_log_n
+    res = T.measure_group(group, local_rank, [lg], reps=3)
+    if res is None:
+        return None
+    r = res["2p%d" % lg]
+    return {"workload": "co-Plonk Rep3, BN254, synthetic snarkjs-style circuit, domain 2^%d, 3 parties on 3xB200 "
+                        "(BASELINE.json configs[3])" % lg,
+            "ms_per_proof": r["ms_per_proof"], "proofs_per_s": r["proofs_per_s"], "pairing_verified": r["verified"],
+            "net_bytes_per_party_per_proof": r["bytes_sent_per_party"], "key_setup_s": r["setup_s"],
+            "timing": "wall clock per proof from host share buffers to the opened proof, max over the three ranks, "
+                      "mean of 2 proofs after 1 warm-up",
+            "driver": r.get("driver"),
+            "transport": "CUDA-IPC mailboxes for tokens / points; products stored into the next party's HBM by the kernels, "
+                         "n-sized openings read from the peers' HBM (NVLink)"}
+
+
 def rep3_multi_gpu(args, ctx, pk, syn, groups, gpp, rank, world, local_rank):
     """One Rep3 proving group per entry of `groups` (global ranks, party-major: [p0 main, (p0 helper), p1 main, ...]);
     one process per GPU, party exchange through CUDA-IPC mailboxes in peer HBM (NVLink), protocol in the library.
@@ -459,6 +485,12 @@ def run_ours(args):
                 rep3_split = rep3_multi_gpu(args, ctx, pk, syn, [list(range(6))], 2, rank, world, local_rank)
         barrier()
 
+    # ---- BASELINE configs[3] in the same run when three GPUs are there: Rep3 co-Plonk at domain 2^22 on ranks 0-2
+    plonk_blk = None
+    if world >= 3 and not args.no_rep3 and not args.no_plonk:
+        plonk_blk = plonk_rep3_block(args, rank, local_rank)
+        barrier()
+
     out = None
     if rank == 0:
         # ---- kernel roofline (rank 0, single stream): standalone G1 MSM over a_query with stage events
@@ -551,6 +583,8 @@ def run_ours(args):
         }
         if rep3_split is not None:
             out["rep3_2gpu_per_party"] = rep3_split
+        if plonk_blk is not None:
+            out["plonk_rep3"] = plonk_blk
     pk.free()
     ctx.close()
     if world > 1:
@@ -694,6 +728,8 @@ def main():
     ap.add_argument("--fast-setup", action="store_true", help="random (invalid) key: skips the host-side QAP setup")
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-rep3", action="store_true", help="skip the Rep3 block of the default run")
+    ap.add_argument("--no-plonk", action="store_true", help="skip the co-Plonk block of runs with >= 3 GPUs")
+    ap.add_argument("--plonk-log-n", type=int, default=22, help="log2 domain size of the co-Plonk block")
     ap.add_argument("--timeline", action="store_true",
                     help="after the timed region: one more proof with stage events, reported as timeline_ms (diagnostic)")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="diagnostic runs: skip the CPU leg")

@@ -189,6 +189,9 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     "cs_plonk_rep3_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "cs_plonk_rep3_prf_words": (C.c_uint64, [C.c_void_p]),
+    "cs_plonk_rep3_connect_io": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cs_plonk_rep3_prove": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]),
     "cs_chacha_keystream": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64, C.c_uint, C.c_uint, C.c_void_p]),
     "cs_rep3_to_shamir": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cs_groth16_pk_create": (C.c_int, [C.c_void_p, C.POINTER(KeyDesc), C.POINTER(C.c_void_p)]),
@@ -672,6 +675,26 @@ class PlonkRep3Session:
 
     def prf_words(self):
         return int(self.ctx.lib.cs_plonk_rep3_prf_words(self.h))
+
+    def connect_io(self, d_prev_out, d_next_out):
+        """The two peers' additive-out vectors: n-sized openings then read peer HBM instead of crossing the net."""
+        self.ctx._check(self.ctx.lib.cs_plonk_rep3_connect_io(self.h, C.c_void_p(d_prev_out) if d_prev_out else None,
+                                                              C.c_void_p(d_next_out) if d_next_out else None))
+
+    def prove(self, net, state, public_inputs, witness_shares, blinder_shares=None):
+        """Rep3CoPlonk::prove for this party, entirely inside the library (cs_plonk_rep3_prove).
+        -> (points [9, 2 fq]: A B C Z T1 T2 T3 Wxi Wxiw, evals [6, 4]: a b c s1 s2 zw)"""
+        pub = np.ascontiguousarray(public_inputs, dtype=np.uint64).reshape(-1, 4)
+        wit = np.ascontiguousarray(witness_shares, dtype=np.uint64).reshape(-1, 8)
+        bl = None
+        if blinder_shares is not None:
+            bl = np.ascontiguousarray(blinder_shares, dtype=np.uint64).reshape(-1, 8)
+            assert bl.shape[0] == 11
+        pts = np.zeros((9, 2 * self.pk.fq), dtype=np.uint64)
+        evs = np.zeros((6, 4), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.cs_plonk_rep3_prove(self.h, net.h, state.h, _ptr(pub), pub.shape[0], _ptr(wit) if wit.shape[0] else None,
+                                                         wit.shape[0], _ptr(bl), _ptr(pts), _ptr(evs)))
+        return pts, evs
 
     def free(self):
         if self.h:

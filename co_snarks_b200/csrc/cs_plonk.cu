@@ -8,6 +8,7 @@
 // coefficient vectors that are committed / evaluated are permuted back.
 #include <algorithm>
 #include "cs_lib.cuh"
+#include "cs_net.h"
 #include "cs_plonk.cuh"
 #include "cs_plonk_rep3.cuh"
 
@@ -502,6 +503,7 @@ struct cs_plonk_rep3 {
   int party = 0;
   DevBuf w, buf[3], polysh[4], ev[4], polyadd[4], arena, addv, pubv, t, tz, t1, t2, t3, tmp0, tmp1, totals, small;
   uint32_t* next_arena = nullptr;
+  const uint32_t* peer_out[2] = {nullptr, nullptr};  // previous / next party's additive-out vector (cs_plonk_rep3_connect_io)
   size_t slot_words = 0;  // 32-bit words per arena slot (4n shares)
   cs::PrfArgs prf;
   uint64_t ctr = 0;       // field elements drawn from each stream so far
@@ -820,6 +822,195 @@ int r3_step_t(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out)
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Rep3CoPlonk::prove for one party (co-plonk/src/lib.rs:222-240; prove_inner :80-115; openings mpc/rep3.rs:113-138):
+// the step sequence of the device session, the Keccak transcript and the openings, over a cs_net.
+//  * "reshare" of first-layer products: with the next party's arena connected the kernels have already stored them
+//    there (NVLink peer stores) and the exchange is a token round; otherwise the a-halves travel through the net.
+//  * opening of an m-element additive vector: with the peers' out-vectors connected (cs_plonk_rep3_connect_io) the sum
+//    is two vector additions that READ THE PEERS' HBM, fenced by token rounds; otherwise host-staged through the net.
+namespace {
+
+int r3_token_round(cs_net* net) {  // broadcast of one byte: nobody passes before everybody has arrived
+  const int id = net->id, nx = (id + 1) % 3, pv = (id + 2) % 3;
+  uint8_t one = 1, a = 0, b = 0;
+  CS_TRY(cs_net_send(net, nx, &one, 1));
+  CS_TRY(cs_net_send(net, pv, &one, 1));
+  CS_TRY(cs_net_recv(net, pv, &a, 1));
+  return cs_net_recv(net, nx, &b, 1);
+}
+
+template <class Cfg>
+int r3_prove_t(cs_plonk_rep3* s, cs_net* net, cs_rep3_state* state, const uint64_t* h_pub, size_t n_pub, const uint64_t* h_wit,
+               size_t n_wit, const uint64_t* h_blind, uint64_t* out_points, uint64_t* out_evals) {
+  typedef typename Cfg::FrP FrP;
+  typedef host::HFp<FrP> HR;
+  typedef host::HFp<typename Cfg::FqP> HQ;
+  typedef host::HAffine<HQ> A1;
+  typedef host::HXyzz<HQ> X1;
+  cs_ctx* ctx = s->ctx;
+  const cs_plonk_pk* pk = s->pk;
+  const cs_curve cv = (cs_curve)pk->curve;
+  const size_t n = pk->n, pl = 2 * HQ::N;
+  const int id = net->id, nx = (id + 1) % 3, pv = (id + 2) % 3;
+  // Round1Challenges::random (round1.rs:82-92): eleven T::rand shares, unless the caller brings them (known-answer tests)
+  uint64_t blind[11 * 2 * HR::N];
+  if (h_blind) memcpy(blind, h_blind, sizeof(blind));
+  else for (int i = 0; i < 11; i++) CS_TRY(cs_rep3_state_rand(state, cv, blind + (size_t)i * 2 * HR::N));
+  cs_rep3_prf prf;
+  CS_TRY(cs_rep3_state_prf(state, &prf));
+  // whatever happens below, the streams move past what the device kernels may have consumed: PRF output is never reused
+  struct Advance {
+    cs_plonk_rep3* s; cs_rep3_state* st;
+    ~Advance() { cs_rep3_state_advance(st, cs_plonk_rep3_prf_words(s)); }
+  } advance{s, state};
+
+  auto open_points = [&](uint64_t* p, int k) -> int {  // open_point_vec_g1: every party adds the three partial points
+    std::vector<uint64_t> a(k * pl), b(k * pl);
+    CS_TRY(cs_net_send(net, nx, p, k * pl * 8));
+    CS_TRY(cs_net_send(net, pv, p, k * pl * 8));
+    CS_TRY(cs_net_recv(net, pv, a.data(), k * pl * 8));
+    CS_TRY(cs_net_recv(net, nx, b.data(), k * pl * 8));
+    for (int i = 0; i < k; i++) {
+      A1 x, y, z;
+      memcpy(&x, p + i * pl, sizeof(x)); memcpy(&y, a.data() + i * pl, sizeof(y)); memcpy(&z, b.data() + i * pl, sizeof(z));
+      A1 r = host::haffine(host::hadd(host::hadd(X1::from_affine(x), X1::from_affine(y)), X1::from_affine(z)));
+      memcpy(p + i * pl, &r, sizeof(r));
+    }
+    return 0;
+  };
+  auto open_scalars = [&](uint64_t* v, int k) -> int {  // open_vec on a handful of values
+    std::vector<uint64_t> a(k * HR::N), b(k * HR::N);
+    CS_TRY(cs_net_send(net, nx, v, k * HR::N * 8));
+    CS_TRY(cs_net_send(net, pv, v, k * HR::N * 8));
+    CS_TRY(cs_net_recv(net, pv, a.data(), k * HR::N * 8));
+    CS_TRY(cs_net_recv(net, nx, b.data(), k * HR::N * 8));
+    for (int i = 0; i < k; i++) {
+      HR x, y, z;
+      memcpy(x.l, v + i * HR::N, sizeof(x.l)); memcpy(y.l, a.data() + i * HR::N, sizeof(y.l)); memcpy(z.l, b.data() + i * HR::N, sizeof(z.l));
+      x = x + y + z;
+      memcpy(v + i * HR::N, x.l, sizeof(x.l));
+    }
+    return 0;
+  };
+  void *d_out_v = nullptr, *d_in_v = nullptr;
+  CS_TRY(cs_plonk_rep3_io(s, &d_out_v, &d_in_v));
+  uint64_t* d_out = (uint64_t*)d_out_v;
+  uint64_t* d_in = (uint64_t*)d_in_v;
+  auto open_device_vector = [&](size_t m) -> int {  // sum of the parties' additive vectors at d_out -> d_in
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s->peer_out[0]) {
+      CS_TRY(r3_token_round(net));  // all three vectors are complete
+      CS_TRY(cs_vec_add(ctx, cv, d_out, (const uint64_t*)s->peer_out[0], d_in, m));
+      CS_TRY(cs_vec_add(ctx, cv, d_in, (const uint64_t*)s->peer_out[1], d_in, m));
+      CS_CUDA(cudaStreamSynchronize(ctx->stream));
+      net->bytes_sent += 2 * m * 32;  // what the two peers pulled from this party over NVLink
+      return r3_token_round(net);     // nobody overwrites its vector while a peer still reads it
+    }
+    std::vector<uint64_t> mine(m * HR::N), a(m * HR::N), b(m * HR::N);
+    CS_CUDA(cudaMemcpyAsync(mine.data(), d_out, m * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    // ring order with both directions progressing: messages may exceed the mailbox credit window
+    CS_TRY(cs_net_sendrecv(net, nx, mine.data(), m * 32, pv, a.data(), m * 32));
+    CS_TRY(cs_net_sendrecv(net, pv, mine.data(), m * 32, nx, b.data(), m * 32));
+    DevBuf da, db;
+    int rc = da.reserve(m * 32);
+    if (!rc) rc = db.reserve(m * 32);
+    if (!rc) {
+      cudaMemcpyAsync(da.p, a.data(), m * 32, cudaMemcpyHostToDevice, ctx->stream);
+      cudaMemcpyAsync(db.p, b.data(), m * 32, cudaMemcpyHostToDevice, ctx->stream);
+      rc = cs_vec_add(ctx, cv, d_out, da.as<uint64_t>(), d_in, m);
+      if (!rc) rc = cs_vec_add(ctx, cv, d_in, db.as<uint64_t>(), d_in, m);
+      cudaStreamSynchronize(ctx->stream);
+    }
+    da.release(); db.release();
+    return rc;
+  };
+  auto reshare = [&](std::initializer_list<int> slots, size_t count) -> int {
+    CS_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (s->next_arena) return r3_token_round(net);
+    // staged: the a-halves of every slot go to the next party, the previous party's arrive as our b-halves
+    std::vector<uint64_t> za(count * HR::N), zb(count * HR::N);
+    DevBuf d;
+    CS_TRY(d.reserve(count * 32));
+    int rc = 0;
+    for (int k : slots) {
+      uint8_t* base = (uint8_t*)s->arena.p + (size_t)k * s->slot_words * 4;
+      cudaMemcpy2DAsync(za.data(), 32, base, 64, 32, count, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      rc = cs_net_sendrecv(net, nx, za.data(), count * 32, pv, zb.data(), count * 32);
+      if (rc) break;
+      cudaMemcpyAsync(d.p, zb.data(), count * 32, cudaMemcpyHostToDevice, ctx->stream);
+      rc = cs_rep3_set_b(ctx, cv, d.as<uint64_t>(), count, (uint64_t*)base);
+      if (rc) break;
+      cudaStreamSynchronize(ctx->stream);
+    }
+    d.release();
+    return rc;
+  };
+  auto step = [&](int st, const uint64_t* in, uint64_t* out) { return cs_plonk_rep3_step(s, st, in, out); };
+  auto scalar = [](const uint64_t* p) { HR v; memcpy(v.l, p, sizeof(v.l)); return v; };
+
+  uint64_t* pts = out_points;  // A B C Z T1 T2 T3 Wxi Wxiw
+  // ---- round 1
+  CS_TRY(cs_plonk_rep3_round1(s, &prf, h_pub, n_pub, h_wit, n_wit, blind, pts));
+  CS_TRY(open_points(pts, 3));
+  // ---- round 2 (challenges: round2.rs:226-245)
+  Transcript<Cfg> t;
+  for (int i = 0; i < 8; i++) t.add_point(pk->vk_points.data() + i * pl);
+  for (size_t i = 1; i < n_pub; i++) t.add_scalar(scalar(h_pub + i * HR::N));
+  for (int i = 0; i < 3; i++) t.add_point(pts + i * pl);
+  const HR beta = t.get_challenge();
+  t = Transcript<Cfg>();
+  t.add_scalar(beta);
+  const HR gamma = t.get_challenge();
+  uint64_t bg[2 * HR::N];
+  memcpy(bg, beta.l, sizeof(beta.l)); memcpy(bg + HR::N, gamma.l, sizeof(gamma.l));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_A, bg, nullptr)); CS_TRY(reshare({0, 1}, n));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_B, nullptr, nullptr)); CS_TRY(reshare({2, 3}, n));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_C, nullptr, nullptr));
+  CS_TRY(open_device_vector(2 * n + 1));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_D, nullptr, nullptr)); CS_TRY(reshare({4, 5}, n));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_E, nullptr, nullptr)); CS_TRY(reshare({6}, n));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_F, nullptr, nullptr));
+  CS_TRY(open_device_vector(n));
+  CS_TRY(step(CS_PLONK_R3_ROUND2_G, nullptr, pts + 3 * pl));
+  CS_TRY(open_points(pts + 3 * pl, 1));
+  // ---- round 3
+  t = Transcript<Cfg>();
+  t.add_scalar(beta); t.add_scalar(gamma); t.add_point(pts + 3 * pl);
+  const HR alpha = t.get_challenge();
+  CS_TRY(step(CS_PLONK_R3_ROUND3_A, alpha.l, nullptr));
+  CS_TRY(reshare({0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11}, 4 * n));
+  CS_TRY(step(CS_PLONK_R3_ROUND3_B, nullptr, pts + 4 * pl));
+  CS_TRY(open_points(pts + 4 * pl, 3));
+  // ---- round 4
+  t = Transcript<Cfg>();
+  t.add_scalar(alpha);
+  for (int i = 4; i < 7; i++) t.add_point(pts + i * pl);
+  const HR xi = t.get_challenge();
+  uint64_t ev[6 * HR::N];  // partial a b c zw | public s1 s2
+  CS_TRY(step(CS_PLONK_R3_ROUND4, xi.l, ev));
+  CS_TRY(open_scalars(ev, 4));
+  const HR ea = scalar(ev), eb = scalar(ev + HR::N), ec = scalar(ev + 2 * HR::N), ezw = scalar(ev + 3 * HR::N),
+           es1 = scalar(ev + 4 * HR::N), es2 = scalar(ev + 5 * HR::N);
+  // ---- round 5
+  t = Transcript<Cfg>();
+  const HR order[7] = {xi, ea, eb, ec, es1, es2, ezw};
+  for (const HR& x : order) t.add_scalar(x);
+  const HR v0 = t.get_challenge();
+  const HR in5[8] = {xi, v0, ea, eb, ec, es1, es2, ezw};
+  uint64_t in5l[8 * HR::N];
+  for (int i = 0; i < 8; i++) memcpy(in5l + i * HR::N, in5[i].l, sizeof(in5[i].l));
+  CS_TRY(step(CS_PLONK_R3_ROUND5, in5l, pts + 7 * pl));
+  CS_TRY(open_points(pts + 7 * pl, 2));
+  const HR evs[6] = {ea, eb, ec, es1, es2, ezw};
+  for (int i = 0; i < 6; i++) memcpy(out_evals + i * HR::N, evs[i].l, sizeof(evs[i].l));
+  return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
 int cs_plonk_pk_create(cs_ctx* ctx, const cs_plonk_key_desc* d, cs_plonk_pk** out) {
@@ -999,5 +1190,29 @@ int cs_plonk_rep3_step(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_
 }
 
 uint64_t cs_plonk_rep3_prf_words(const cs_plonk_rep3* s) { return s ? 8 * s->ctr : 0; }
+
+int cs_plonk_rep3_connect_io(cs_plonk_rep3* s, void* d_prev_out, void* d_next_out) {
+  if (!s) return fail(CS_ERR_ARG, "cs_plonk_rep3_connect_io: NULL argument");
+  if ((d_prev_out == nullptr) != (d_next_out == nullptr)) return fail(CS_ERR_ARG, "cs_plonk_rep3_connect_io: give both peers or neither");
+  s->peer_out[0] = reinterpret_cast<const uint32_t*>(d_prev_out);
+  s->peer_out[1] = reinterpret_cast<const uint32_t*>(d_next_out);
+  return 0;
+}
+
+int cs_plonk_rep3_prove(cs_plonk_rep3* s, cs_net* net, cs_rep3_state* state, const uint64_t* h_public_inputs, size_t n_public_inputs,
+                        const uint64_t* h_witness_shares, size_t n_witness, const uint64_t* h_blinder_shares, uint64_t* out_points,
+                        uint64_t* out_evals) {
+  if (!s || !net || !state || !h_public_inputs || !out_points || !out_evals || (n_witness && !h_witness_shares))
+    return fail(CS_ERR_ARG, "cs_plonk_rep3_prove: NULL argument");
+  if (net->n != 3 || net->id != s->party) return fail(CS_ERR_ARG, "cs_plonk_rep3_prove: the net is party %d of %d, the session is party %d of 3", net->id, net->n, s->party);
+  CS_CUDA(cudaSetDevice(s->ctx->device));
+  switch (s->pk->curve) {
+    case CS_BN254: return r3_prove_t<Bn254Cfg>(s, net, state, h_public_inputs, n_public_inputs, h_witness_shares, n_witness, h_blinder_shares, out_points, out_evals);
+#if defined(CS_ENABLE_BLS12_381)
+    case CS_BLS12_381: return r3_prove_t<Bls381Cfg>(s, net, state, h_public_inputs, n_public_inputs, h_witness_shares, n_witness, h_blinder_shares, out_points, out_evals);
+#endif
+    default: return fail(CS_ERR_ARG, "unsupported curve id %d", s->pk->curve);
+  }
+}
 
 }  // extern "C"

@@ -580,6 +580,22 @@ int cs_plonk_rep3_round1(cs_plonk_rep3* s, const cs_rep3_prf* prf, const uint64_
                          uint64_t* out_points);
 int cs_plonk_rep3_step(cs_plonk_rep3* s, int step, const uint64_t* h_in, uint64_t* h_out);
 uint64_t cs_plonk_rep3_prf_words(const cs_plonk_rep3* s);
+
+/* The previous and the next party's additive-out vectors (their cs_plonk_rep3_io d_additive_out; CUDA-IPC-mapped or
+ * same-process pointers): openings of n-sized vectors then READ THE PEERS' HBM (two vector additions over NVLink,
+ * fenced by token rounds) instead of travelling through the net.  NULL, NULL = through the net. */
+int cs_plonk_rep3_connect_io(cs_plonk_rep3* s, void* d_prev_out, void* d_next_out);
+
+/* Rep3CoPlonk::prove for one party (co-plonk/src/lib.rs:222-240; prove_inner :80-115; openings mpc/rep3.rs:113-138):
+ * the whole step sequence above, the Keccak-256 transcript (types.rs:140-190) and the openings, inside the library
+ * over `net` (3 parties; the session's party id must equal the net's).  `state`: the party's correlated streams -- the
+ * eleven round-1 blinder shares are drawn from it with T::rand unless h_blinder_shares (11 x {a, b}) is given, the
+ * device kernels draw their masks from the positions that follow, and the streams are advanced past everything
+ * consumed even when the call fails.  out_points: A B C Z T1 T2 T3 Wxi Wxiw (affine, Montgomery); out_evals:
+ * eval_a eval_b eval_c eval_s1 eval_s2 eval_zw.  Every party returns the same opened proof. */
+int cs_plonk_rep3_prove(cs_plonk_rep3* s, cs_net* net, cs_rep3_state* state, const uint64_t* h_public_inputs,
+                        size_t n_public_inputs, const uint64_t* h_witness_shares, size_t n_witness,
+                        const uint64_t* h_blinder_shares, uint64_t* out_points, uint64_t* out_evals);
 /* sha3::Keccak256 of a host buffer (the transcript hash, types.rs:13-14); test hook. */
 int cs_keccak256(const uint8_t* data, size_t len, uint8_t* out32);
 
