@@ -211,7 +211,10 @@ def plonk_rep3_block(args, rank, local_rank):
     sys.path.insert(0, os.path.join(ROOT, "tools"))
     import time_co_plonk as T
     lg = args.plonk_log_n
-    res = T.measure_group(group, local_rank, [lg], reps=3)
+    try:
+        res = T.measure_group(group, local_rank, [lg], reps=3)
+    except Exception as e:  # noqa: BLE001  -- the Groth16 line must still be printed
+        return {"error": "%s: %s" % (type(e).__name__, e)} if rank == 0 else None
     if res is None:
         return None
     r = res["2p%d" % lg]
