@@ -441,6 +441,9 @@ def check_rep3_mask_prf(ctx, n=100):
     assert list(ks) == OC.keystream_words(key, 5 * 16, 48, 12)
     ks20 = ctx.chacha_keystream(key, 1, 20, 1)
     assert list(ks20) == OC.block(struct.unpack("<8I", key), 1, 0, 20)
+    # published known answer (draft-strombergson-chacha-test-vectors-01, TC1, 12 rounds: zero key, block 0)
+    assert bytes(np.asarray(ctx.chacha_keystream(bytes(32), 0, 12, 1), dtype="<u4").tobytes()).hex().startswith(
+        "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f")
     seeds = [bytes((7 * p + i) & 0xff for i in range(32)) for p in range(3)]
     pos = [16, 3, 40]  # word positions, deliberately not block-aligned
     tot = [0] * n

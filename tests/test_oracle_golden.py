@@ -199,3 +199,25 @@ def test_plonk_prover_bls12_381_poseidon_against_round1_kat_and_verifier():
     assert [pr["a"], pr["b"], pr["c"]] == [gp1(P) for P in g["expected_commitments"]]
     vk = F.read_plonk_vk_json(base + "verification_key.json")
     assert OP.verify(BLS12_381, vk, pr, [int(x) for x in json.load(open(base + "public.json"))], ppio)
+
+
+def test_chacha_published_known_answers():
+    """The ChaCha block function behind Rep3Rand (ChaCha12Rng) against PUBLISHED known answers: test vector TC1 (all-zero
+    256-bit key and IV, block 0) of draft-strombergson-chacha-test-vectors-01 for 20, 12 and 8 rounds.  rand_chacha's
+    own tests (chacha.rs, test_chacha_true_values_a) use the same 20-round block for a zero seed: first words
+    0xade0b876, 0x903df1a0, 0xe56a5d40, 0x28bd8653 -- i.e. seed = key, 64-bit block counter from 0, stream 0, words in
+    keystream order, which is the layout oracle/chacha.py and csrc/cs_prf.cuh assume for the 12-round generator."""
+    import struct
+    from oracle import chacha as OC
+    kat = {
+        20: "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+            "da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586",
+        12: "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f"
+            "0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be",
+        8: "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e"
+           "984ce172b9216f419f445367456d5619314a42a3da86b001387bfdb80e0cfe42",
+    }
+    for rounds, hexs in kat.items():
+        w = OC.block((0,) * 8, 0, 0, rounds)
+        assert b"".join(struct.pack("<I", x) for x in w).hex() == hexs, rounds
+    assert OC.keystream_words(bytes(32), 0, 4, 20) == [0xade0b876, 0x903df1a0, 0xe56a5d40, 0x28bd8653]
