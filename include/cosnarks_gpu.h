@@ -657,7 +657,9 @@ typedef struct {
  *   prf (Rep3, optional): the party's two ChaCha12 streams; words [pos, pos + 48) of each become one zero share per
  *         r0 evaluation (the reference masks every product inside local_mul_vec; only the sum reaches the protocol).
  *         The caller advances both streams by 48 words.  NULL: no mask (tests).
- * Edges whose q_arith is zero contribute zero, which is what the reference's can_skip filter leaves out. */
+ * Edges whose q_arith is zero contribute zero, which is what the reference's can_skip filter leaves out.
+ * Shamir parties call this with CS_PLAIN on their degree-t shares: public terms enter every party's share, products
+ * are local, so h_r0 is a degree-2t sharing (degree_reduce next) and h_r1 a degree-t sharing. */
 int cs_sumcheck_arith_round(cs_ctx* ctx, cs_curve curve, cs_share_kind kind, int party, const cs_honk_arith_polys* d_polys,
                             size_t round_size, const uint64_t* d_beta_products, size_t periodicity, const cs_rep3_prf* prf,
                             uint64_t* h_r0, uint64_t* h_r1);

@@ -1213,6 +1213,29 @@ def check_sumcheck(ctx, log_n=5, seed=51, curve="bn254"):
     assert tot0 == exp0 and tot0m == exp0 and tot1 == exp1  # the parties' accumulators open to the plain ones
     assert all(views[i][k][1] == views[(i + 2) % 3][k][0] for i in range(3) for k in range(5))  # r1 stays replicated
 
+    # ---- Shamir(3, 1) parties run the PLAIN kernel on their degree-t shares (co-noir-common/src/mpc/shamir.rs: public
+    # values are added by every party, products are local and raise the degree): r0 comes out as a degree-2t sharing
+    # (what degree_reduce takes next), r1 as a degree-t sharing
+    def shamir_share(vals, t=1, nparties=3):
+        out = [[] for _ in range(nparties)]
+        for v in vals:
+            co = [v] + [rng.randrange(r) for _ in range(t)]
+            for i in range(nparties):
+                out[i].append(sum(c * pow(i + 1, k, r) for k, c in enumerate(co)) % r)
+        return out
+    sh_sh = {nm: shamir_share(polys[nm]) for nm in names_w}
+    got = []
+    for i in range(3):
+        d_sh = dict({nm: dev(cv.fr(sh_sh[nm][i])) for nm in names_w}, **{nm: d_plain[nm] for nm in names_q})
+        g0, g1 = ctx.sumcheck_arith_round(cv.id, B.CS_PLAIN, 0, d_sh, n, d_beta, 2)
+        got.append((cv.fr_back(g0), cv.fr_back(g1)))
+    lag3 = [_lagrange_basis_at(xs_=[1, 2, 3], i=i, x=0, r=r) for i in range(3)]   # 2t + 1 = 3 points: degree 2t
+    lag2 = [_lagrange_basis_at(xs_=[1, 2], i=i, x=0, r=r) for i in range(2)]      # t + 1 = 2 points: degree t
+    assert [sum(l * got[i][0][k] for i, l in enumerate(lag3)) % r for k in range(6)] == exp0
+    assert [sum(l * got[i][1][k] for i, l in enumerate(lag2)) % r for k in range(5)] == exp1
+    assert [sum(l * got[i + 1][1][k] for i, l in enumerate(
+        [_lagrange_basis_at(xs_=[2, 3], i=j, x=0, r=r) for j in range(2)])) % r for k in range(5)] == exp1
+
     # ---- fold: public + shared batches against the oracle, down to one row (+ the zero the reference pushes)
     u0 = rng.randrange(r)
     for shared in (False, True):
@@ -1281,4 +1304,13 @@ def _lagrange_basis(n, i, x, r):
         if j != i:
             num = num * (x - j) % r
             den = den * (i - j) % r
+    return num * pow(den, -1, r) % r
+
+
+def _lagrange_basis_at(xs_, i, x, r):
+    num, den = 1, 1
+    for j, xj in enumerate(xs_):
+        if j != i:
+            num = num * (x - xj) % r
+            den = den * (xs_[i] - xj) % r
     return num * pow(den, -1, r) % r
