@@ -178,6 +178,10 @@ CS_D void padd(Xyzz<F>& acc, const Xyzz<F>& q) {
 template <class P>
 CS_D Fp<P> shfl_down(const Fp<P>& a, unsigned delta) {
   Fp<P> r;
+#if defined(CS_EMU)  // test emulation: one block-wide exchange per element instead of one per 32-bit word
+  cs::emu::shfl_bytes(&a, &r, sizeof(r), 1, delta);
+  return r;
+#endif
   CS_UNROLL
   for (int i = 0; i < P::N; i++) r.l[i] = __shfl_down_sync(0xffffffffu, a.l[i], delta);
   return r;
