@@ -384,30 +384,29 @@ CS_GLOBAL void __launch_bounds__(128) k_msm_reduce_seg(const Xyzz<F>* __restrict
   red[t] = tot;
 }
 
-// Block b sums red[k] for k = b*T + t, stride gridDim.x*T, into out[b]: a warp-shuffle tree inside each warp (no
-// barriers, no shared-memory round trips), the warp results through shared memory, a second shuffle tree in warp 0.
-// Launched twice: many blocks, then one block over the block results.
+// A warp-shuffle version of this tree (five shuffle rounds per warp, then across the warps) was measured on B200 and
+// lost: every lane pays the full point addition in every round, and moving a 128/256-byte XYZZ point is 32/64 SHFL --
+// bucket reduction stage 0.399 ms against 0.329 ms for the tree below (profiles/r2_bench_final2_n1.json).
+// Block b sums red[k] for k = b*T + t, stride gridDim.x*T, into out[b] (shared-memory tree); launched
+// twice: many blocks, then one block over the block results.
 template <class F>
 CS_GLOBAL void k_msm_final_sum(const Xyzz<F>* __restrict__ red, uint32_t cnt,
                                                       Xyzz<F>* __restrict__ out) {
-  CS_DYN_SMEM(Xyzz<F>, sm);  // one entry per warp
-  const uint32_t T = blockDim.x, t = threadIdx.x, lane = t & 31, wid = t >> 5, nwarp = T >> 5;
+  CS_DYN_SMEM(Xyzz<F>, sm);
+  const uint32_t T = blockDim.x, t = threadIdx.x;
   Xyzz<F> acc = Xyzz<F>::inf();
   for (uint32_t k = blockIdx.x * T + t; k < cnt; k += gridDim.x * T) padd(acc, red[k]);
-  for (uint32_t d = 16; d > 0; d >>= 1) {
-    Xyzz<F> o = shfl_down(acc, d);
-    padd(acc, o);
-  }
-  if (lane == 0) sm[wid] = acc;
+  sm[t] = acc;
   __syncthreads();
-  // every warp runs the second tree (uniform control flow around the shuffles; the CPU emulation of the tests needs
-  // all threads of the block in each exchange), warp 0 writes the result
-  acc = lane < nwarp ? sm[lane] : Xyzz<F>::inf();
-  for (uint32_t d = 16; d > 0; d >>= 1) {
-    Xyzz<F> o = shfl_down(acc, d);
-    padd(acc, o);
+  for (uint32_t step = T >> 1; step > 0; step >>= 1) {
+    if (t < step) {
+      Xyzz<F> a = sm[t];
+      padd(a, sm[t + step]);
+      sm[t] = a;
+    }
+    __syncthreads();
   }
-  if (t == 0) out[blockIdx.x] = acc;
+  if (t == 0) out[blockIdx.x] = sm[0];
 }
 
 // --------------------------------------------------------------------------- table precomputation
@@ -577,18 +576,8 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
   CS_TRY(ws.bucket.reserve((size_t)nb1 * sizeof(Xyzz<F>)));
   const uint32_t L = sh.B < MSM_RED_SEG ? sh.B : MSM_RED_SEG;
   const uint32_t nseg = (sh.B + L - 1) / L;
-#if defined(CS_EMU)
-  // the CPU emulation runs one host thread per CUDA thread and every shuffle is a block-wide barrier: two warps keep
-  // both stages of the tree (inside a warp, across warps) under test without 256-thread barriers on a few cores
-  const uint32_t fs_threads = 64;
-#else
-  const uint32_t fs_threads = sizeof(Xyzz<F>) > 128 ? 128 : 256;
-#endif
-#if defined(CS_EMU)
-  const uint32_t fs_blocks = nseg > 4 * fs_threads ? 2 : 1;  // few emulated blocks: each one costs ~20 host-thread barriers
-#else
+  const uint32_t fs_threads = sizeof(Xyzz<F>) > 128 ? 128 : 256;  // <= 32 KB of dynamic shared memory
   const uint32_t fs_blocks = nseg > 4 * fs_threads ? (nseg + fs_threads - 1) / fs_threads : 1;
-#endif
   CS_TRY(ws.red.reserve(((size_t)nseg + fs_blocks) * sizeof(Xyzz<F>)));
   CS_TRY(ws.result.reserve(sizeof(Xyzz<F>)));
   // slice order: slice_len | slice_bkt | order | order_b (max_s0 each) | block_hist | len_base
@@ -700,12 +689,12 @@ int msm_enqueue(MsmWorkspace& ws, const Affine<F>* table, const uint32_t* infmas
             ws.red.as<Xyzz<F>>());
   if (fs_blocks > 1) {
     Xyzz<F>* stage = ws.red.as<Xyzz<F>>() + nseg;
-    CS_LAUNCH_SYNC(k_msm_final_sum<F>, fs_blocks, fs_threads, (fs_threads / 32) * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
+    CS_LAUNCH_SYNC(k_msm_final_sum<F>, fs_blocks, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
                    stage);
-    CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, (fs_threads / 32) * sizeof(Xyzz<F>), st, stage, fs_blocks,
+    CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, stage, fs_blocks,
                    ws.result.as<Xyzz<F>>());
   } else {
-    CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, (fs_threads / 32) * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
+    CS_LAUNCH_SYNC(k_msm_final_sum<F>, 1, fs_threads, fs_threads * sizeof(Xyzz<F>), st, ws.red.as<Xyzz<F>>(), nseg,
                    ws.result.as<Xyzz<F>>());
   }
   CS_TRY(ws.mark(5, st));
