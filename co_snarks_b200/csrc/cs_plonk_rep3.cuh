@@ -239,7 +239,10 @@ CS_D void r3_mul4(const Sh<FrP>& ab, const Sh<FrP>& abp, const Sh<FrP>& apb, con
     rz = rz + x1 * cload<FrP>(K.z1[m]) + x2 * cload<FrP>(K.z2[m]) + x3 * cload<FrP>(K.z3[m]);
   }
 }
-// layer 2: additive shares of t and tz at every extended-domain point (compute_t, round3.rs:300-520)
+// layer 2: additive shares of t and tz at every extended-domain point (compute_t, round3.rs:300-520).
+// Operands are fetched where they are used (first-layer products from the arena, wire / z evaluations and their
+// blinding parts recomputed from the nine blinders): holding the twelve products and the ten point values at once
+// needed ~350 registers and spilled; the re-reads hit L1/L2.
 template <class FrP>
 CS_GLOBAL void k_r3_quot_l2(R3QuotIn in, R3Blinders B, R3KeyEvals E, uint32_t n, uint32_t nlag, PlonkConsts K, int party,
                              PrfArgs P, uint64_t mbase, const uint32_t* arena, size_t slot_words, uint32_t* t_out,
@@ -251,46 +254,53 @@ CS_GLOBAL void k_r3_quot_l2(R3QuotIn in, R3Blinders B, R3KeyEvals E, uint32_t n,
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   const uint32_t m = i & 3;
-  R3Point<FrP> p = r3_point<FrP>(in, B, n, i);
-  S Pr[12];
-  for (int k = 0; k < 12; k++) Pr[k] = ld_sh<FrP>(arena + (size_t)k * slot_words, i);
-  F beta = cload<FrP>(K.beta), gamma = cload<FrP>(K.gamma), alpha = cload<FrP>(K.alpha);
-  F qm = ld_fr<FrP>(E.qm + (size_t)i * NW), ql = ld_fr<FrP>(E.ql + (size_t)i * NW), qr = ld_fr<FrP>(E.qr + (size_t)i * NW),
-    qo = ld_fr<FrP>(E.qo + (size_t)i * NW);
+  const F w = root_pow<FrP>(in.tw4, 2 * n, i);
+  auto PR = [&](int k) { return ld_sh<FrP>(arena + (size_t)k * slot_words, i); };
+  auto lin = [&](int hi, int lo) { return sh_add<FrP>(sh_const<FrP>(B.b[lo]), sh_mulp<FrP>(sh_const<FrP>(B.b[hi]), w)); };
+  auto quad = [&](const F& x) {  // b6 x^2 + b7 x + b8
+    return sh_add<FrP>(sh_add<FrP>(sh_mulp<FrP>(sh_const<FrP>(B.b[6]), x.sqr()), sh_mulp<FrP>(sh_const<FrP>(B.b[7]), x)), sh_const<FrP>(B.b[8]));
+  };
+  const F beta = cload<FrP>(K.beta), gamma = cload<FrP>(K.gamma);
   // e1, e1z: linear in the first-layer products -> this party's additive part is the .a component
-  F e1 = Pr[0].a * qm + p.a.a * ql + p.b.a * qr + p.c.a * qo;
-  F a0 = Pr[1].a + Pr[2].a;
-  if (m) a0 = a0 + Pr[3].a * cload<FrP>(K.z1[m]);
-  F e1z = a0 * qm + p.ap.a * ql + p.bp.a * qr + p.cp.a * qo;
-  for (uint32_t j = 0; j < nlag; j++)
-    e1 = e1 - ld_fr<FrP>(E.buf_a + (size_t)(2 * j) * NW) * ld_fr<FrP>(E.lagrange + ((size_t)j * n4 + i) * NW);
-  if (party == 0) e1 = e1 + ld_fr<FrP>(E.qc + (size_t)i * NW);
+  F e1, e1z;
+  {
+    const F qm = ld_fr<FrP>(E.qm + (size_t)i * NW), ql = ld_fr<FrP>(E.ql + (size_t)i * NW), qr = ld_fr<FrP>(E.qr + (size_t)i * NW),
+            qo = ld_fr<FrP>(E.qo + (size_t)i * NW);
+    e1 = PR(0).a * qm + ld_sh<FrP>(in.a, i).a * ql + ld_sh<FrP>(in.b, i).a * qr + ld_sh<FrP>(in.c, i).a * qo;
+    F a0 = PR(1).a + PR(2).a;
+    if (m) a0 = a0 + PR(3).a * cload<FrP>(K.z1[m]);
+    e1z = a0 * qm + lin(0, 1).a * ql + lin(2, 3).a * qr + lin(4, 5).a * qo;
+    for (uint32_t j = 0; j < nlag; j++)
+      e1 = e1 - ld_fr<FrP>(E.buf_a + (size_t)(2 * j) * NW) * ld_fr<FrP>(E.lagrange + ((size_t)j * n4 + i) * NW);
+    if (party == 0) e1 = e1 + ld_fr<FrP>(E.qc + (size_t)i * NW);
+  }
   // e2: (a + oa)(b + ob)(c + oc) z with oa = beta w + gamma, ...
-  F bw = beta * p.w;
-  F oa = bw + gamma, ob = bw * cload<FrP>(K.k1) + gamma, oc = bw * cload<FrP>(K.k2) + gamma;
   F e2, e2z, e3, e3z;
   {
-    S ab = sh_addp<FrP>(sh_add<FrP>(Pr[0], sh_add<FrP>(sh_mulp<FrP>(p.a, ob), sh_mulp<FrP>(p.b, oa))), oa * ob, party);
-    S abp = sh_add<FrP>(Pr[1], sh_mulp<FrP>(p.bp, oa));
-    S apb = sh_add<FrP>(Pr[2], sh_mulp<FrP>(p.ap, ob));
-    S cd = sh_add<FrP>(Pr[4], sh_mulp<FrP>(p.z, oc));
-    S cdp = sh_add<FrP>(Pr[5], sh_mulp<FrP>(p.zp, oc));
-    r3_mul4<FrP>(ab, abp, apb, Pr[3], cd, cdp, Pr[6], Pr[7], m, K, e2, e2z);
+    const F bw = beta * w;
+    const F oa = bw + gamma, ob = bw * cload<FrP>(K.k1) + gamma, oc = bw * cload<FrP>(K.k2) + gamma;
+    S ab = sh_addp<FrP>(sh_add<FrP>(PR(0), sh_add<FrP>(sh_mulp<FrP>(ld_sh<FrP>(in.a, i), ob), sh_mulp<FrP>(ld_sh<FrP>(in.b, i), oa))), oa * ob, party);
+    S abp = sh_add<FrP>(PR(1), sh_mulp<FrP>(lin(2, 3), oa));
+    S apb = sh_add<FrP>(PR(2), sh_mulp<FrP>(lin(0, 1), ob));
+    S cd = sh_add<FrP>(PR(4), sh_mulp<FrP>(ld_sh<FrP>(in.z, i), oc));
+    S cdp = sh_add<FrP>(PR(5), sh_mulp<FrP>(quad(w), oc));
+    r3_mul4<FrP>(ab, abp, apb, PR(3), cd, cdp, PR(6), PR(7), m, K, e2, e2z);
   }
   {
-    F o1 = ld_fr<FrP>(E.s1 + (size_t)i * NW) * beta + gamma, o2 = ld_fr<FrP>(E.s2 + (size_t)i * NW) * beta + gamma,
-      o3 = ld_fr<FrP>(E.s3 + (size_t)i * NW) * beta + gamma;
-    S ab = sh_addp<FrP>(sh_add<FrP>(Pr[0], sh_add<FrP>(sh_mulp<FrP>(p.a, o2), sh_mulp<FrP>(p.b, o1))), o1 * o2, party);
-    S abp = sh_add<FrP>(Pr[1], sh_mulp<FrP>(p.bp, o1));
-    S apb = sh_add<FrP>(Pr[2], sh_mulp<FrP>(p.ap, o2));
-    S cd = sh_add<FrP>(Pr[8], sh_mulp<FrP>(p.zw, o3));
-    S cdp = sh_add<FrP>(Pr[9], sh_mulp<FrP>(p.zwp, o3));
-    r3_mul4<FrP>(ab, abp, apb, Pr[3], cd, cdp, Pr[10], Pr[11], m, K, e3, e3z);
+    const F o1 = ld_fr<FrP>(E.s1 + (size_t)i * NW) * beta + gamma, o2 = ld_fr<FrP>(E.s2 + (size_t)i * NW) * beta + gamma,
+            o3 = ld_fr<FrP>(E.s3 + (size_t)i * NW) * beta + gamma;
+    S ab = sh_addp<FrP>(sh_add<FrP>(PR(0), sh_add<FrP>(sh_mulp<FrP>(ld_sh<FrP>(in.a, i), o2), sh_mulp<FrP>(ld_sh<FrP>(in.b, i), o1))), o1 * o2, party);
+    S abp = sh_add<FrP>(PR(1), sh_mulp<FrP>(lin(2, 3), o1));
+    S apb = sh_add<FrP>(PR(2), sh_mulp<FrP>(lin(0, 1), o2));
+    S cd = sh_add<FrP>(PR(8), sh_mulp<FrP>(ld_sh<FrP>(in.z, (i + 4) % n4), o3));
+    S cdp = sh_add<FrP>(PR(9), sh_mulp<FrP>(quad(root_pow<FrP>(in.tw4, 2 * n, (i + 4) % n4)), o3));
+    r3_mul4<FrP>(ab, abp, apb, PR(3), cd, cdp, PR(10), PR(11), m, K, e3, e3z);
   }
-  F l0a2 = ld_fr<FrP>(E.lagrange + (size_t)i * NW) * cload<FrP>(K.alpha2);
-  F zm1 = p.z.a;
+  const F alpha = cload<FrP>(K.alpha);
+  const F l0a2 = ld_fr<FrP>(E.lagrange + (size_t)i * NW) * cload<FrP>(K.alpha2);
+  F zm1 = ld_sh<FrP>(in.z, i).a;
   if (party == 0) zm1 = zm1 - F::one();
-  F e4 = zm1 * l0a2, e4z = p.zp.a * l0a2;
+  const F e4 = zm1 * l0a2, e4z = quad(w).a * l0a2;
   st_fr<FrP>(t_out + (size_t)i * NW, e1 + (e2 - e3) * alpha + e4 + prf_mask<FrP>(P, mbase + i));
   st_fr<FrP>(tz_out + (size_t)i * NW, e1z + (e2z - e3z) * alpha + e4z + prf_mask<FrP>(P, mbase + n4 + i));
 }
