@@ -124,6 +124,28 @@ struct Plonk {
 };
 
 struct Rep3CoPlonk {
+  // The same through the library's own party driver (cs_plonk_rep3_prove: step sequence, transcript and openings in
+  // C++ inside libcosnarks_gpu.so) over any mpc_net::Network via the NetAdapter callbacks; correlated randomness =
+  // Rep3State::new over `net`.  `blinders` == nullptr: Round1Challenges::random (eleven T::rand shares).
+  static PlonkProof prove_in_library(Context& ctx, mpc_net::Network& net, Zkey& zkey, const SharedWitness<Rep3PrimeFieldShare>& w,
+                                     const std::array<Rep3PrimeFieldShare, 11>* blinders = nullptr) {
+    check_witness_lengths(zkey, w.public_inputs.size(), w.witness.size());
+    co_groth16::NetAdapter adapter(net);
+    co_groth16::Rep3State state(adapter);
+    struct Session {
+      cs_plonk_rep3* h = nullptr;
+      ~Session() { cs_plonk_rep3_free(h); }
+    } s;
+    check(cs_plonk_rep3_create(ctx.h, zkey.h, (int)net.id(), &s.h));
+    // nothing connected: a-halves and opened vectors travel through `net` (parties on different hosts)
+    G1 pts[9];
+    Fr evs[6];
+    check(cs_plonk_rep3_prove(s.h, adapter.h, state.h, w.public_inputs[0].data(), w.public_inputs.size(),
+                              w.witness.empty() ? nullptr : w.witness[0].a.data(), w.witness.size(),
+                              blinders ? (*blinders)[0].a.data() : nullptr, pts[0].data(), evs[0].data()));
+    return assemble(pts, evs);
+  }
+
   // Rep3CoPlonk::prove(nets, zkey, witness)  (lib.rs:222-240).  One call per party (thread / process); `blinders`
   // = this party's shares of the eleven round-1 scalars (Round1Challenges::random draws them with T::rand).
   // The parties' GPUs exchange first-layer products through the arena of the next party (same-process pointer
