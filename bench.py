@@ -572,7 +572,7 @@ def run_ours(args):
                          "launch_ms": accum_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "int_pipe": {"achieved_gmodmul_s": gmul, "peak_gmodmul_s": gmul_peak, "frac": gmul / gmul_peak,
                                       "imad_wide_tops": imad_tops, "imad_wide_tops_source": "profiles/r2_pipe_probe.json (data-dependent operands)", "peak_source": peak_src,
-                                      "note": "the resource that actually bounds the kernel: 10 Montgomery products per mixed addition"}},
+                                      "note": "the resource that actually bounds the kernel: 10 Montgomery products per mixed addition, counted as 10 although two of them (R (Q - X3) - Y1 PPP) share one reduction (Fp::dot2, 1.5 product-equivalents of multiply work)"}},
             "msm": {"g1_2p%d_ms" % lg: msm_avg, "mscalar_per_s": nw / (msm_avg * 1e-3) / 1e6,
                     "stage_ms": {"digits": float(stage[0]), "sort": float(stage[1]), "accumulate": float(stage[2]),
                                  "fold": float(stage[3]), "reduce": float(stage[4])}},

@@ -56,6 +56,12 @@ struct Fp2 {
   }
 };
 
+// a b - c d: one fused reduction in the base field (Fp::dot2), two products in the extension
+template <class P>
+CS_D Fp<P> mul_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) { return Fp<P>::dot2(a, b, c.neg(), d); }
+template <class P>
+CS_D Fp2<P> mul_sub(const Fp2<P>& a, const Fp2<P>& b, const Fp2<P>& c, const Fp2<P>& d) { return a * b - c * d; }
+
 // Affine point; (0, 0) encodes infinity (never on y^2 = x^3 + b with b != 0) -- the same marker
 // snarkjs .zkey files use.
 template <class F>
@@ -94,7 +100,7 @@ CS_DN Xyzz<F> dbl_affine(const Affine<F>& p) {
   F X2 = p.x.sqr();
   F M = X2.dbl() + X2;
   r.x = M.sqr() - S.dbl();
-  r.y = M * (S - r.x) - W * p.y;
+  r.y = mul_sub(M, S - r.x, W, p.y);
   r.zz = V;
   r.zzz = W;
   return r;
@@ -112,7 +118,7 @@ CS_DN Xyzz<F> dbl_xyzz(const Xyzz<F>& p) {
   F X2 = p.x.sqr();
   F M = X2.dbl() + X2;
   r.x = M.sqr() - S.dbl();
-  r.y = M * (S - r.x) - W * p.y;
+  r.y = mul_sub(M, S - r.x, W, p.y);
   r.zz = V * p.zz;
   r.zzz = W * p.zzz;
   return r;
@@ -141,7 +147,7 @@ CS_D void madd(Xyzz<F>& acc, const Affine<F>& p_in, bool negate) {
   F PPP = Pp * PP;
   F Q = acc.x * PP;
   F X3 = R.sqr() - PPP - Q.dbl();
-  acc.y = R * (Q - X3) - acc.y * PPP;
+  acc.y = mul_sub(R, Q - X3, acc.y, PPP);
   acc.x = X3;
   acc.zz = acc.zz * PP;
   acc.zzz = acc.zzz * PPP;
@@ -167,7 +173,7 @@ CS_D void padd(Xyzz<F>& acc, const Xyzz<F>& q) {
   F PPP = Pp * PP;
   F Q = U1 * PP;
   F X3 = R.sqr() - PPP - Q.dbl();
-  acc.y = R * (Q - X3) - S1 * PPP;
+  acc.y = mul_sub(R, Q - X3, S1, PPP);
   acc.x = X3;
   acc.zz = acc.zz * q.zz * PP;
   acc.zzz = acc.zzz * q.zzz * PPP;

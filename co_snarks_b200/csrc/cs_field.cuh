@@ -215,6 +215,53 @@ struct Fp {
     return r;
   }
 
+  // a b + c d with ONE Montgomery reduction (product scanning: both partial-product sets and the reduction terms of
+  // a column meet in one 3-word accumulator): 2 N^2 + N^2 wide multiply-adds instead of the 4 N^2 of two products.
+  // Needs 2 p < 2^(32 N), true for every modulus here (254 / 255 / 381 bits in 256 / 256 / 384).
+  static CS_D Fp dot2(const Fp& a, const Fp& b, const Fp& c, const Fp& d) { return dot2_ool(a, b, c, d); }
+  static CS_DN Fp dot2_ool(Fp a, Fp b, Fp c, Fp d) {
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+    uint32_t m[N];
+    Fp r;
+    CS_UNROLL
+    for (int k = 0; k < 2 * N - 1; k++) {
+      CS_UNROLL
+      for (int i = 0; i < N; i++) {
+        const int j = k - i;
+        if (j >= 0 && j < N) {
+          c0 = mad_lo_cc(a.l[i], b.l[j], c0);
+          c1 = madc_hi_cc(a.l[i], b.l[j], c1);
+          c2 = addc(c2, 0);
+          c0 = mad_lo_cc(c.l[i], d.l[j], c0);
+          c1 = madc_hi_cc(c.l[i], d.l[j], c1);
+          c2 = addc(c2, 0);
+        }
+      }
+      // reduction terms m_i p_j, i + j = k, of the rows already determined (j >= 1)
+      CS_UNROLL
+      for (int i = 0; i < N; i++) {
+        const int j = k - i;
+        if (j >= 1 && j < N) {
+          c0 = mad_lo_cc(m[i], P::mod(j), c0);
+          c1 = madc_hi_cc(m[i], P::mod(j), c1);
+          c2 = addc(c2, 0);
+        }
+      }
+      if (k < N) {
+        m[k] = mul_lo(c0, P::M0);
+        c0 = mad_lo_cc(m[k], P::mod(0), c0);
+        c1 = madc_hi_cc(m[k], P::mod(0), c1);
+        c2 = addc(c2, 0);
+      } else {
+        r.l[k - N] = c0;
+      }
+      c0 = c1; c1 = c2; c2 = 0;
+    }
+    r.l[N - 1] = c0;
+    r.final_sub();
+    return r;
+  }
+
   // Montgomery <-> canonical
   CS_D Fp to_mont() const { return (*this) * r2(); }
   CS_D Fp from_mont() const {

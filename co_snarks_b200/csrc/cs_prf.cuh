@@ -175,7 +175,7 @@ CS_GLOBAL void k_rep3_mul_vec_reshare(const uint32_t* __restrict__ a, const uint
   if (i >= n) return;
   Fp<FrP> aa = ld_fr<FrP>(a + (2 * i) * NW), ab = ld_fr<FrP>(a + (2 * i + 1) * NW);
   Fp<FrP> ba = ld_fr<FrP>(b + (2 * i) * NW), bb = ld_fr<FrP>(b + (2 * i + 1) * NW);
-  Fp<FrP> z = aa * (ba + bb) + ab * ba;
+  Fp<FrP> z = Fp<FrP>::dot2(aa, ba + bb, ab, ba);  // one reduction for both products
   if (rounds) {
     Fp<FrP> m1 = prf_field_element<FrP>(keys.k, pos1 + 8 * i, rounds);
     Fp<FrP> m2 = prf_field_element<FrP>(keys.k + 8, pos2 + 8 * i, rounds);

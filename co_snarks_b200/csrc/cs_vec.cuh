@@ -62,7 +62,7 @@ CS_GLOBAL void k_rep3_local_mul(const uint32_t* __restrict__ a, const uint32_t* 
     Fp<FrP> aa = ld_fr<FrP>(a + (2 * i) * NW), ab = ld_fr<FrP>(a + (2 * i + 1) * NW);
     Fp<FrP> ba = ld_fr<FrP>(b + (2 * i) * NW), bb = ld_fr<FrP>(b + (2 * i + 1) * NW);
     // a.a*b.a + a.a*b.b + a.b*b.a  ==  a.a*(b.a + b.b) + a.b*b.a   (exact in the field)
-    Fp<FrP> z = aa * (ba + bb) + ab * ba;
+    Fp<FrP> z = Fp<FrP>::dot2(aa, ba + bb, ab, ba);  // one reduction for both products
     if (mask) z = z + ld_fr<FrP>(mask + i * NW);
     if (sub) z = z - ld_fr<FrP>(sub + i * NW);
     st_fr<FrP>(out + i * NW, z);
