@@ -5,6 +5,9 @@ The GPU counterpart of `co-circom generate-proof groth16|plonk` for the plain dr
 Groth16::plain_prove with fresh (r, s) or Plonk::plain_prove with fresh blinders (the protocol is read from
 the zkey), proof written in snarkjs' JSON layout (decimal strings, the layout of
 test_vectors/{Groth16,Plonk}/bn254/multiplier2/circom.proof) plus public.json.
+
+`python -m co_snarks_b200.prove --zkey circuit.zkey --rep3-shares s.0 s.1 s.2 --out proof.json` is
+`generate-proof groth16 --protocol REP3` for the three parties of one box, from their share files.
 """
 import struct
 import argparse
@@ -71,15 +74,81 @@ def plonk_proof_json(lib, pts, evs, curve=B.CS_BN254):
     return proof
 
 
+def prove_rep3_from_share_files(args):
+    """`co-circom generate-proof groth16 --protocol REP3` for all three parties on this box
+    (co-circom.rs:1005-1050): each party reads its CompressedRep3SharedWitness / Rep3SharedWitness share file
+    (cs_rep3_witness_read), holds its own context, device-resident key and OS-seeded correlated streams, and runs
+    Rep3CoGroth16::prove inside the library (cs_groth16_rep3_prove) over in-process mailbox nets; the parties are three
+    host threads sharing the GPU.  Every party must return the same opened proof."""
+    import threading
+    ctxs = [B.Context(args.device, lib_path=args.lib) for _ in range(3)]
+    lib = ctxs[0].lib
+    t0 = time.time()
+    pks = [B.Groth16Key.from_zkey(c, args.zkey) for c in ctxs]
+    cv = pks[0].curve
+    inputs = []
+    for i, path in enumerate(args.rep3_shares):
+        pub, sh, kind = B.read_rep3_witness(lib, path, cv)
+        if kind != B.CS_REP3:
+            raise SystemExit("%s holds additive shares: replicate them first (cs_rep3_replicate_additive)" % path)
+        if pub.shape[0] != pks[i].ni:
+            raise SystemExit("%s: %d public inputs, the key expects %d" % (path, pub.shape[0], pks[i].ni))
+        inputs.append((np.ascontiguousarray(pub), np.ascontiguousarray(sh)))
+    nets0 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    nets1 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
+    for i in range(3):
+        nets0[i].connect_local(nets0)
+        nets1[i].connect_local(nets1)
+    seeds = [B.os_random(lib, 32) for _ in range(3)]  # Rep3State::new: every party's seed, shared with the next party
+    states = [B.Rep3StateC.from_seeds(lib, i, seeds[i], seeds[(i + 2) % 3]) for i in range(3)]
+    t1 = time.time()
+    res, errs = {}, []
+
+    def party(i):
+        try:
+            res[i] = pks[i].rep3_prove(nets0[i], nets1[i], states[i], inputs[i][0], inputs[i][1])
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+    th = [threading.Thread(target=party, args=(i,)) for i in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    if errs:
+        raise errs[0]
+    t2 = time.time()
+    if not all(all((res[i][k] == res[0][k]).all() for k in range(3)) for i in (1, 2)):
+        raise SystemExit("the three parties opened different proofs")
+    A, Bp, C = res[0][:3]
+    with open(args.out, "w") as f:
+        json.dump(proof_json(lib, A, Bp, C, cv), f)
+    if args.public_out:
+        with open(args.public_out, "w") as f:
+            json.dump([str(x) for x in _canon(lib, inputs[0][0][1:], "fr", cv)], f)
+    print("keys+shares load %.1f ms, Generate proof took %.1f ms (3 parties, Rep3)" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3))
+    for x in states + nets0 + nets1 + pks:
+        x.free()
+    for c in ctxs:
+        c.close()
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     ap.add_argument("--zkey", required=True)
-    ap.add_argument("--wtns", required=True)
+    ap.add_argument("--wtns", default=None)
+    ap.add_argument("--rep3-shares", nargs=3, default=None, metavar=("PARTY0", "PARTY1", "PARTY2"),
+                    help="Groth16, 3-party Rep3: the three parties' share files (co-circom split-witness output) instead of --wtns")
     ap.add_argument("--out", default="proof.json")
     ap.add_argument("--public-out", default=None)
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--lib", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args(argv)
+    if args.rep3_shares:
+        if zkey_protocol(args.zkey) != 1:
+            raise SystemExit("--rep3-shares: Groth16 keys only")
+        return prove_rep3_from_share_files(args)
+    if not args.wtns:
+        raise SystemExit("give --wtns (plain prover) or --rep3-shares")
     ctx = B.Context(args.device, lib_path=args.lib)
     t0 = time.time()
     if zkey_protocol(args.zkey) == 2:

@@ -863,6 +863,37 @@ def check_prove_cli(ctx_lib_path, tmp_path, name="multiplier2"):
     assert json.load(open(out))["protocol"] == "groth16"
 
 
+def check_prove_cli_rep3_shares(ctx_lib_path, tmp_path, name="multiplier2"):
+    """The CLI in Rep3 mode: three share files (the bincode layout co-circom split-witness writes; party 1's previous
+    half given as a seed to exercise the compressed variant) in, one opened proof out, accepted under the fixture's
+    verification key -- tests/tests/circom/e2e_tests/rep3.rs:36-137 from files."""
+    import json
+    import os
+    import zkey_writer
+    from co_snarks_b200 import prove as P
+    from oracle.formats import read_proof_json
+    cv = Conv("bn254")
+    r = cv.r
+    z, m, w, g = golden_groth16(name)
+    ni = m["num_instance_variables"]
+    zp = os.path.join(str(tmp_path), "c3.zkey")
+    zkey_writer.write_zkey(zp, z, m)
+    wsh = OG.share_rep3(w[ni:], r, random.Random(61))
+    paths = []
+    for i in range(3):
+        pth = os.path.join(str(tmp_path), "shares.%d" % i)
+        write_rep3_share_file(pth, w[:ni], 0, wsh[i], r)
+        paths.append(pth)
+    out, pub = os.path.join(str(tmp_path), "proof3.json"), os.path.join(str(tmp_path), "public3.json")
+    argv = ["--zkey", zp, "--rep3-shares"] + paths + ["--out", out, "--public-out", pub]
+    if ctx_lib_path:
+        argv += ["--lib", ctx_lib_path]
+    P.main(argv)
+    public = [int(x) for x in json.load(open(pub))]
+    assert public == [ih(x) for x in g["public"]]
+    assert groth16_verify(OG.vk_from_zkey(z), public, read_proof_json(out))
+
+
 def check_prove_cli_plonk(ctx_lib_path, tmp_path, name="multiplier2"):
     """The same CLI on a Plonk zkey: snarkjs-layout Plonk proof.json accepted by Plonk::verify (plonk.rs:110-245)."""
     import json

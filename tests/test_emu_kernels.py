@@ -91,6 +91,7 @@ def test_emu_prove_cli(emu_ctx, tmp_path):
     import build_emu
     K.check_prove_cli(build_emu.OUT, tmp_path)
     K.check_prove_cli_plonk(build_emu.OUT, tmp_path)
+    K.check_prove_cli_rep3_shares(build_emu.OUT, tmp_path)
 
 
 def test_emu_libsnark_reduction(emu_ctx):
