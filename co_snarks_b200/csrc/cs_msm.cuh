@@ -411,19 +411,55 @@ CS_GLOBAL void k_msm_final_sum(const Xyzz<F>* __restrict__ red, uint32_t cnt,
 
 // --------------------------------------------------------------------------- table precomputation
 // table[w * n + i] = 2^(c w) * P_i  (affine), w = 0..W-1.  One thread per base point; runs once per
-// proving key (cs_bases_upload), off the per-proof path.
+// proving key (cs_bases_upload), off the per-proof path.  The affine conversions of up to MSM_PRE_CHUNK consecutive
+// windows share ONE field inversion (Montgomery's trick on their ZZZ values): 2 inversions of 356 products per base
+// at W = 16 instead of 15.
+constexpr int MSM_PRE_CHUNK = 8;
 template <class F>
 CS_GLOBAL void __launch_bounds__(128) k_msm_precompute(Affine<F>* __restrict__ table, uint32_t n,
                                                        uint32_t c, uint32_t W) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Affine<F> p = table[i];
+  if (p.is_inf()) {
+    for (uint32_t w = 1; w < W; w++) table[(size_t)w * n + i] = Affine<F>::inf();
+    return;
+  }
   Xyzz<F> cur = Xyzz<F>::from_affine(p);
-  for (uint32_t w = 1; w < W; w++) {
-    for (uint32_t k = 0; k < c; k++) cur = dbl_xyzz(cur);
-    Affine<F> a = to_affine(cur);
-    table[(size_t)w * n + i] = a;
-    cur = Xyzz<F>::from_affine(a);  // keeps ZZ = ZZZ = 1 so the next doublings stay cheap
+  uint32_t w = 1;
+  while (w < W) {
+    Xyzz<F> pts[MSM_PRE_CHUNK];
+    F pre[MSM_PRE_CHUNK];
+    int cnt = 0;
+    bool degenerate = false;
+    for (; cnt < MSM_PRE_CHUNK && w + cnt < W; cnt++) {
+      for (uint32_t k = 0; k < c; k++) cur = dbl_xyzz(cur);
+      pts[cnt] = cur;
+      degenerate = degenerate || cur.is_inf();
+    }
+    Affine<F> last;
+    if (degenerate) {  // a multiple hit the point at infinity (not on the curves in use): one inversion per point
+      for (int j = 0; j < cnt; j++) {
+        last = to_affine(pts[j]);
+        table[(size_t)(w + j) * n + i] = last;
+      }
+    } else {
+      pre[0] = pts[0].zzz;
+      for (int j = 1; j < cnt; j++) pre[j] = pre[j - 1] * pts[j].zzz;
+      F inv = pre[cnt - 1].inverse();  // 1 / (zzz_0 ... zzz_{cnt-1})
+      for (int j = cnt - 1; j >= 0; j--) {
+        F zi = j ? inv * pre[j - 1] : inv;   // 1 / zzz_j
+        inv = inv * pts[j].zzz;              // 1 / (zzz_0 ... zzz_{j-1})
+        F zzi = (zi * pts[j].zz).sqr();      // (ZZ / ZZZ)^2 = 1 / ZZ   (ZZ^3 = ZZZ^2)
+        Affine<F> a;
+        a.x = pts[j].x * zzi;
+        a.y = pts[j].y * zi;
+        table[(size_t)(w + j) * n + i] = a;
+        if (j == cnt - 1) last = a;
+      }
+    }
+    cur = Xyzz<F>::from_affine(last);  // ZZ = ZZZ = 1 again: the next chunk's first doublings stay cheap
+    w += cnt;
   }
 }
 
