@@ -24,7 +24,12 @@ else:
           8495653923123431417604973247489272438418190587263600148770280649306958101930, 4082367875863433681332203403145435568316851327593401208105741076214120093531]
     gen = B.ints_to_limbs(B.to_mont_ints(g2, Q, 4), 4).reshape(-1)
 pts = ctx.fixed_base_mul(B.CS_BN254, group, gen, rnd(n), montgomery=False)
+import time
+ctx.synchronize()
+_t0 = time.perf_counter()
 bases = ctx.bases_upload(B.CS_BN254, group, pts, wb)
+ctx.synchronize()
+print("bases_upload_ms", round((time.perf_counter() - _t0) * 1e3, 1), "(H2D of n points + per-window table expansion)")
 sc = rnd(n)
 if skew > 0:
     ones = rng.random(n) < skew
