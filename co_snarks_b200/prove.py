@@ -89,11 +89,12 @@ def prove_rep3_from_share_files(args):
     inputs = []
     for i, path in enumerate(args.rep3_shares):
         pub, sh, kind = B.read_rep3_witness(lib, path, cv)
-        if kind != B.CS_REP3:
-            raise SystemExit("%s holds additive shares: replicate them first (cs_rep3_replicate_additive)" % path)
         if pub.shape[0] != pks[i].ni:
             raise SystemExit("%s: %d public inputs, the key expects %d" % (path, pub.shape[0], pks[i].ni))
-        inputs.append((np.ascontiguousarray(pub), np.ascontiguousarray(sh)))
+        inputs.append([np.ascontiguousarray(pub), np.ascontiguousarray(sh), kind])
+    kinds = {x[2] for x in inputs}
+    if len(kinds) != 1:
+        raise SystemExit("the three share files are of different kinds (replicated / additive)")
     nets0 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
     nets1 = [B.Net.peer(ctxs[i], i, 3) for i in range(3)]
     for i in range(3):
@@ -106,7 +107,14 @@ def prove_rep3_from_share_files(args):
 
     def party(i):
         try:
-            res[i] = pks[i].rep3_prove(nets0[i], nets1[i], states[i], inputs[i][0], inputs[i][1])
+            sh = inputs[i][1]
+            if inputs[i][2] != B.CS_REP3:
+                # additive (compressed) shares: one reshare makes them replicated (uncompress_shared_witness,
+                # co-circom/src/lib.rs:64-73): share_i = (mine_i, previous party's_i)
+                out = np.zeros((sh.shape[0], 8), dtype=np.uint64)
+                ctxs[i]._check(lib.cs_rep3_replicate_additive(nets0[i].h, B._ptr(sh), sh.shape[0], B._ptr(out)))
+                sh = out
+            res[i] = pks[i].rep3_prove(nets0[i], nets1[i], states[i], inputs[i][0], sh)
         except Exception as e:  # noqa: BLE001
             errs.append(e)
     th = [threading.Thread(target=party, args=(i,)) for i in range(3)]

@@ -892,6 +892,18 @@ def check_prove_cli_rep3_shares(ctx_lib_path, tmp_path, name="multiplier2"):
     public = [int(x) for x in json.load(open(pub))]
     assert public == [ih(x) for x in g["public"]]
     assert groth16_verify(OG.vk_from_zkey(z), public, read_proof_json(out))
+    # the compressed form: additive shares (variant 2), replicated by one reshare inside the CLI
+    paths2 = []
+    for i in range(3):
+        pth = os.path.join(str(tmp_path), "add_shares.%d" % i)
+        write_rep3_share_file(pth, w[:ni], 2, [ab[0] for ab in wsh[i]], r)
+        paths2.append(pth)
+    out2 = os.path.join(str(tmp_path), "proof3b.json")
+    argv = ["--zkey", zp, "--rep3-shares"] + paths2 + ["--out", out2]
+    if ctx_lib_path:
+        argv += ["--lib", ctx_lib_path]
+    P.main(argv)
+    assert groth16_verify(OG.vk_from_zkey(z), public, read_proof_json(out2))
 
 
 def check_prove_cli_plonk(ctx_lib_path, tmp_path, name="multiplier2"):
