@@ -88,6 +88,22 @@ def test_argument_errors_come_back_as_codes_not_crashes():
         lambda: lib.cs_groth16_pk_from_zkey(null, b"/nonexistent.zkey", 0, C.byref(out), null),
         lambda: lib.cs_msm(null, null, 0, null, 4, 1, null, null),
         lambda: lib.cs_plonk_pk_info(null, null, null, null, null),
+        # round 2: transport, states, in-library parties, VM / Honk / sumcheck entry points
+        lambda: lib.cs_net_send(null, 1, null, 0),
+        lambda: lib.cs_net_sendrecv(null, 1, null, 0, 2, null, 0),
+        lambda: lib.cs_net_peer_create(null, 0, 3, C.byref(out)),
+        lambda: lib.cs_rep3_state_create(null, C.byref(out)),
+        lambda: lib.cs_groth16_rep3_prove(null, null, null, null, null, null, null, null, null, null, null, null),
+        lambda: lib.cs_groth16_shamir_prove(null, null, null, null, 3, 1, null, null, null, null, null, null),
+        lambda: lib.cs_plonk_rep3_prove(null, null, null, null, 0, null, 0, null, null, null),
+        lambda: lib.cs_plonk_rep3_connect_io(null, null, null),
+        lambda: lib.cs_rep3_batch(null, 0, 0, 0, null, null, null, 4),
+        lambda: lib.cs_honk_commit_batch(null, null, 0, null, null, 1, null),
+        lambda: lib.cs_sumcheck_gate_separator(null, 0, null, 3, null),
+        lambda: lib.cs_sumcheck_fold(null, 0, null, null, 1, 0, 4, null),
+        lambda: lib.cs_sumcheck_arith_round(null, 0, 0, 0, null, 4, null, 2, null, null, null),
+        lambda: lib.cs_shamir_state_create(null, 0, 3, 1, 0, C.byref(out)),
+        lambda: lib.cs_rep3_witness_read(b"/nonexistent.shares", 0, null, 0, null, 0, null, null, null),
     ]
     for i, call in enumerate(calls):
         assert call() < 0, "call %d accepted NULL arguments" % i
