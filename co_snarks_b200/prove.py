@@ -79,7 +79,10 @@ def prove_rep3_from_share_files(args):
     (co-circom.rs:1005-1050): each party reads its CompressedRep3SharedWitness / Rep3SharedWitness share file
     (cs_rep3_witness_read), holds its own context, device-resident key and OS-seeded correlated streams, and runs
     Rep3CoGroth16::prove inside the library (cs_groth16_rep3_prove) over in-process mailbox nets; the parties are three
-    host threads sharing the GPU.  Every party must return the same opened proof."""
+    host threads sharing the GPU.  Every party must return the same opened proof.
+    This is a one-operator convenience (and the test of the file path): one process holds all three share files, so there
+    is no privacy between the parties here; separate operators run one party per process over cs_net (bench.py,
+    tests/test_rep3_native.py)."""
     import threading
     ctxs = [B.Context(args.device, lib_path=args.lib) for _ in range(3)]
     lib = ctxs[0].lib
