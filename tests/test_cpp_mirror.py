@@ -113,14 +113,14 @@ def _write_plonk_fixture(tmp_path, name="multiplier2"):
     return zp, fx
 
 
-def _build_and_run_plonk(tmp_path, lib_path):
+def _build_and_run_plonk(tmp_path, lib_path, extra_args=()):
     zp, fx = _write_plonk_fixture(tmp_path)
     exe = str(tmp_path / "test_co_plonk")
     libdir, libname = os.path.dirname(lib_path), os.path.basename(lib_path)
     subprocess.check_call(["g++", "-std=c++17", "-O1", "-pthread", "-I", os.path.join(ROOT, "include"),
                            os.path.join(ROOT, "tests", "cpp", "test_co_plonk.cpp"), "-o", exe,
                            "-L", libdir, "-l:" + libname, "-Wl,-rpath," + libdir])
-    out = subprocess.run([exe, zp, fx], capture_output=True, text=True, timeout=900)
+    out = subprocess.run([exe, zp, fx] + list(extra_args), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "checks passed" in out.stdout
 
@@ -128,7 +128,7 @@ def _build_and_run_plonk(tmp_path, lib_path):
 def test_cpp_plonk_mirror_on_emulated_kernels(tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
     import build_emu
-    _build_and_run_plonk(tmp_path, build_emu.build())
+    _build_and_run_plonk(tmp_path, build_emu.build(), ["library-driver"])  # + Rep3CoPlonk::prove_in_library
 
 
 @pytest.mark.gpu

@@ -105,7 +105,6 @@ def test_zkey_ingest(gpu_ctx, tmp_path):
 def test_prove_cli(gpu_ctx, tmp_path):
     K.check_prove_cli(None, tmp_path, "poseidon")
     K.check_prove_cli_plonk(None, tmp_path, "multiplier2")
-    K.check_prove_cli_rep3_shares(None, tmp_path, "multiplier2")
 
 
 def test_libsnark_reduction(gpu_ctx):
