@@ -114,7 +114,7 @@ CS_GLOBAL void __launch_bounds__(128) k_sc_arith_round(ScArithPolys p, size_t n_
       F mul;
       if (SH) {
         const F wr_b = sc_ext<FrP>(p.w_r, ee, WC, 1, k);
-        mul = wl_a * (wr_a + wr_b) + wl_b * wr_a;  // local_mul_vec without the mask
+        mul = F::dot2(wl_a, wr_a + wr_b, wl_b, wr_a);  // local_mul_vec without the mask, one reduction for both products
       } else {
         mul = wl_a * wr_a;
       }
