@@ -68,7 +68,9 @@ def witness_map_plain(matrices, public_inputs, witness, r, two_adicity):
 
 # ---------------------------------------------------------------- LibSnarkReduction (reduction.rs:241-342)
 ARK_GENERATOR = {21888242871839275222246405745257275088548364400416034343698204186575808495617: 5,
-                 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001: 7}
+                 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001: 7,
+                 # BLS12-377 Fr (ark-bls12-377): the LibSnark fixtures of the reference live on this field
+                 8444461749428370424248824938781546531375899335154063827935233455917409239041: 22}
 
 
 def ark_domain(n_min, r):
@@ -81,7 +83,10 @@ def ark_domain(n_min, r):
 
 def witness_map_libsnark(matrices, public_inputs, witness, r, kind="plain", pid=0, mask=None):
     """LibSnarkReduction::witness_map_from_matrices -> coefficients of H in natural order.
-    kind = "plain" (witness = values) or "rep3" (witness = (a, b) shares, one mask vector)."""
+    kind = "plain" (witness = values) or "rep3" (witness = (a, b) shares, one mask vector).
+    PINNED on the reference's own fixture: with these coefficients and the reference's BLS12-377 Penumbra proving key
+    the assembled proof verifies under its circuit.vk (tests/golden/make_libsnark_bls12_377.py,
+    tests/test_oracle_golden.py::test_libsnark_reduction_pinned_on_the_reference_bls12_377_fixture)."""
     nc, ni = matrices["num_constraints"], matrices["num_instance_variables"]
     n, gen, g = ark_domain(nc + ni, r)
     table = bit_reversed_coset_table(g, n, r)
