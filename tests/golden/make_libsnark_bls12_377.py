@@ -20,8 +20,10 @@ sys.path.insert(0, ROOT)
 from oracle import groth16 as OG
 from oracle import pairing_bls12_377 as P
 
-SRC = "/root/reference/test_vectors/Groth16/bls12_377/penumbra_output"
-OUT = os.path.join(ROOT, "tests", "golden", "libsnark_bls12_377_penumbra_output.json.gz")
+CIRCUIT = sys.argv[1] if len(sys.argv) > 1 else "penumbra_output"   # also: penumbra_spend, penumbra_delegator_vote
+WRITE = CIRCUIT == "penumbra_output"                                # the other two are only verified, not stored
+SRC = "/root/reference/test_vectors/Groth16/bls12_377/" + CIRCUIT
+OUT = os.path.join(ROOT, "tests", "golden", "libsnark_bls12_377_%s.json.gz" % CIRCUIT)
 
 
 def h_digest(h):
@@ -76,6 +78,8 @@ def main():
     ok = P.groth16_verify(vk, inputs, (A, B2, C))
     print("proof verifies under the reference's circuit.vk:", ok)
     assert ok, "the oracle's LibSnark proof does not verify"
+    if not WRITE:
+        return
     enc = lambda x: [str(c) for c in x] if isinstance(x, tuple) and isinstance(x[0], int) else [[str(c) for c in y] for y in x]
     out = {"source": SRC, "r": str(P.R), "matrices": {"a": [[(str(cf), ix) for cf, ix in row] for row in a],
                                                        "b": [[(str(cf), ix) for cf, ix in row] for row in b],
